@@ -1,0 +1,118 @@
+/* rcwa_b200.h -- C ABI of the B200-native RCWA hot path (librcwa_b200.so).
+ *
+ * This is the drop-in boundary.  The reference (kch3782/torcwa) has NO native
+ * boundary: every step below is a chain of ATen calls issued from torcwa/rcwa.py.  Each entry point
+ * names the reference code it replaces (file:line under /root/reference).  INTEGRATION.md shows the
+ * ctypes stub a torcwa maintainer would add.
+ *
+ * Conventions
+ *   - every matrix pointer is a DEVICE pointer to row-major, interleaved (re,im) fp64 ("c128")
+ *     data, 16-byte aligned; batched tensors are [nb, rows, cols] contiguous unless a stride is given;
+ *   - the caller allocates everything (outputs, workspaces, info); the library keeps no state,
+ *     never allocates or frees device memory, never synchronises; every call only enqueues work
+ *     on `stream` (a cudaStream_t passed as void*), so sequences are CUDA-graph capturable
+ *     (rcwa_eig polls a device flag through pinned host memory supplied by the caller -- see there);
+ *   - return value: 0 ok; -k = argument k invalid (LAPACK style); <= -1000 = CUDA runtime error
+ *     (-1000 - cudaError_t);
+ *   - numerical status is reported per batch entry in device int32 info[nb]
+ *     (0 ok; >0 = zero pivot / unconverged eigenvalue index), never by the return value.
+ */
+#ifndef RCWA_B200_H
+#define RCWA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCWA_B200_ABI_VERSION 1
+
+/* grid element types for rcwa_convmat */
+#define RCWA_GRID_F32 0
+#define RCWA_GRID_F64 1
+#define RCWA_GRID_C64 2
+#define RCWA_GRID_C128 3
+/* GEMM operand ops */
+#define RCWA_OP_N 0
+#define RCWA_OP_T 1
+#define RCWA_OP_H 2
+
+int rcwa_b200_abi_version(void);
+
+/* bytes of the grouped-GEMM descriptor scratch every dense routine needs for a batch of nb */
+size_t rcwa_gemm_scratch_bytes(int nb);
+
+/* ---- stage 1: Fourier factorisation --------------------------------------------------------
+ * E[b] (N x N, N=(2ox+1)(2oy+1)) = Toeplitz matrix of the 2-D Fourier coefficients of grid[b]
+ * (nx x ny samples, element type grid_type; grid_stride = elements between consecutive grids,
+ * 0 = one grid shared by the whole batch).  Requires nx >= 4ox+1, ny >= 4oy+1.
+ * Replaces rcwa._material_conv, torcwa/rcwa.py:1183-1204 (fft2 + index gather). */
+size_t rcwa_convmat_workspace_bytes(int nx, int ny, int nb, int ox, int oy);
+int rcwa_convmat(const void* grid, int grid_type, long long grid_stride, int nx, int ny, int nb,
+                 int ox, int oy, void* E, void* ws, void* stream);
+
+/* ---- dense building blocks -----------------------------------------------------------------
+ * C[b] = alpha op(A[b]) op(B[b]) + beta C[b]; strides in elements.
+ * Replaces torch.matmul call sites of the path (rcwa.py:1228,1232,1236,1264,1276-1281,1291-1294). */
+int rcwa_zgemm_batched(int opa, int opb, int M, int N, int K, double alpha_re, double alpha_im,
+                       const void* A, int lda, long long stride_a, const void* B, int ldb, long long stride_b,
+                       double beta_re, double beta_im, void* C, int ldc, long long stride_c,
+                       int nb, void* gemm_scratch, void* stream);
+
+/* In-place LU with column pivoting for right-solves X*A = B (A*Pi = L*U, L lower, U unit upper).
+ * ipiv, perm: int32 [nb,n]; info int32 [nb].
+ * Replaces torch.linalg.inv call sites (rcwa.py:1226,1230,1248,1266-1267,1271,1273,1287-1288). */
+int rcwa_lu_factor(void* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info,
+                   void* gemm_scratch, void* stream);
+/* X[b] (nrows x n) = B[b] * A[b]^-1 given rcwa_lu_factor output; X must not alias B. */
+int rcwa_lu_solve_right(const void* LU, long long lu_stride, int n, int lda, const int* perm,
+                        const void* B, long long b_stride, int ldb, int nrows,
+                        void* X, long long x_stride, int ldx, int nb, void* gemm_scratch, void* stream);
+
+/* ---- stage 1 -> 2: P, Q of the layer eigenproblem -----------------------------------------
+ * eta = E^-1, optional Mc (mu conv. matrix) and nu = Mc^-1 (both NULL => homogeneous mu given per
+ * batch entry in mu_scalar[nb]); kx, ky: [nb,N] normalised wavevectors.  P, Q: [nb,2N,2N].
+ * Replaces the assembly in rcwa._eigen_decomposition, rcwa.py:1224-1232. */
+int rcwa_pq_assemble(const void* eta, const void* E, const void* Mc, const void* nu, const void* mu_scalar,
+                     const void* kx, const void* ky, int nb, int N, void* P, void* Q, void* stream);
+
+/* ---- stage 2: non-Hermitian eigendecomposition --------------------------------------------
+ * A[b] (n x n, destroyed) -> eigenvalues w[b] (n) and right eigenvectors V[b] (n x n, columns,
+ * unit 2-norm, arbitrary order) with A V = V diag(w).  Householder Hessenberg reduction, windowed
+ * multishift QR with Schur-vector accumulation, blocked triangular eigenvector solve,
+ * back-transformation; everything on the device.  host_flag: 64 bytes of PINNED host memory the
+ * routine uses to poll convergence without a device-wide synchronisation (may be NULL: then the
+ * routine runs its full sweep budget).
+ * Replaces torch.linalg.eig in Eig.forward, torcwa/torch_eig.py:11-17 (called at rcwa.py:1236/1238). */
+size_t rcwa_eig_workspace_bytes(int n, int nb);
+int rcwa_eig(void* A, int n, int nb, void* w, void* V, void* ws, size_t ws_bytes, int* info,
+             void* host_flag, void* stream);
+/* kz = sqrt(lambda), negated where Im < 0 (rcwa.py:1240-1241). total = nb*n elements. */
+int rcwa_kz_branch(const void* lam, void* kz, long long total, void* stream);
+
+/* ---- stage 3a: layer S-matrix -------------------------------------------------------------
+ * Inputs: eigenvectors W [nb,n,n], kz [nb,n], Q [nb,n,n], vfinv [nb,4,N] = the four diagonals of
+ * Vf^-1 (free-space E->H matrix, rcwa.py:1143-1147), omega[nb], thickness[nb] (fp64).
+ * Outputs S11 (= S22) and S21 (= S12) of the single layer, [nb,n,n].
+ * Minimal algebra: V = Q W Kz^-1, two LU right-solves; replaces
+ * rcwa._solve_layer_smatrix, rcwa.py:1244-1281 (dense inv of the 4N x 4N coupling matrix). */
+size_t rcwa_layer_smatrix_workspace_bytes(int N, int nb);
+int rcwa_layer_smatrix(const void* W, const void* kz, const void* Q, const void* vfinv,
+                       const double* omega, const double* thickness, int nb, int N,
+                       void* S11, void* S21, void* ws, int* info, void* stream);
+
+/* ---- stage 3b: Redheffer star product -----------------------------------------------------
+ * out = Sm (*) Sn, each S = {S11,S21,S12,S22} of [nb,n,n]; outputs must not alias inputs.
+ * One LU + two right-solves + 8 GEMMs; replaces rcwa._RS_prod, rcwa.py:1283-1294. */
+size_t rcwa_redheffer_workspace_bytes(int n, int nb);
+int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const out[4],
+                   int nb, int n, void* ws, int* info, void* stream);
+
+/* dense [nb,2N,2N] from four diagonals d4 [nb,4,N] (order 11,12,21,22): half-space and
+ * homogeneous-layer blocks (rcwa.py:1157-1181, :1206-1222). */
+int rcwa_blockdiag_dense(const void* d4, int nb, int N, void* D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

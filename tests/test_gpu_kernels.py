@@ -1,0 +1,155 @@
+"""Stage-level parity of the CUDA kernels (through the C ABI) against torch fp64 / the oracle.
+All tests need a GPU:  python -m pytest tests -m gpu"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cases as C  # noqa: E402
+from oracle.rcwa_oracle import OracleSim  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.complex(torch.randn(*shape, generator=g, dtype=torch.float64),
+                         torch.randn(*shape, generator=g, dtype=torch.float64)).to(dev())
+
+
+def rel(a, b):
+    return float(torch.linalg.norm((a - b).reshape(-1)) / torch.linalg.norm(b.reshape(-1)))
+
+
+@pytest.mark.parametrize("opa", ["N", "T", "H"])
+@pytest.mark.parametrize("opb", ["N", "T", "H"])
+@pytest.mark.parametrize("mnk", [(64, 128, 8), (97, 130, 37), (1, 1, 1), (200, 33, 64), (33, 300, 5), (128, 64, 129)])
+def test_zgemm(opa, opb, mnk):
+    from torcwa_b200 import _lib
+    M, N, K = mnk
+    nb = 3
+    A = rnd(nb, *((M, K) if opa == "N" else (K, M)), seed=1)
+    B = rnd(nb, *((K, N) if opb == "N" else (N, K)), seed=2)
+    Cin = rnd(nb, M, N, seed=3)
+    f = {"N": lambda x: x, "T": lambda x: x.transpose(1, 2), "H": lambda x: x.transpose(1, 2).conj()}
+    ref = (0.5 - 0.25j) * (f[opa](A) @ f[opb](B)) + (2.0 + 1.0j) * Cin
+    out = Cin.clone()
+    _lib.zgemm(A, B, opa, opb, alpha=0.5 - 0.25j, beta=2.0 + 1.0j, out=out)
+    assert rel(out, ref) < 1e-14
+    out0 = _lib.zgemm(A, B, opa, opb)
+    assert rel(out0, f[opa](A) @ f[opb](B)) < 1e-14
+
+
+def test_zgemm_large():
+    from torcwa_b200 import _lib
+    A, B = rnd(2, 500, 700, seed=4), rnd(2, 700, 450, seed=5)
+    assert rel(_lib.zgemm(A, B), A @ B) < 1e-14
+
+
+@pytest.mark.parametrize("n", [5, 32, 33, 100, 242, 500])
+def test_lu_right_solve(n):
+    from torcwa_b200 import _lib
+    nb = 3
+    A = rnd(nb, n, n, seed=n) + 0.5 * torch.eye(n, dtype=torch.complex128, device=dev())
+    Bm = rnd(nb, 17, n, seed=n + 1)
+    LU = A.clone()
+    perm, info = _lib.lu_factor_(LU)
+    assert int(info.abs().max()) == 0
+    X = _lib.lu_solve_right(LU, perm, Bm)
+    assert rel(X @ A, Bm) < 1e-11
+    Ai, info = _lib.inverse(A)
+    assert rel(Ai, torch.linalg.inv(A)) < 1e-10
+
+
+def test_lu_singular_reports_info():
+    from torcwa_b200 import _lib
+    A = rnd(2, 40, 40, seed=9)
+    A[1, 7, :] = 0
+    _, info = _lib.lu_factor_(A.clone())
+    assert int(info[0]) == 0 and int(info[1]) > 0
+
+
+@pytest.mark.parametrize("name,gdtype", [("ex1_o3", torch.float64), ("ex1_o3", torch.complex128), ("stack_o4x2", torch.complex64),
+                                         ("stack_o4x2", torch.float32)])
+def test_convmat_vs_oracle(name, gdtype):
+    from torcwa_b200 import _lib
+    case = C.CASES[name]
+    cd = torch.complex128
+    grid = C.build_layers(case, cd)[0][1]
+    if not gdtype.is_complex:
+        grid = grid.real.contiguous()
+    grid = grid.to(gdtype)
+    sim = OracleSim(freq=1 / case["lam"], order=case["order"], L=case["L"], dtype=cd)
+    ref = sim.material_conv(grid.to(torch.complex128) if gdtype.is_complex else grid.to(torch.float64))
+    E = _lib.convmat(grid.to(dev()), case["order"][0], case["order"][1])
+    tol = 1e-13 if gdtype in (torch.float64, torch.complex128) else 1e-13   # inputs are exactly representable
+    assert rel(E[0].cpu(), ref.to(torch.complex128)) < tol
+    # batched with distinct grids
+    g2 = torch.stack([grid, 2 * grid]).to(dev())
+    E2 = _lib.convmat(g2, case["order"][0], case["order"][1])
+    assert rel(E2[1].cpu(), 2 * ref.to(torch.complex128)) < tol
+
+
+def _oracle_layer(name):
+    case = C.CASES[name]
+    sim = C.run_case(lambda **kw: OracleSim(**kw), case, torch.complex128)
+    return case, sim
+
+
+@pytest.mark.parametrize("name", ["ex1_o3", "stack_o3"])
+def test_pq_and_layer_smatrix_vs_oracle(name):
+    """Feed the oracle's eigenpairs to the CUDA layer-S stage: isolates stage 3a from stage 2."""
+    from torcwa_b200 import _lib
+    from torcwa_b200.rcwa import vf_inverse_diagonals
+    case, sim = _oracle_layer(name)
+    d = dev()
+    N = sim.order_N
+    E = sim.eps_conv[0].to(d)[None]
+    eta, info = _lib.inverse(E)
+    kx, ky = sim.Kx_norm_dn.to(d)[None].contiguous(), sim.Ky_norm_dn.to(d)[None].contiguous()
+    mu = torch.ones(1, dtype=torch.complex128, device=d)
+    P, Q = _lib.pq_assemble(eta, E, kx, ky, mu_scalar=mu)
+    assert rel(P[0].cpu(), sim.P[0]) < 1e-12
+    assert rel(Q[0].cpu(), sim.Q[0]) < 1e-12
+    W, kz = sim.E_eigvec[0].to(d)[None].contiguous(), sim.kz_norm[0].to(d)[None].contiguous()
+    vfinv = vf_inverse_diagonals(kx, ky)
+    omega = torch.tensor([float(sim.omega)], dtype=torch.float64, device=d)
+    thick = torch.tensor([float(sim.thickness[0])], dtype=torch.float64, device=d)
+    S11, S21, info = _lib.layer_smatrix(W, kz, Q, vfinv, omega, thick)
+    assert int(info.abs().max()) == 0
+    ref = sim.layer_S[0]
+    assert rel(S11[0].cpu(), ref[0]) < 1e-10 and rel(S21[0].cpu(), ref[1]) < 1e-10
+    assert rel(S11[0].cpu(), ref[3]) < 1e-10 and rel(S21[0].cpu(), ref[2]) < 1e-10   # single-layer symmetry
+
+
+def test_redheffer_vs_oracle():
+    from torcwa_b200 import _lib
+    case, sim = _oracle_layer("stack_o3")
+    d = dev()
+    Sm = [s.to(d)[None].contiguous() for s in sim.layer_S[0]]
+    Sn = [s.to(d)[None].contiguous() for s in sim.layer_S[1]]
+    out, info = _lib.redheffer(Sm, Sn)
+    ref = sim._star(sim.layer_S[0], sim.layer_S[1])
+    for k in range(4):
+        assert rel(out[k][0].cpu(), ref[k]) < 1e-11
+    # batched: two different pairs at once
+    Sm2 = [torch.cat([a, b]) for a, b in zip(Sm, Sn)]
+    Sn2 = [torch.cat([b, a]) for a, b in zip(Sm, Sn)]
+    out2, _ = _lib.redheffer(Sm2, Sn2)
+    ref2 = sim._star(sim.layer_S[1], sim.layer_S[0])
+    for k in range(4):
+        assert rel(out2[k][0].cpu(), ref[k]) < 1e-11
+        assert rel(out2[k][1].cpu(), ref2[k]) < 1e-11
+
+
+def test_blockdiag_dense():
+    from torcwa_b200 import _lib
+    d4 = rnd(2, 4, 9, seed=11)
+    D = _lib.blockdiag_dense(d4)
+    for b in range(2):
+        ref = torch.cat([torch.cat([torch.diag(d4[b, 0]), torch.diag(d4[b, 1])], 1),
+                         torch.cat([torch.diag(d4[b, 2]), torch.diag(d4[b, 3])], 1)], 0)
+        assert torch.equal(D[b], ref)

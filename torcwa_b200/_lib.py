@@ -1,0 +1,247 @@
+"""ctypes binding of librcwa_b200.so (C ABI: include/rcwa_b200.h).
+
+The library is the product: there is no Python/torch fallback.  If it is missing or a call
+fails, this module raises -- it never reroutes work to another implementation.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librcwa_b200.so")
+
+EXPORTS = [
+    "rcwa_b200_abi_version", "rcwa_gemm_scratch_bytes", "rcwa_convmat_workspace_bytes", "rcwa_convmat",
+    "rcwa_zgemm_batched", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
+    "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_kz_branch", "rcwa_layer_smatrix_workspace_bytes",
+    "rcwa_layer_smatrix", "rcwa_redheffer_workspace_bytes", "rcwa_redheffer", "rcwa_blockdiag_dense",
+]
+
+_vp, _i, _ll, _d, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_size_t
+_SIGS = {
+    "rcwa_b200_abi_version": (_i, []),
+    "rcwa_gemm_scratch_bytes": (_sz, [_i]),
+    "rcwa_convmat_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "rcwa_convmat": (_i, [_vp, _i, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "rcwa_zgemm_batched": (_i, [_i, _i, _i, _i, _i, _d, _d, _vp, _i, _ll, _vp, _i, _ll, _d, _d, _vp, _i, _ll, _i, _vp, _vp]),
+    "rcwa_lu_factor": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "rcwa_lu_solve_right": (_i, [_vp, _ll, _i, _i, _vp, _vp, _ll, _i, _i, _vp, _ll, _i, _i, _vp, _vp]),
+    "rcwa_pq_assemble": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "rcwa_eig_workspace_bytes": (_sz, [_i, _i]),
+    "rcwa_eig": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "rcwa_kz_branch": (_i, [_vp, _vp, _ll, _vp]),
+    "rcwa_layer_smatrix_workspace_bytes": (_sz, [_i, _i]),
+    "rcwa_layer_smatrix": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "rcwa_redheffer_workspace_bytes": (_sz, [_i, _i]),
+    "rcwa_redheffer": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "rcwa_blockdiag_dense": (_i, [_vp, _i, _i, _vp, _vp]),
+}
+
+_lib = None
+
+
+class RcwaB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (no CUDA context is created by loading)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "torcwa_b200: %s is missing. Build it with `python -m torcwa_b200.build` "
+                "(needs nvcc, sm_100a). There is no fallback implementation." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.rcwa_b200_abi_version() != 1:
+            raise ImportError("torcwa_b200: ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        if rc <= -1000:
+            raise RcwaB200Error("%s: CUDA error %d (%s)" % (what, -1000 - rc, "see cudaError_t"))
+        raise RcwaB200Error("%s: invalid argument #%d" % (what, -rc))
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _c128(t, name):
+    if not (t.is_cuda and t.dtype == torch.complex128 and t.is_contiguous()):
+        raise TypeError("%s must be a contiguous CUDA complex128 tensor" % name)
+    return t
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+GRID_TYPES = {torch.float32: 0, torch.float64: 1, torch.complex64: 2, torch.complex128: 3}
+
+
+# ------------------------------------------------------------------------------------------ wrappers
+def convmat(grid, ox, oy, nb=None):
+    """grid: [nx,ny] (shared) or [B,nx,ny]; -> E [B,N,N] complex128."""
+    lib = load()
+    if not grid.is_cuda:
+        raise TypeError("grid must be a CUDA tensor")
+    grid = grid.contiguous()
+    if grid.dim() == 2:
+        nbatch, stride = (nb or 1), 0
+    else:
+        nbatch, stride = grid.shape[0], grid.shape[-2] * grid.shape[-1]
+    nx, ny = grid.shape[-2], grid.shape[-1]
+    N = (2 * ox + 1) * (2 * oy + 1)
+    E = torch.empty((nbatch, N, N), dtype=torch.complex128, device=grid.device)
+    ws = _ws(lib.rcwa_convmat_workspace_bytes(nx, ny, nbatch, ox, oy), grid.device)
+    _check(lib.rcwa_convmat(_ptr(grid), GRID_TYPES[grid.dtype], stride, nx, ny, nbatch, ox, oy, _ptr(E), _ptr(ws), _stream()),
+           "rcwa_convmat")
+    return E
+
+
+_OPS = {"N": 0, "T": 1, "H": 2}
+
+
+def zgemm(A, B, opa="N", opb="N", alpha=1.0, beta=0.0, out=None):
+    """Batched C = alpha op(A) op(B) + beta C on [nb,*,*] complex128 tensors."""
+    lib = load()
+    _c128(A, "A"); _c128(B, "B")
+    nb = A.shape[0]
+    M = A.shape[1] if opa == "N" else A.shape[2]
+    K = A.shape[2] if opa == "N" else A.shape[1]
+    N = B.shape[2] if opb == "N" else B.shape[1]
+    if out is None:
+        out = torch.empty((nb, M, N), dtype=torch.complex128, device=A.device)
+        beta = 0.0
+    _c128(out, "out")
+    gs = _ws(lib.rcwa_gemm_scratch_bytes(nb), A.device)
+    al, be = complex(alpha), complex(beta)
+    _check(lib.rcwa_zgemm_batched(_OPS[opa], _OPS[opb], M, N, K, al.real, al.imag,
+                                  _ptr(A), A.shape[2], A.shape[1] * A.shape[2], _ptr(B), B.shape[2], B.shape[1] * B.shape[2],
+                                  be.real, be.imag, _ptr(out), N, M * N, nb, _ptr(gs), _stream()), "rcwa_zgemm_batched")
+    return out
+
+
+def lu_factor_(A):
+    """In place on A [nb,n,n]; returns (perm, info)."""
+    lib = load()
+    _c128(A, "A")
+    nb, n = A.shape[0], A.shape[1]
+    ipiv = torch.empty((nb, n), dtype=torch.int32, device=A.device)
+    perm = torch.empty((nb, n), dtype=torch.int32, device=A.device)
+    info = torch.zeros((nb,), dtype=torch.int32, device=A.device)
+    gs = _ws(lib.rcwa_gemm_scratch_bytes(nb), A.device)
+    _check(lib.rcwa_lu_factor(_ptr(A), n * n, n, n, nb, _ptr(ipiv), _ptr(perm), _ptr(info), _ptr(gs), _stream()), "rcwa_lu_factor")
+    return perm, info
+
+
+def lu_solve_right(LU, perm, Bm):
+    """X = Bm @ inv(A) for factored LU [nb,n,n], Bm [nb,r,n]."""
+    lib = load()
+    _c128(LU, "LU"); _c128(Bm, "B")
+    nb, n = LU.shape[0], LU.shape[1]
+    r = Bm.shape[1]
+    X = torch.empty_like(Bm)
+    gs = _ws(lib.rcwa_gemm_scratch_bytes(nb), LU.device)
+    _check(lib.rcwa_lu_solve_right(_ptr(LU), n * n, n, n, _ptr(perm), _ptr(Bm), r * n, n, r, _ptr(X), r * n, n, nb, _ptr(gs), _stream()),
+           "rcwa_lu_solve_right")
+    return X
+
+
+def inverse(A):
+    """inv(A) for [nb,n,n] via X*A = I; returns (inv, info). A is preserved."""
+    LU = A.clone()
+    perm, info = lu_factor_(LU)
+    eye = torch.eye(A.shape[1], dtype=A.dtype, device=A.device).expand(A.shape[0], -1, -1).contiguous()
+    return lu_solve_right(LU, perm, eye), info
+
+
+def pq_assemble(eta, E, kx, ky, mu_scalar=None, Mc=None, nu=None):
+    lib = load()
+    nb, N = E.shape[0], E.shape[1]
+    P = torch.empty((nb, 2 * N, 2 * N), dtype=torch.complex128, device=E.device)
+    Q = torch.empty_like(P)
+    _check(lib.rcwa_pq_assemble(_ptr(_c128(eta, "eta")), _ptr(_c128(E, "E")), _ptr(Mc), _ptr(nu), _ptr(mu_scalar),
+                                _ptr(_c128(kx, "kx")), _ptr(_c128(ky, "ky")), nb, N, _ptr(P), _ptr(Q), _stream()), "rcwa_pq_assemble")
+    return P, Q
+
+
+_host_flag = None
+
+
+def eig(A):
+    """A [nb,n,n] (destroyed) -> (w [nb,n], V [nb,n,n], info [nb])."""
+    global _host_flag
+    lib = load()
+    _c128(A, "A")
+    nb, n = A.shape[0], A.shape[1]
+    w = torch.empty((nb, n), dtype=torch.complex128, device=A.device)
+    V = torch.empty((nb, n, n), dtype=torch.complex128, device=A.device)
+    info = torch.zeros((nb,), dtype=torch.int32, device=A.device)
+    nbytes = lib.rcwa_eig_workspace_bytes(n, nb)
+    ws = _ws(nbytes, A.device)
+    if _host_flag is None:
+        _host_flag = torch.zeros(16, dtype=torch.int32).pin_memory()
+    _check(lib.rcwa_eig(_ptr(A), n, nb, _ptr(w), _ptr(V), _ptr(ws), nbytes, _ptr(info),
+                        ctypes.c_void_p(_host_flag.data_ptr()), _stream()), "rcwa_eig")
+    return w, V, info
+
+
+def kz_branch(lam):
+    lib = load()
+    kz = torch.empty_like(lam)
+    _check(lib.rcwa_kz_branch(_ptr(_c128(lam, "lam")), _ptr(kz), lam.numel(), _stream()), "rcwa_kz_branch")
+    return kz
+
+
+def layer_smatrix(W, kz, Q, vfinv, omega, thickness):
+    """-> (S11, S21, info) for the single layer (S22 = S11, S12 = S21)."""
+    lib = load()
+    nb, n = W.shape[0], W.shape[1]
+    N = n // 2
+    S11 = torch.empty_like(W)
+    S21 = torch.empty_like(W)
+    info = torch.zeros((nb,), dtype=torch.int32, device=W.device)
+    ws = _ws(lib.rcwa_layer_smatrix_workspace_bytes(N, nb), W.device)
+    omega = omega.to(torch.float64).contiguous()
+    thickness = thickness.to(torch.float64).contiguous()
+    _check(lib.rcwa_layer_smatrix(_ptr(_c128(W, "W")), _ptr(_c128(kz, "kz")), _ptr(_c128(Q, "Q")), _ptr(_c128(vfinv, "vfinv")),
+                                  _ptr(omega), _ptr(thickness), nb, N, _ptr(S11), _ptr(S21), _ptr(ws), _ptr(info), _stream()),
+           "rcwa_layer_smatrix")
+    return S11, S21, info
+
+
+def redheffer(Sm, Sn):
+    """Star product of two S-matrices given as lists [S11,S21,S12,S22] of [nb,n,n]; -> (list, info)."""
+    lib = load()
+    nb, n = Sm[0].shape[0], Sm[0].shape[1]
+    out = [torch.empty_like(Sm[0]) for _ in range(4)]
+    info = torch.zeros((nb,), dtype=torch.int32, device=Sm[0].device)
+    ws = _ws(lib.rcwa_redheffer_workspace_bytes(n, nb), Sm[0].device)
+    arr = ctypes.c_void_p * 4
+    a_m = arr(*[t.data_ptr() for t in (_c128(x, "Sm") for x in Sm)])
+    a_n = arr(*[t.data_ptr() for t in (_c128(x, "Sn") for x in Sn)])
+    a_o = arr(*[t.data_ptr() for t in out])
+    _check(lib.rcwa_redheffer(a_m, a_n, a_o, nb, n, _ptr(ws), _ptr(info), _stream()), "rcwa_redheffer")
+    return out, info
+
+
+def blockdiag_dense(d4):
+    """d4 [nb,4,N] -> dense [nb,2N,2N]."""
+    lib = load()
+    nb, N = d4.shape[0], d4.shape[2]
+    D = torch.empty((nb, 2 * N, 2 * N), dtype=torch.complex128, device=d4.device)
+    _check(lib.rcwa_blockdiag_dense(_ptr(_c128(d4, "d4")), nb, N, _ptr(D), _stream()), "rcwa_blockdiag_dense")
+    return D

@@ -1,0 +1,235 @@
+// extern "C" boundary of librcwa_b200.so -- see include/rcwa_b200.h for the contract.
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/rcwa_b200.h"
+
+using namespace rcwa;
+
+namespace {
+inline int cu(cudaError_t e) { return e == cudaSuccess ? 0 : RCWA_ERR_CUDA - (int)e; }
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+#define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return cu(_e); } while (0)
+}  // namespace
+
+extern "C" {
+
+int rcwa_b200_abi_version(void) { return RCWA_B200_ABI_VERSION; }
+
+size_t rcwa_gemm_scratch_bytes(int nb) { return align256(sizeof(ZGemmProblem) * (size_t)(nb > 0 ? nb : 1) * 4); }
+
+size_t rcwa_convmat_workspace_bytes(int nx, int ny, int nb, int ox, int oy) {
+    return align256(convmat_workspace_elems(nx, ny, nb, ox, oy) * sizeof(cplx));
+}
+
+int rcwa_convmat(const void* grid, int grid_type, long long grid_stride, int nx, int ny, int nb, int ox, int oy,
+                 void* E, void* ws, void* stream) {
+    if (!grid) return -1;
+    if (grid_type < 0 || grid_type > 3) return -2;
+    if (nx < 4 * ox + 1) return -4;
+    if (ny < 4 * oy + 1) return -5;
+    if (nb <= 0) return -6;
+    if (ox < 0) return -7;
+    if (oy < 0) return -8;
+    if (!E) return -9;
+    if (!ws) return -10;
+    return cu(convmat(grid, grid_type, grid_stride, nx, ny, nb, ox, oy, (cplx*)E, (cplx*)ws, S(stream)));
+}
+
+int rcwa_zgemm_batched(int opa, int opb, int M, int N, int K, double alpha_re, double alpha_im,
+                       const void* A, int lda, long long sa, const void* B, int ldb, long long sb,
+                       double beta_re, double beta_im, void* Cm, int ldc, long long sc, int nb, void* gs, void* stream) {
+    if (opa < 0 || opa > 2) return -1;
+    if (opb < 0 || opb > 2) return -2;
+    if (M < 0) return -3;
+    if (N < 0) return -4;
+    if (K < 0) return -5;
+    if (!A) return -8;
+    if (!B) return -11;
+    if (!Cm) return -16;
+    if (nb <= 0) return -19;
+    if (!gs) return -20;
+    return cu(zgemm_strided(opa, opb, M, N, K, C(alpha_re, alpha_im), (const cplx*)A, lda, sa, (const cplx*)B, ldb, sb,
+                            C(beta_re, beta_im), (cplx*)Cm, ldc, sc, nb, (ZGemmProblem*)gs, S(stream)));
+}
+
+int rcwa_lu_factor(void* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info, void* gs, void* stream) {
+    if (!A) return -1;
+    if (n <= 0) return -3;
+    if (lda < n) return -4;
+    if (nb <= 0) return -5;
+    if (!ipiv) return -6;
+    if (!perm) return -7;
+    if (!info) return -8;
+    if (!gs) return -9;
+    return cu(lu_factor((cplx*)A, stride, n, lda, nb, ipiv, perm, info, (ZGemmProblem*)gs, S(stream)));
+}
+
+int rcwa_lu_solve_right(const void* LU, long long lus, int n, int lda, const int* perm, const void* B, long long bs, int ldb,
+                        int nrows, void* X, long long xs, int ldx, int nb, void* gs, void* stream) {
+    if (!LU) return -1;
+    if (n <= 0) return -3;
+    if (!perm) return -5;
+    if (!B) return -6;
+    if (nrows <= 0) return -9;
+    if (!X || X == B) return -10;
+    if (nb <= 0) return -13;
+    if (!gs) return -14;
+    return cu(lu_solve_right((const cplx*)LU, lus, n, lda, perm, (const cplx*)B, bs, ldb, nrows, (cplx*)X, xs, ldx, nb,
+                             (ZGemmProblem*)gs, S(stream)));
+}
+
+int rcwa_pq_assemble(const void* eta, const void* E, const void* Mc, const void* nu, const void* mu_scalar,
+                     const void* kx, const void* ky, int nb, int N, void* P, void* Q, void* stream) {
+    if (!eta) return -1;
+    if (!E) return -2;
+    if ((Mc == nullptr) != (nu == nullptr)) return -3;
+    if (!Mc && !mu_scalar) return -5;
+    if (!kx) return -6;
+    if (!ky) return -7;
+    if (nb <= 0) return -8;
+    if (N <= 0) return -9;
+    if (!P) return -10;
+    if (!Q) return -11;
+    return cu(pq_assemble((const cplx*)eta, (const cplx*)E, (const cplx*)Mc, (const cplx*)nu, (const cplx*)mu_scalar,
+                          (const cplx*)kx, (const cplx*)ky, nb, N, (cplx*)P, (cplx*)Q, S(stream)));
+}
+
+size_t rcwa_eig_workspace_bytes(int n, int nb) { return eig_workspace_bytes(n, nb); }
+
+int rcwa_eig(void* A, int n, int nb, void* w, void* V, void* ws, size_t ws_bytes, int* info, void* host_flag, void* stream) {
+    if (!A) return -1;
+    if (n <= 0) return -2;
+    if (nb <= 0) return -3;
+    if (!w) return -4;
+    if (!V) return -5;
+    if (!ws || ws_bytes < eig_workspace_bytes(n, nb)) return -6;
+    if (!info) return -8;
+    return cu(eig((cplx*)A, n, nb, (cplx*)w, (cplx*)V, (char*)ws, ws_bytes, info, (volatile int*)host_flag, S(stream)));
+}
+
+int rcwa_kz_branch(const void* lam, void* kz, long long total, void* stream) {
+    if (!lam) return -1;
+    if (!kz) return -2;
+    if (total <= 0) return -3;
+    return cu(kz_branch((const cplx*)lam, (cplx*)kz, (size_t)total, S(stream)));
+}
+
+// workspace layout helpers ---------------------------------------------------------------------
+size_t rcwa_layer_smatrix_workspace_bytes(int N, int nb) {
+    const size_t n = 2 * (size_t)N, mat = align256(n * n * nb * sizeof(cplx));
+    return 5 * mat + 2 * align256(n * nb * sizeof(int)) + rcwa_gemm_scratch_bytes(nb);
+}
+
+int rcwa_layer_smatrix(const void* W, const void* kz, const void* Q, const void* vfinv, const double* omega,
+                       const double* thickness, int nb, int N, void* S11, void* S21, void* ws, int* info, void* stream) {
+    if (!W) return -1;
+    if (!kz) return -2;
+    if (!Q) return -3;
+    if (!vfinv) return -4;
+    if (!omega) return -5;
+    if (!thickness) return -6;
+    if (nb <= 0) return -7;
+    if (N <= 0) return -8;
+    if (!S11) return -9;
+    if (!S21) return -10;
+    if (!ws) return -11;
+    if (!info) return -12;
+    cudaStream_t st = S(stream);
+    const int n = 2 * N;
+    const long long ms = (long long)n * n;
+    const size_t mat = align256((size_t)ms * nb * sizeof(cplx));
+    char* p = (char*)ws;
+    cplx* b0 = (cplx*)p; p += mat;
+    cplx* b1 = (cplx*)p; p += mat;
+    cplx* b2 = (cplx*)p; p += mat;
+    cplx* b3 = (cplx*)p; p += mat;
+    cplx* b4 = (cplx*)p; p += mat;
+    int* ipiv = (int*)p; p += align256((size_t)n * nb * sizeof(int));
+    int* perm = (int*)p; p += align256((size_t)n * nb * sizeof(int));
+    ZGemmProblem* gs = (ZGemmProblem*)p;
+    // QW = Q * W
+    CK(zgemm_strided(OP_N, OP_N, n, n, n, C(1, 0), (const cplx*)Q, n, ms, (const cplx*)W, n, ms, C(0, 0), b0, n, ms, nb, gs, st));
+    // M+ (b1), M- (b2), R+ (b3), R- (b4)
+    CK(layer_form((const cplx*)W, b0, (const cplx*)kz, (const cplx*)vfinv, omega, thickness, nb, N, b1, b2, b3, b4, st));
+    // T+ = R+ M+^-1  -> b0
+    CK(lu_factor(b1, ms, n, n, nb, ipiv, perm, info, gs, st));
+    CK(lu_solve_right(b1, ms, n, n, perm, b3, ms, n, n, b0, ms, n, nb, gs, st));
+    // T- = R- M-^-1  -> b3   (info keeps the first failure: the second factorisation does not clear it)
+    CK(lu_factor(b2, ms, n, n, nb, ipiv, perm, info, gs, st, false));
+    CK(lu_solve_right(b2, ms, n, n, perm, b4, ms, n, n, b3, ms, n, nb, gs, st));
+    CK(layer_finish(b0, b3, nb, n, (cplx*)S11, (cplx*)S21, st));
+    return 0;
+}
+
+size_t rcwa_redheffer_workspace_bytes(int n, int nb) {
+    const size_t mat = align256((size_t)n * n * nb * sizeof(cplx));
+    return 5 * mat + 2 * align256((size_t)n * nb * sizeof(int)) + rcwa_gemm_scratch_bytes(nb);
+}
+
+int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const out[4], int nb, int n, void* ws, int* info, void* stream) {
+    if (!Sm) return -1;
+    if (!Sn) return -2;
+    if (!out) return -3;
+    for (int k = 0; k < 4; ++k) {
+        if (!Sm[k]) return -1;
+        if (!Sn[k]) return -2;
+        if (!out[k]) return -3;
+    }
+    if (nb <= 0) return -4;
+    if (n <= 0) return -5;
+    if (!ws) return -6;
+    if (!info) return -7;
+    cudaStream_t st = S(stream);
+    const long long ms = (long long)n * n;
+    const size_t mat = align256((size_t)ms * nb * sizeof(cplx));
+    char* p = (char*)ws;
+    cplx* D = (cplx*)p; p += mat;
+    cplx* Y1 = (cplx*)p; p += mat;
+    cplx* Y2 = (cplx*)p; p += mat;
+    cplx* G = (cplx*)p; p += mat;
+    cplx* T = (cplx*)p; p += mat;
+    int* ipiv = (int*)p; p += align256((size_t)n * nb * sizeof(int));
+    int* perm = (int*)p; p += align256((size_t)n * nb * sizeof(int));
+    ZGemmProblem* gs = (ZGemmProblem*)p;
+    const cplx *Sm11 = (const cplx*)Sm[0], *Sm21 = (const cplx*)Sm[1], *Sm12 = (const cplx*)Sm[2], *Sm22 = (const cplx*)Sm[3];
+    const cplx *Sn11 = (const cplx*)Sn[0], *Sn21 = (const cplx*)Sn[1], *Sn12 = (const cplx*)Sn[2], *Sn22 = (const cplx*)Sn[3];
+    cplx *O11 = (cplx*)out[0], *O21 = (cplx*)out[1], *O12 = (cplx*)out[2], *O22 = (cplx*)out[3];
+    const cplx one = C(1, 0), zero = C(0, 0), mone = C(-1, 0);
+    const size_t bytes = (size_t)ms * nb * sizeof(cplx);
+#define GEMM(a, b, beta, c) CK(zgemm_strided(OP_N, OP_N, n, n, n, one, a, n, ms, b, n, ms, beta, c, n, ms, nb, gs, st))
+    // D = I - Sm12 Sn21
+    CK(set_identity(D, n, n, ms, nb, st));
+    CK(zgemm_strided(OP_N, OP_N, n, n, n, mone, Sm12, n, ms, Sn21, n, ms, one, D, n, ms, nb, gs, st));
+    CK(lu_factor(D, ms, n, n, nb, ipiv, perm, info, gs, st));
+    // Y1 = Sn11 D^-1 ; Y2 = Sn21 D^-1
+    CK(lu_solve_right(D, ms, n, n, perm, Sn11, ms, n, n, Y1, ms, n, nb, gs, st));
+    CK(lu_solve_right(D, ms, n, n, perm, Sn21, ms, n, n, Y2, ms, n, nb, gs, st));
+    // G = Sm12 Sn22
+    GEMM(Sm12, Sn22, zero, G);
+    // S11 = Y1 Sm11
+    GEMM(Y1, Sm11, zero, O11);
+    // S12 = Sn12 + Y1 G
+    CK(cudaMemcpyAsync(O12, Sn12, bytes, cudaMemcpyDeviceToDevice, st));
+    GEMM(Y1, G, one, O12);
+    // S21 = Sm21 + Sm22 (Y2 Sm11)
+    GEMM(Y2, Sm11, zero, T);
+    CK(cudaMemcpyAsync(O21, Sm21, bytes, cudaMemcpyDeviceToDevice, st));
+    GEMM(Sm22, T, one, O21);
+    // S22 = Sm22 (Sn22 + Y2 G)
+    CK(cudaMemcpyAsync(D, Sn22, bytes, cudaMemcpyDeviceToDevice, st));
+    GEMM(Y2, G, one, D);
+    GEMM(Sm22, D, zero, O22);
+#undef GEMM
+    return 0;
+}
+
+int rcwa_blockdiag_dense(const void* d4, int nb, int N, void* D, void* stream) {
+    if (!d4) return -1;
+    if (nb <= 0) return -2;
+    if (N <= 0) return -3;
+    if (!D) return -4;
+    return cu(blockdiag_dense((const cplx*)d4, nb, N, (cplx*)D, S(stream)));
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+// Elementwise assembly kernels around the dense stages (all HBM-bound, O(n^2) per design point).
+//
+//  * pq_assemble      : P, Q of the layer eigenproblem from the convolution matrices
+//                       (reference: rcwa._eigen_decomposition, torcwa/rcwa.py:1224-1232).  The
+//                       reference multiplies by dense diag(Kx), diag(Ky); those are row/column
+//                       scalings, done here in one pass.
+//  * kz_branch        : kz = sqrt(lambda), negated where Im < 0 (rcwa.py:1240-1241).
+//  * layer_form       : operands of the two right-solves of the minimal layer S-matrix
+//                       (reference: rcwa._solve_layer_smatrix, rcwa.py:1244-1281).
+//  * layer_finish     : S11 = T+ + T-,  S21 = T+ - T- - I.
+//  * blockdiag_dense  : scatter four diagonals into a dense 2N x 2N matrix (half-space and
+//                       homogeneous-layer S blocks, rcwa.py:1157-1181 / :1206-1222).
+//  * small utilities  : identity, axpby.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+// grid (ceil(N/256), N, B)
+__global__ void pq_assemble_kernel(const cplx* __restrict__ eta, const cplx* __restrict__ E,
+                                   const cplx* __restrict__ Mc, const cplx* __restrict__ nu,
+                                   const cplx* __restrict__ mu_s,   // [B] scalar mu when Mc == nullptr
+                                   const cplx* __restrict__ kx, const cplx* __restrict__ ky,   // [B,N]
+                                   int N, cplx* __restrict__ P, cplx* __restrict__ Q) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+    if (j >= N) return;
+    const int n = 2 * N;
+    const size_t e = ((size_t)b * N + i) * N + j;
+    const cplx kxi = kx[(size_t)b * N + i], kyi = ky[(size_t)b * N + i];
+    const cplx kxj = kx[(size_t)b * N + j], kyj = ky[(size_t)b * N + j];
+    const cplx et = eta[e], ep = E[e];
+    cplx m, v;
+    if (Mc) { m = Mc[e]; v = nu[e]; }
+    else { cplx mu = mu_s[b]; m = (i == j) ? mu : C(0, 0); v = (i == j) ? cinv(mu) : C(0, 0); }
+    const cplx xe = cmul(kxi, et), ye = cmul(kyi, et), xv = cmul(kxi, v), yv = cmul(kyi, v);
+    cplx* p = P + (size_t)b * n * n;
+    cplx* q = Q + (size_t)b * n * n;
+    const size_t r0 = (size_t)i * n + j, r1 = (size_t)(i + N) * n + j;
+    p[r0] = cmul(xe, kyj);                    // Kx eta Ky
+    p[r0 + N] = csub(m, cmul(xe, kxj));       // M - Kx eta Kx
+    p[r1] = csub(cmul(ye, kyj), m);           // Ky eta Ky - M
+    p[r1 + N] = cneg(cmul(ye, kxj));          // -Ky eta Kx
+    q[r0] = cneg(cmul(xv, kyj));              // -Kx nu Ky
+    q[r0 + N] = csub(cmul(xv, kxj), ep);      // Kx nu Kx - E
+    q[r1] = csub(ep, cmul(yv, kyj));          // E - Ky nu Ky
+    q[r1 + N] = cmul(yv, kxj);                // Ky nu Kx
+}
+
+__global__ void kz_branch_kernel(const cplx* __restrict__ lam, cplx* __restrict__ kz, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    cplx r = csqrt_(lam[i]);
+    if (r.y < 0.0) r = cneg(r);
+    kz[i] = r;
+}
+
+// grid (ceil(n/256), N, B); thread handles column j of rows i and i+N
+__global__ void layer_form_kernel(const cplx* __restrict__ W, const cplx* __restrict__ QW, const cplx* __restrict__ kz,
+                                  const cplx* __restrict__ vfinv,          // [B,4,N]: Vf^-1 diagonals (11,12,21,22)
+                                  const double* __restrict__ omega, const double* __restrict__ thick,   // [B]
+                                  int N, cplx* __restrict__ Mp, cplx* __restrict__ Mm, cplx* __restrict__ Rp, cplx* __restrict__ Rm) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+    const int n = 2 * N;
+    if (j >= n) return;
+    const cplx kzj = kz[(size_t)b * n + j];
+    // X_j = exp(i * omega * kz_j * d)
+    const double od = omega[b] * thick[b];
+    const double mag = exp(-od * kzj.y);
+    double s, c;
+    sincos(od * kzj.x, &s, &c);
+    const cplx X = C(mag * c, mag * s);
+    const cplx onep = C(1.0 + X.x, X.y), onem = C(1.0 - X.x, -X.y);
+    const cplx ikz = cinv(kzj);
+    const size_t base = (size_t)b * n * n;
+    const size_t e0 = base + (size_t)i * n + j, e1 = base + (size_t)(i + N) * n + j;
+    const cplx w0 = W[e0], w1 = W[e1];
+    const cplx v0 = cmul(QW[e0], ikz), v1 = cmul(QW[e1], ikz);      // V = Q W Kz^-1
+    const cplx* vi = vfinv + (size_t)b * 4 * N;
+    const cplx b0 = cadd(cmul(vi[i], v0), cmul(vi[N + i], v1));      // B = Vf^-1 V (per-order 2x2)
+    const cplx b1 = cadd(cmul(vi[2 * N + i], v0), cmul(vi[3 * N + i], v1));
+    const cplx rp0 = cmul(w0, onep), rp1 = cmul(w1, onep);
+    const cplx wm0 = cmul(w0, onem), wm1 = cmul(w1, onem);
+    Rp[e0] = rp0; Rp[e1] = rp1;
+    Rm[e0] = cneg(wm0); Rm[e1] = cneg(wm1);
+    Mp[e0] = cadd(rp0, cmul(b0, onem)); Mp[e1] = cadd(rp1, cmul(b1, onem));
+    Mm[e0] = cadd(wm0, cmul(b0, onep)); Mm[e1] = cadd(wm1, cmul(b1, onep));
+}
+
+// grid (ceil(n/256), n, B)
+__global__ void layer_finish_kernel(const cplx* __restrict__ Tp, const cplx* __restrict__ Tm, int n,
+                                    cplx* __restrict__ S11, cplx* __restrict__ S21) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+    if (j >= n) return;
+    const size_t e = ((size_t)b * n + i) * n + j;
+    const cplx a = Tp[e], c = Tm[e];
+    S11[e] = cadd(a, c);
+    cplx d = csub(a, c);
+    if (i == j) d.x -= 1.0;
+    S21[e] = d;
+}
+
+// grid (ceil(n/256), n, B): D[b] = [[diag d0, diag d1],[diag d2, diag d3]]
+__global__ void blockdiag_dense_kernel(const cplx* __restrict__ d4, int N, cplx* __restrict__ D) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+    const int n = 2 * N;
+    if (j >= n) return;
+    cplx v = C(0, 0);
+    const int ii = i % N, jj = j % N;
+    if (ii == jj) v = d4[((size_t)b * 4 + (i / N) * 2 + (j / N)) * N + ii];
+    D[((size_t)b * n + i) * n + j] = v;
+}
+
+__global__ void identity_kernel(cplx* __restrict__ A, int n, int lda, long long stride) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+    if (j >= n) return;
+    A[(size_t)b * stride + (size_t)i * lda + j] = C(i == j ? 1.0 : 0.0, 0.0);
+}
+
+// Y = alpha * X + beta * Y (flat)
+__global__ void axpby_kernel(cplx alpha, const cplx* __restrict__ X, cplx beta, cplx* __restrict__ Y, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    Y[i] = cadd(cmul(alpha, X[i]), cmul(beta, Y[i]));
+}
+
+}  // namespace
+
+namespace rcwa {
+
+cudaError_t pq_assemble(const cplx* eta, const cplx* E, const cplx* Mc, const cplx* nu, const cplx* mu_s,
+                        const cplx* kx, const cplx* ky, int nb, int N, cplx* P, cplx* Q, cudaStream_t st) {
+    pq_assemble_kernel<<<dim3((N + 255) / 256, N, nb), 256, 0, st>>>(eta, E, Mc, nu, mu_s, kx, ky, N, P, Q);
+    return cudaGetLastError();
+}
+cudaError_t kz_branch(const cplx* lam, cplx* kz, size_t total, cudaStream_t st) {
+    kz_branch_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lam, kz, total);
+    return cudaGetLastError();
+}
+cudaError_t layer_form(const cplx* W, const cplx* QW, const cplx* kz, const cplx* vfinv, const double* omega,
+                       const double* thick, int nb, int N, cplx* Mp, cplx* Mm, cplx* Rp, cplx* Rm, cudaStream_t st) {
+    layer_form_kernel<<<dim3((2 * N + 255) / 256, N, nb), 256, 0, st>>>(W, QW, kz, vfinv, omega, thick, N, Mp, Mm, Rp, Rm);
+    return cudaGetLastError();
+}
+cudaError_t layer_finish(const cplx* Tp, const cplx* Tm, int nb, int n, cplx* S11, cplx* S21, cudaStream_t st) {
+    layer_finish_kernel<<<dim3((n + 255) / 256, n, nb), 256, 0, st>>>(Tp, Tm, n, S11, S21);
+    return cudaGetLastError();
+}
+cudaError_t blockdiag_dense(const cplx* d4, int nb, int N, cplx* D, cudaStream_t st) {
+    blockdiag_dense_kernel<<<dim3((2 * N + 255) / 256, 2 * N, nb), 256, 0, st>>>(d4, N, D);
+    return cudaGetLastError();
+}
+cudaError_t set_identity(cplx* A, int n, int lda, long long stride, int nb, cudaStream_t st) {
+    identity_kernel<<<dim3((n + 255) / 256, n, nb), 256, 0, st>>>(A, n, lda, stride);
+    return cudaGetLastError();
+}
+cudaError_t axpby(cplx alpha, const cplx* X, cplx beta, cplx* Y, size_t total, cudaStream_t st) {
+    axpby_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(alpha, X, beta, Y, total);
+    return cudaGetLastError();
+}
+
+}  // namespace rcwa

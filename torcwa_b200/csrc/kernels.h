@@ -1,0 +1,49 @@
+// Internal C++ interface between the .cu translation units (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+#define GEMM_TILE_64x128 0
+#define GEMM_TILE_128x64 1
+#define OP_N 0
+#define OP_T 1
+#define OP_H 2
+
+namespace rcwa {
+
+// ---- zgemm.cu
+int gemm_tiles(int tile_cfg, int M, int N);
+cudaError_t zgemm_grouped(int tile_cfg, int opa, int opb, const ZGemmProblem* probs, int nprob, int max_tiles,
+                          cplx alpha, cplx beta, cudaStream_t st);
+// `scratch`: device array of >= batch ZGemmProblem
+cudaError_t zgemm_strided(int opa, int opb, int M, int N, int K, cplx alpha, const cplx* A, int lda, long long sa,
+                          const cplx* B, int ldb, long long sb, cplx beta, cplx* C, int ldc, long long sc,
+                          int batch, ZGemmProblem* scratch, cudaStream_t st);
+
+
+// ---- convmat.cu
+size_t convmat_workspace_elems(int nx, int ny, int nb, int ox, int oy);
+cudaError_t convmat(const void* grid, int grid_type, long long grid_stride, int nx, int ny, int nb, int ox, int oy,
+                    cplx* E, cplx* ws, cudaStream_t st);
+
+// ---- assemble.cu
+cudaError_t pq_assemble(const cplx* eta, const cplx* E, const cplx* Mc, const cplx* nu, const cplx* mu_s,
+                        const cplx* kx, const cplx* ky, int nb, int N, cplx* P, cplx* Q, cudaStream_t st);
+cudaError_t kz_branch(const cplx* lam, cplx* kz, size_t total, cudaStream_t st);
+cudaError_t layer_form(const cplx* W, const cplx* QW, const cplx* kz, const cplx* vfinv, const double* omega,
+                       const double* thick, int nb, int N, cplx* Mp, cplx* Mm, cplx* Rp, cplx* Rm, cudaStream_t st);
+cudaError_t layer_finish(const cplx* Tp, const cplx* Tm, int nb, int n, cplx* S11, cplx* S21, cudaStream_t st);
+cudaError_t blockdiag_dense(const cplx* d4, int nb, int N, cplx* D, cudaStream_t st);
+cudaError_t set_identity(cplx* A, int n, int lda, long long stride, int nb, cudaStream_t st);
+cudaError_t axpby(cplx alpha, const cplx* X, cplx beta, cplx* Y, size_t total, cudaStream_t st);
+
+// ---- lu.cu
+cudaError_t lu_factor(cplx* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info,
+                      ZGemmProblem* gscratch, cudaStream_t st, bool clear_info = true);
+cudaError_t lu_solve_right(const cplx* LU, long long lustride, int n, int lda, const int* perm, const cplx* Bm, long long bstride,
+                           int ldb, int nrows, cplx* X, long long xstride, int ldx, int nb, ZGemmProblem* gscratch, cudaStream_t st);
+
+// ---- eig.cu
+size_t eig_workspace_bytes(int n, int nb);
+cudaError_t eig(cplx* A, int n, int nb, cplx* w, cplx* V, char* ws, size_t ws_bytes, int* info, volatile int* host_flag, cudaStream_t st);
+
+}  // namespace rcwa

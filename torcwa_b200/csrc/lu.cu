@@ -1,0 +1,309 @@
+// Batched complex128 LU for ROW-MAJOR RIGHT-SOLVES:   X * A = B   (X, B are nrows x n).
+//
+// Every linear solve of the RCWA path can be put in this form without a single transpose
+// (inv(eps_conv); the two solves of the minimal layer S-matrix; the one solve of
+// the Redheffer product, SURVEY.md A.6 via the push-through identity).  In row-major storage the
+// natural elimination is then by ROWS with COLUMN pivoting,
+//
+//      A * Pi = L * U,    L lower (non-unit),   U unit upper,
+//
+// i.e. LAPACK getrf applied to A^T, which makes pivot search, scaling and the rank-1 update all
+// contiguous along rows.  Blocked right-looking, panel = NB rows:
+//   panel kernel (one CTA per matrix; phase-structured, also compiled by the CPU emulation build)
+//   -> column swaps outside the panel -> TRSM of the rows below (x * U11 = a, per row)
+//   -> trailing update A22 -= A21 * A12 on the DMMA grouped GEMM.
+// Solve: X = B*Pi (gather) ; X := X * U^-1 (forward over column blocks) ; X := X * L^-1 (backward),
+// each block step = a per-row small triangular solve + one GEMM.
+//
+// Replaces torch.linalg.inv at /root/reference/torcwa/rcwa.py:1226,1230,1248,1266-1267,
+// 1271,1273,1287-1288.
+#include "common.cuh"
+#ifndef RCWA_EMU
+#include "kernels.h"
+#else
+#include <vector>
+#endif
+
+#define LU_NB 32
+
+// ------------------------------------------------------------------------------------------------
+// panel factorisation: rows [k0, k0+nbe) of A (n x n, leading dim lda), columns [k0, n)
+// smem: 40 doubles + 40 ints scratch
+DEV void lu_panel_body(const Cta& c, cplx* A, int n, int lda, int k0, int nbe, int* ipiv, int* info) {
+    double* red_v = reinterpret_cast<double*>(c.smem);          // [33]
+    int* red_i = reinterpret_cast<int*>(red_v + 40);             // [33]
+    for (int j = k0; j < k0 + nbe; ++j) {
+        // ---- pivot search along row j
+        cplx* rowj = A + (size_t)j * lda;
+        double best = -1.0; int bidx = j;
+        for (int col = j + c.tid; col < n; col += c.nthreads) {
+            double v = cabs1(rowj[col]);
+            if (v > best) { best = v; bidx = col; }
+        }
+#ifndef RCWA_EMU
+        // warp argmax (ties -> smaller index), then across warps
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+            if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+        }
+        {
+            int w = c.tid >> 5, l = c.tid & 31, nw = (c.nthreads + 31) >> 5;
+            CTA_SYNC();
+            if (l == 0) { red_v[w] = best; red_i[w] = bidx; }
+            CTA_SYNC();
+            if (w == 0) {
+                double v = (l < nw) ? red_v[l] : -2.0; int i2 = (l < nw) ? red_i[l] : 0x7fffffff;
+                for (int o = 16; o > 0; o >>= 1) {
+                    double ov = __shfl_xor_sync(0xffffffffu, v, o);
+                    int oi = __shfl_xor_sync(0xffffffffu, i2, o);
+                    if (ov > v || (ov == v && oi < i2)) { v = ov; i2 = oi; }
+                }
+                if (l == 0) { red_v[32] = v; red_i[32] = i2; }
+            }
+            CTA_SYNC();
+            best = red_v[32]; bidx = red_i[32];
+        }
+#else
+        (void)red_v; (void)red_i;
+#endif
+        const int p = bidx;
+        if (c.tid == 0) {
+            ipiv[j] = p;
+            if (best == 0.0 && *info == 0) *info = j + 1;
+        }
+        // ---- swap columns j <-> p inside the panel rows
+        if (p != j) {
+            for (int r = k0 + c.tid; r < k0 + nbe; r += c.nthreads) {
+                cplx* row = A + (size_t)r * lda;
+                cplx t = row[j]; row[j] = row[p]; row[p] = t;
+            }
+        }
+        CTA_SYNC();
+        // ---- scale row j right of the diagonal by 1/pivot
+        const cplx piv = rowj[j];
+        if (best != 0.0) {
+            const cplx ip = cinv(piv);
+            for (int col = j + 1 + c.tid; col < n; col += c.nthreads) rowj[col] = cmul(rowj[col], ip);
+        }
+        CTA_SYNC();
+        // ---- rank-1 update of the remaining panel rows
+        const int nr = k0 + nbe - (j + 1), ncol = n - (j + 1);
+        if (nr > 0 && ncol > 0) {
+            for (long long idx = c.tid; idx < (long long)nr * ncol; idx += c.nthreads) {
+                int r = j + 1 + (int)(idx / ncol), col = j + 1 + (int)(idx % ncol);
+                cplx* row = A + (size_t)r * lda;
+                row[col] = csub(row[col], cmul(row[j], rowj[col]));
+            }
+        }
+        CTA_SYNC();
+    }
+}
+
+// perm[c] = original column sitting at position c after all swaps (so (B*Pi)[r][c] = B[r][perm[c]])
+DEV void lu_perm_body(const Cta& c, const int* ipiv, int n, int* perm) {
+    int* idx = reinterpret_cast<int*>(c.smem);   // [n]
+    for (int i = c.tid; i < n; i += c.nthreads) idx[i] = i;
+    CTA_SYNC();
+    if (c.tid == 0) {
+        for (int j = 0; j < n; ++j) { int p = ipiv[j]; if (p != j) { int t = idx[j]; idx[j] = idx[p]; idx[p] = t; } }
+    }
+    CTA_SYNC();
+    for (int i = c.tid; i < n; i += c.nthreads) perm[i] = idx[i];
+}
+
+// x * T = a for one row: mode 0: T unit upper (forward over columns); mode 1: T lower non-unit (backward).
+// T is nbe x nbe with leading dimension ldt; x overwrites a (nbe contiguous entries).
+DEV void trsm_row(cplx* x, const cplx* T, int ldt, int nbe, int mode) {
+    if (mode == 0) {
+        for (int col = 1; col < nbe; ++col) {
+            cplx acc = x[col];
+            for (int s = 0; s < col; ++s) acc = csub(acc, cmul(x[s], T[s * ldt + col]));
+            x[col] = acc;
+        }
+    } else {
+        for (int col = nbe - 1; col >= 0; --col) {
+            cplx acc = x[col];
+            for (int s = col + 1; s < nbe; ++s) acc = csub(acc, cmul(x[s], T[s * ldt + col]));
+            x[col] = cdiv(acc, T[col * ldt + col]);
+        }
+    }
+}
+
+#ifdef RCWA_EMU
+// ------------------------------------------------------------------ CPU emulation entry points (tests only)
+extern "C" int emu_lu_factor(cplx* A, int n, int lda, int* ipiv, int* perm, int* info) {
+    char smem[65536];
+    Cta c; c.tid = 0; c.nthreads = 1; c.bid = 0; c.smem = smem;
+    *info = 0;
+    for (int k0 = 0; k0 < n; k0 += LU_NB) {
+        int nbe = (n - k0 < LU_NB) ? n - k0 : LU_NB;
+        lu_panel_body(c, A, n, lda, k0, nbe, ipiv, info);
+        // column swaps outside the panel
+        for (int r = 0; r < n; ++r) {
+            if (r >= k0 && r < k0 + nbe) continue;
+            for (int j = k0; j < k0 + nbe; ++j) { int p = ipiv[j]; if (p != j) { cplx t = A[(size_t)r * lda + j]; A[(size_t)r * lda + j] = A[(size_t)r * lda + p]; A[(size_t)r * lda + p] = t; } }
+        }
+        // rows below: x * U11 = a ; then A22 -= A21 * A12
+        for (int r = k0 + nbe; r < n; ++r) trsm_row(A + (size_t)r * lda + k0, A + (size_t)k0 * lda + k0, lda, nbe, 0);
+        for (int r = k0 + nbe; r < n; ++r)
+            for (int col = k0 + nbe; col < n; ++col) {
+                cplx acc = A[(size_t)r * lda + col];
+                for (int s = 0; s < nbe; ++s) acc = csub(acc, cmul(A[(size_t)r * lda + k0 + s], A[(size_t)(k0 + s) * lda + col]));
+                A[(size_t)r * lda + col] = acc;
+            }
+    }
+    std::vector<char> big((size_t)n * sizeof(int) + 64);
+    c.smem = big.data();
+    lu_perm_body(c, ipiv, n, perm);
+    return 0;
+}
+extern "C" int emu_lu_solve(const cplx* LU, int n, int lda, const int* perm, const cplx* B, int nrows, int ldb, cplx* X, int ldx) {
+    for (int r = 0; r < nrows; ++r) for (int col = 0; col < n; ++col) X[(size_t)r * ldx + col] = B[(size_t)r * ldb + perm[col]];
+    for (int k0 = 0; k0 < n; k0 += LU_NB) {
+        int nbe = (n - k0 < LU_NB) ? n - k0 : LU_NB;
+        for (int r = 0; r < nrows; ++r) trsm_row(X + (size_t)r * ldx + k0, LU + (size_t)k0 * lda + k0, lda, nbe, 0);
+        for (int r = 0; r < nrows; ++r)
+            for (int col = k0 + nbe; col < n; ++col) {
+                cplx acc = X[(size_t)r * ldx + col];
+                for (int s = 0; s < nbe; ++s) acc = csub(acc, cmul(X[(size_t)r * ldx + k0 + s], LU[(size_t)(k0 + s) * lda + col]));
+                X[(size_t)r * ldx + col] = acc;
+            }
+    }
+    int nblk = (n + LU_NB - 1) / LU_NB;
+    for (int kb = nblk - 1; kb >= 0; --kb) {
+        int k0 = kb * LU_NB, nbe = (n - k0 < LU_NB) ? n - k0 : LU_NB;
+        for (int r = 0; r < nrows; ++r) trsm_row(X + (size_t)r * ldx + k0, LU + (size_t)k0 * lda + k0, lda, nbe, 1);
+        for (int r = 0; r < nrows; ++r)
+            for (int col = 0; col < k0; ++col) {
+                cplx acc = X[(size_t)r * ldx + col];
+                for (int s = 0; s < nbe; ++s) acc = csub(acc, cmul(X[(size_t)r * ldx + k0 + s], LU[(size_t)(k0 + s) * lda + col]));
+                X[(size_t)r * ldx + col] = acc;
+            }
+    }
+    return 0;
+}
+#else
+// ------------------------------------------------------------------ device kernels
+namespace {
+
+__global__ void __launch_bounds__(512, 1)
+lu_panel_kernel(cplx* A, long long stride, int n, int lda, int k0, int nbe, int* ipiv, int* info) {
+    extern __shared__ __align__(16) char smem_raw[];
+    Cta c = make_cta(blockIdx.x, smem_raw);
+    lu_panel_body(c, A + (size_t)blockIdx.x * stride, n, lda, k0, nbe, ipiv + (size_t)blockIdx.x * n, info + blockIdx.x);
+}
+
+__global__ void lu_perm_kernel(const int* ipiv, int n, int* perm) {
+    extern __shared__ __align__(16) char smem_raw[];
+    Cta c = make_cta(blockIdx.x, smem_raw);
+    lu_perm_body(c, ipiv + (size_t)blockIdx.x * n, n, perm + (size_t)blockIdx.x * n);
+}
+
+// grid (ceil(n/128), B): thread per row outside the panel applies the panel's column swaps in order
+__global__ void lu_colswap_kernel(cplx* A, long long stride, int n, int lda, int k0, int nbe, const int* ipiv) {
+    __shared__ int piv[LU_NB];
+    const int b = blockIdx.y;
+    if (threadIdx.x < nbe) piv[threadIdx.x] = ipiv[(size_t)b * n + k0 + threadIdx.x];
+    __syncthreads();
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n || (r >= k0 && r < k0 + nbe)) return;
+    cplx* row = A + (size_t)b * stride + (size_t)r * lda;
+    for (int jj = 0; jj < nbe; ++jj) {
+        int p = piv[jj], j = k0 + jj;
+        if (p != j) { cplx t = row[j]; row[j] = row[p]; row[p] = t; }
+    }
+}
+
+// grid (ceil(nrows/32), B): X[r0+r, c0 : c0+nbe] := X[...] * T^-1 ; T = diagonal block of the LU at (k0,k0)
+// mode 0: unit upper, mode 1: lower non-unit.  Tile staged through shared memory for coalescing.
+__global__ void __launch_bounds__(32)
+trsm_rows_kernel(cplx* X, long long xstride, int ldx, int row0, int nrows, int c0,
+                 const cplx* LU, long long lustride, int lda, int k0, int nbe, int mode) {
+    __shared__ cplx T[LU_NB * LU_NB];
+    __shared__ cplx tile[32 * (LU_NB + 1)];
+    const int b = blockIdx.y;
+    const cplx* lu = LU + (size_t)b * lustride + (size_t)k0 * lda + k0;
+    for (int i = threadIdx.x; i < nbe * nbe; i += 32) T[(i / nbe) * LU_NB + (i % nbe)] = lu[(size_t)(i / nbe) * lda + (i % nbe)];
+    const int rbase = row0 + blockIdx.x * 32;
+    cplx* xb = X + (size_t)b * xstride;
+    for (int i = threadIdx.x; i < 32 * nbe; i += 32) {
+        int r = i / nbe, col = i % nbe;
+        if (rbase + r < row0 + nrows) tile[r * (LU_NB + 1) + col] = xb[(size_t)(rbase + r) * ldx + c0 + col];
+    }
+    __syncthreads();
+    if (rbase + (int)threadIdx.x < row0 + nrows) trsm_row(tile + threadIdx.x * (LU_NB + 1), T, LU_NB, nbe, mode);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * nbe; i += 32) {
+        int r = i / nbe, col = i % nbe;
+        if (rbase + r < row0 + nrows) xb[(size_t)(rbase + r) * ldx + c0 + col] = tile[r * (LU_NB + 1) + col];
+    }
+}
+
+// grid (nrows, B): X[r][c] = Bm[r][perm[c]]
+__global__ void gather_cols_kernel(const cplx* __restrict__ Bm, long long bstride, int ldb, const int* __restrict__ perm,
+                                   int n, cplx* __restrict__ X, long long xstride, int ldx) {
+    const int r = blockIdx.x, b = blockIdx.y;
+    const cplx* src = Bm + (size_t)b * bstride + (size_t)r * ldb;
+    cplx* dst = X + (size_t)b * xstride + (size_t)r * ldx;
+    const int* pm = perm + (size_t)b * n;
+    for (int col = threadIdx.x; col < n; col += blockDim.x) dst[col] = src[pm[col]];
+}
+
+}  // namespace
+
+namespace rcwa {
+
+// A: [B] matrices n x n (lda, stride) overwritten by L\U; ipiv, perm: [B,n] ints; info: [B] ints
+cudaError_t lu_factor(cplx* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info,
+                      ZGemmProblem* gscratch, cudaStream_t st, bool clear_info) {
+    if (clear_info) cudaMemsetAsync(info, 0, sizeof(int) * nb, st);
+    const cplx one = C(1, 0), mone = C(-1, 0);
+    for (int k0 = 0; k0 < n; k0 += LU_NB) {
+        const int nbe = (n - k0 < LU_NB) ? n - k0 : LU_NB;
+        lu_panel_kernel<<<nb, 512, 1024, st>>>(A, stride, n, lda, k0, nbe, ipiv, info);
+        lu_colswap_kernel<<<dim3((n + 127) / 128, nb), 128, 0, st>>>(A, stride, n, lda, k0, nbe, ipiv);
+        const int rem = n - k0 - nbe;
+        if (rem > 0) {
+            trsm_rows_kernel<<<dim3((rem + 31) / 32, nb), 32, 0, st>>>(A, stride, lda, k0 + nbe, rem, k0, A, stride, lda, k0, nbe, 0);
+            cudaError_t e = zgemm_strided(OP_N, OP_N, rem, rem, nbe, mone,
+                                          A + (size_t)(k0 + nbe) * lda + k0, lda, stride,
+                                          A + (size_t)k0 * lda + (k0 + nbe), lda, stride, one,
+                                          A + (size_t)(k0 + nbe) * lda + (k0 + nbe), lda, stride, nb, gscratch, st);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    lu_perm_kernel<<<nb, 256, n * sizeof(int), st>>>(ipiv, n, perm);
+    return cudaGetLastError();
+}
+
+// X (nrows x n, ldx, xstride) = Bm * A^-1 ; X must not alias Bm
+cudaError_t lu_solve_right(const cplx* LU, long long lustride, int n, int lda, const int* perm, const cplx* Bm, long long bstride,
+                           int ldb, int nrows, cplx* X, long long xstride, int ldx, int nb, ZGemmProblem* gscratch, cudaStream_t st) {
+    const cplx one = C(1, 0), mone = C(-1, 0);
+    gather_cols_kernel<<<dim3(nrows, nb), 256, 0, st>>>(Bm, bstride, ldb, perm, n, X, xstride, ldx);
+    for (int k0 = 0; k0 < n; k0 += LU_NB) {
+        const int nbe = (n - k0 < LU_NB) ? n - k0 : LU_NB;
+        trsm_rows_kernel<<<dim3((nrows + 31) / 32, nb), 32, 0, st>>>(X, xstride, ldx, 0, nrows, k0, LU, lustride, lda, k0, nbe, 0);
+        const int rem = n - k0 - nbe;
+        if (rem > 0) {
+            cudaError_t e = zgemm_strided(OP_N, OP_N, nrows, rem, nbe, mone, X + k0, ldx, xstride,
+                                          LU + (size_t)k0 * lda + (k0 + nbe), lda, lustride, one, X + (k0 + nbe), ldx, xstride, nb, gscratch, st);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    const int nblk = (n + LU_NB - 1) / LU_NB;
+    for (int kb = nblk - 1; kb >= 0; --kb) {
+        const int k0 = kb * LU_NB, nbe = (n - k0 < LU_NB) ? n - k0 : LU_NB;
+        trsm_rows_kernel<<<dim3((nrows + 31) / 32, nb), 32, 0, st>>>(X, xstride, ldx, 0, nrows, k0, LU, lustride, lda, k0, nbe, 1);
+        if (k0 > 0) {
+            cudaError_t e = zgemm_strided(OP_N, OP_N, nrows, k0, nbe, mone, X + k0, ldx, xstride,
+                                          LU + (size_t)k0 * lda, lda, lustride, one, X, ldx, xstride, nb, gscratch, st);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace rcwa
+#endif

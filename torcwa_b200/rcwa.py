@@ -1,0 +1,417 @@
+"""Host side of the B200-native RCWA solver: the reference's public object, batched.
+
+Mirrors ``torcwa.rcwa`` (torcwa/rcwa.py:7-524 of the reference) -- same constructor, same call
+order (add_input_layer -> set_incident_angle -> add_layer... -> solve_global_smatrix ->
+S_parameters), same attribute names, same warnings -- but every heavy step is a call into
+librcwa_b200.so (C ABI, include/rcwa_b200.h) and every tensor carries a leading batch dimension of
+independent design points (wavelength x geometry), which the reference does not have
+(SURVEY.md 7.2):
+
+  * ``freq`` may be a [B] tensor, ``eps`` of a layer may be [nx,ny] (shared) or [B,nx,ny],
+    ``thickness`` / angles / half-space permittivities may be scalars or [B];
+  * with scalar ``freq`` every public attribute has exactly the reference's shape.
+
+Arithmetic: all device work is complex128 ("fp64 internals behind the c64 API", SURVEY.md finding
+5); for ``dtype=torch.complex64`` inputs are widened on entry and public results rounded on exit.
+torch is used for device memory, streams and O(N) per-order bookkeeping only; there is no torch
+fallback for the dense stages -- if the CUDA library is missing the constructor raises.
+"""
+import warnings
+
+import torch
+
+from . import _lib
+from ._bd import bd, bd_diag, bd_inv, bd_mul, sqrt_upper, v_matrix
+
+# The reference's pi is mistyped (torcwa/rcwa.py:5); omega = 2*pi*freq enters every layer phase, so
+# parity at 1e-10 requires the same constant.
+pi = 3.141592652589793
+
+_C = torch.complex128
+
+
+def vf_inverse_diagonals(kx, ky):
+    """Four diagonals of Vf^-1 (free-space E->H matrix, torcwa/rcwa.py:1143-1147) as [B,4,N]."""
+    return bd_inv(v_matrix(kx, ky, sqrt_upper(1.0 - kx * kx - ky * ky))).contiguous()
+
+
+class rcwa:
+    def __init__(self, freq, order, L, *,
+                 dtype=torch.complex64,
+                 device=None,
+                 stable_eig_grad=True,
+                 avoid_Pinv_instability=False,
+                 max_Pinv_instability=0.005,
+                 store_intermediates=None):
+        """Same parameters as the reference (torcwa/rcwa.py:9-35).  ``store_intermediates``
+        (new): keep per-layer P, Q, eigenvectors, convolution matrices as attributes
+        (default: only for unbatched sims, where the reference keeps them)."""
+        if dtype != torch.complex64 and dtype != torch.complex128:
+            warnings.warn('Invalid simulation data type. Set as torch.complex64.', UserWarning)
+            dtype = torch.complex64
+        self._dtype = dtype
+        self._rdtype = torch.float32 if dtype == torch.complex64 else torch.float64
+        if device is None:
+            device = torch.device('cuda')
+        self._device = torch.device(device)
+        if self._device.type != 'cuda':
+            raise RuntimeError('torcwa_b200 runs on CUDA devices only (no CPU path); got device=%s' % device)
+        _lib.load()   # fail loudly, now, if the CUDA library is missing
+
+        self.stable_eig_grad = True if stable_eig_grad else False
+        if avoid_Pinv_instability is True:
+            self.avoid_Pinv_instability = True
+            self.max_Pinv_instability = max_Pinv_instability
+            self.Pinv_instability, self.Qinv_instability = [], []
+        else:
+            self.avoid_Pinv_instability = False
+            self.max_Pinv_instability = None
+            self.Pinv_instability = self.Qinv_instability = None
+
+        f = torch.as_tensor(freq)
+        self._batched = f.dim() >= 1 and f.numel() > 1
+        self._B = f.numel() if self._batched else 1
+        self.freq = torch.as_tensor(freq, dtype=self._dtype, device=self._device)
+        self.omega = 2 * pi * freq                     # raw argument, as the reference (rcwa.py:61)
+        self._omega64 = torch.as_tensor(self.omega).to(device=self._device).real.to(torch.float64).reshape(-1)
+        self._freq128 = self.freq.to(_C).reshape(-1)   # widened *after* the cast to the sim dtype (rcwa.py:60)
+        self.L = L
+        self.order = order
+        self.order_x = torch.arange(-order[0], order[0] + 1, dtype=torch.int64, device=self._device)
+        self.order_y = torch.arange(-order[1], order[1] + 1, dtype=torch.int64, device=self._device)
+        self.order_N = len(self.order_x) * len(self.order_y)
+        self.Gx_norm, self.Gy_norm = 1 / (L[0] * self.freq), 1 / (L[1] * self.freq)
+        self._Gx = 1 / (L[0] * self._freq128)
+        self._Gy = 1 / (L[1] * self._freq128)
+
+        one = torch.tensor(1., dtype=self._dtype, device=self._device)
+        self.eps_in, self.mu_in, self.eps_out, self.mu_out = one, one.clone(), one.clone(), one.clone()
+        self._store = (not self._batched) if store_intermediates is None else bool(store_intermediates)
+
+        self.layer_N = 0
+        self.thickness = []
+        self.eps_conv, self.mu_conv = [], []
+        self.P, self.Q = [], []
+        self.kz_norm, self.E_eigvec, self.H_eigvec = [], [], []
+        self.Cf, self.Cb = [], []
+        self.layer_S11, self.layer_S21, self.layer_S12, self.layer_S22 = [], [], [], []
+        self._layers = []          # internal: per layer [S11, S21] complex128 [B,n,n]
+        self.eig_info = []         # per patterned layer: int32 [B] status of the eigensolver
+
+    # ------------------------------------------------------------------ helpers
+    def _b(self, v):
+        """scalar or [B] -> complex128 [B] on the device."""
+        t = torch.as_tensor(v, device=self._device).to(_C).reshape(-1)
+        if t.numel() == 1:
+            t = t.expand(self._B)
+        elif t.numel() != self._B:
+            raise ValueError('expected a scalar or %d values' % self._B)
+        return t
+
+    def _pub(self, t):
+        """internal complex128 [B,...] -> public tensor (sim dtype, batch dim dropped if unbatched)."""
+        t = t.to(self._dtype)
+        return t if self._batched else t[0]
+
+    # ------------------------------------------------------------------ setup (rcwa.py:95-144)
+    def add_input_layer(self, eps=1., mu=1.):
+        self.eps_in = torch.as_tensor(eps, dtype=self._dtype, device=self._device)
+        self.mu_in = torch.as_tensor(mu, dtype=self._dtype, device=self._device)
+        self.Sin = []
+
+    def add_output_layer(self, eps=1., mu=1.):
+        self.eps_out = torch.as_tensor(eps, dtype=self._dtype, device=self._device)
+        self.mu_out = torch.as_tensor(mu, dtype=self._dtype, device=self._device)
+        self.Sout = []
+
+    def set_incident_angle(self, inc_ang, azi_ang, angle_layer='input'):
+        self.inc_ang = torch.as_tensor(inc_ang, dtype=self._dtype, device=self._device)
+        self.azi_ang = torch.as_tensor(azi_ang, dtype=self._dtype, device=self._device)
+        if angle_layer in ['i', 'in', 'input']:
+            self.angle_layer = 'input'
+        elif angle_layer in ['o', 'out', 'output']:
+            self.angle_layer = 'output'
+        else:
+            warnings.warn('Invalid angle layer. Set as input layer.', UserWarning)
+            self.angle_layer = 'input'
+        self._kvectors()
+
+    def _kvectors(self):
+        """Per-order wavevectors and half-space S-matrices (rcwa.py:1124-1181), O(N)."""
+        B, N = self._B, self.order_N
+        e_in, m_in = self._b(self.eps_in), self._b(self.mu_in)
+        e_out, m_out = self._b(self.eps_out), self._b(self.mu_out)
+        inc, azi = self._b(self.inc_ang), self._b(self.azi_ang)
+        nref = torch.sqrt(e_in * m_in).real if self.angle_layer == 'input' else torch.sqrt(e_out * m_out).real
+        kx0 = nref * torch.sin(inc) * torch.cos(azi)
+        ky0 = nref * torch.sin(inc) * torch.sin(azi)
+        kxl = kx0[:, None] + self.order_x[None, :] * self._Gx[:, None]      # [B, 2ox+1]
+        kyl = ky0[:, None] + self.order_y[None, :] * self._Gy[:, None]      # [B, 2oy+1]
+        kx = kxl[:, :, None].expand(B, len(self.order_x), len(self.order_y)).reshape(B, N).contiguous()
+        ky = kyl[:, None, :].expand(B, len(self.order_x), len(self.order_y)).reshape(B, N).contiguous()
+        self._kx, self._ky = kx, ky
+        self.kx0_norm, self.ky0_norm = self._pub(kx0), self._pub(ky0)
+        self.kx_norm, self.ky_norm = self._pub(kxl), self._pub(kyl)
+        self.Kx_norm_dn, self.Ky_norm_dn = self._pub(kx), self._pub(ky)
+        self._Vf = v_matrix(kx, ky, sqrt_upper(1.0 - kx * kx - ky * ky))
+        self._Vf_inv = bd_inv(self._Vf).contiguous()
+        if hasattr(self, 'Sin'):
+            Vi = v_matrix(kx, ky, sqrt_upper((e_in * m_in)[:, None] - kx * kx - ky * ky))
+            T = bd_inv(self._Vf + Vi)
+            D = bd_mul(T, self._Vf - Vi)
+            self._Vi = Vi
+            self._Sin = [2 * bd_mul(T, Vi), -D, D, 2 * bd_mul(T, self._Vf)]
+            self.Sin = _LazyDense(self, self._Sin)
+        if hasattr(self, 'Sout'):
+            Vo = v_matrix(kx, ky, sqrt_upper((e_out * m_out)[:, None] - kx * kx - ky * ky))
+            T = bd_inv(self._Vf + Vo)
+            D = bd_mul(T, self._Vf - Vo)
+            self._Vo = Vo
+            self._Sout = [2 * bd_mul(T, self._Vf), D, -D, 2 * bd_mul(T, Vo)]
+            self.Sout = _LazyDense(self, self._Sout)
+
+    # dense views of the 2x2-block-diagonal matrices, built on demand (drop-in attributes)
+    @property
+    def Kx_norm(self):
+        return torch.diag_embed(self.Kx_norm_dn)
+
+    @property
+    def Ky_norm(self):
+        return torch.diag_embed(self.Ky_norm_dn)
+
+    @property
+    def Vf(self):
+        return self._pub(_lib.blockdiag_dense(self._Vf.contiguous()))
+
+    @property
+    def Vi(self):
+        return self._pub(_lib.blockdiag_dense(self._Vi.contiguous()))
+
+    @property
+    def Vo(self):
+        return self._pub(_lib.blockdiag_dense(self._Vo.contiguous()))
+
+    # ------------------------------------------------------------------ layers (rcwa.py:146-170)
+    def _is_homogeneous(self, v):
+        # same acceptance rule as the reference (rcwa.py:156-157): float, complex, 0-d tensor,
+        # one-element 1-d tensor; an int has no .dim() and raises AttributeError before any state changes.
+        if type(v) == float or type(v) == complex:
+            return True
+        if v.dim() == 0 or (v.dim() == 1 and v.shape[0] == 1):
+            return True
+        return self._batched and v.dim() == 1 and v.shape[0] == self._B     # per-point scalar (new)
+
+    def _conv(self, grid):
+        """Convolution matrix of a sampled cell, [B,N,N] complex128 (CUDA stage 1)."""
+        grid = torch.as_tensor(grid, device=self._device)
+        want_real = torch.float32 if self._dtype == torch.complex64 else torch.float64
+        if grid.dtype not in (want_real, self._dtype):
+            # the reference fails inside torch.matmul on mixed precision (SURVEY.md finding 9)
+            raise RuntimeError('expected material of dtype %s or %s but found %s' % (want_real, self._dtype, grid.dtype))
+        if grid.dim() == 3 and grid.shape[0] != self._B:
+            raise ValueError('batched material must have leading dimension %d' % self._B)
+        if grid.shape[-2] < 4 * self.order[0] + 1 or grid.shape[-1] < 4 * self.order[1] + 1:
+            raise IndexError('material grid too coarse for the Fourier order (needs >= 4*order+1 samples)')
+        return _lib.convmat(grid, self.order[0], self.order[1], nb=self._B)
+
+    def add_layer(self, thickness, eps=1., mu=1.):
+        he, hm = self._is_homogeneous(eps), self._is_homogeneous(mu)
+        B, N = self._B, self.order_N
+        kx, ky = self._kx, self._ky
+        thick = torch.as_tensor(thickness, device=self._device).to(torch.float64).reshape(-1)
+        thick = (thick.expand(B) if thick.numel() == 1 else thick).contiguous()
+        omega = (self._omega64.expand(B) if self._omega64.numel() == 1 else self._omega64).contiguous()
+
+        if he and hm:
+            S11, S21, kz = self._homogeneous_layer(self._b(eps), self._b(mu), omega, thick)
+            if self._store:
+                self.eps_conv.append(self._pub(self._b(eps)[:, None, None] * torch.eye(N, dtype=_C, device=self._device)))
+                self.mu_conv.append(self._pub(self._b(mu)[:, None, None] * torch.eye(N, dtype=_C, device=self._device)))
+                self.E_eigvec.append(self._pub(torch.eye(2 * N, dtype=_C, device=self._device).expand(B, -1, -1)))
+        else:
+            E = self._b(eps)[:, None, None] * torch.eye(N, dtype=_C, device=self._device) if he else self._conv(eps)
+            eta, info_e = _lib.inverse(E)
+            if hm:
+                P, Q = _lib.pq_assemble(eta, E.contiguous(), kx, ky, mu_scalar=self._b(mu).contiguous())
+                M = None
+            else:
+                M = self._conv(mu)
+                nu, _ = _lib.inverse(M)
+                P, Q = _lib.pq_assemble(eta, E.contiguous(), kx, ky, Mc=M, nu=nu)
+            A = _lib.zgemm(P, Q)
+            lam, W, info = _lib.eig(A)
+            del A
+            self.eig_info.append(info)
+            kz = _lib.kz_branch(lam)
+            S11, S21, info_s = _lib.layer_smatrix(W, kz, Q, self._Vf_inv, omega, thick)
+            if self._store:
+                self.eps_conv.append(self._pub(E))
+                self.mu_conv.append(self._pub(M if M is not None else self._b(mu)[:, None, None] * torch.eye(N, dtype=_C, device=self._device)))
+                self.P.append(self._pub(P)); self.Q.append(self._pub(Q))
+                self.E_eigvec.append(self._pub(W))
+        self.kz_norm.append(self._pub(kz))
+        self.layer_N += 1
+        self.thickness.append(thickness)
+        self._layers.append([S11, S21])
+        if self._store:
+            s11, s21 = self._pub(S11), self._pub(S21)
+            self.layer_S11.append(s11); self.layer_S21.append(s21)
+            self.layer_S12.append(s21); self.layer_S22.append(s11)      # single-layer symmetry
+
+    def _homogeneous_layer(self, eps, mu, omega, thick):
+        """Analytic modes (rcwa.py:1206-1222: W = I, kz = conj-branch sqrt) pushed through the
+        minimal layer-S algebra in 2x2-block form; returns dense S11, S21 and kz [B,2N]."""
+        kx, ky = self._kx, self._ky
+        kz1 = sqrt_upper((eps * mu)[:, None] - kx * kx - ky * ky)
+        im = 1 / mu[:, None]
+        Q = bd(-kx * ky * im, kx * kx * im - eps[:, None], eps[:, None] - ky * ky * im, ky * kx * im)
+        ikz = bd_diag(1 / kz1)
+        Bm = bd_mul(self._Vf_inv, bd_mul(Q, ikz))                 # Vf^-1 Q Kz^-1  (W = I)
+        X = torch.exp(1j * (omega * thick)[:, None] * kz1)
+        onep, onem = bd_diag(1 + X), bd_diag(1 - X)
+        Tp = bd_mul(onep, bd_inv(onep + bd_mul(Bm, onem)))        # R+ M+^-1
+        Tm = bd_mul(-onem, bd_inv(onem + bd_mul(Bm, onep)))       # R- M-^-1
+        eye = bd_diag(torch.ones_like(kz1))
+        S11 = _lib.blockdiag_dense((Tp + Tm).contiguous())
+        S21 = _lib.blockdiag_dense((Tp - Tm - eye).contiguous())
+        return S11, S21, torch.cat((kz1, kz1), dim=1)
+
+    # ------------------------------------------------------------------ cascade (rcwa.py:173-211)
+    def solve_global_smatrix(self):
+        B, n = self._B, 2 * self.order_N
+        if self.layer_N > 0:
+            s11, s21 = self._layers[0]
+            S = [s11, s21, s21, s11]
+            for i in range(1, self.layer_N):
+                n11, n21 = self._layers[i]
+                S, _ = _lib.redheffer(S, [n11, n21, n21, n11])
+        else:
+            eye = torch.eye(n, dtype=_C, device=self._device).expand(B, -1, -1).contiguous()
+            zero = torch.zeros((B, n, n), dtype=_C, device=self._device)
+            S = [eye, zero, zero.clone(), eye.clone()]
+        if hasattr(self, 'Sin'):
+            S, _ = _lib.redheffer([_lib.blockdiag_dense(s.contiguous()) for s in self._Sin], S)
+        if hasattr(self, 'Sout'):
+            S, _ = _lib.redheffer(S, [_lib.blockdiag_dense(s.contiguous()) for s in self._Sout])
+        self._S = S
+        self.S = [self._pub(s) for s in S]
+        self.C = [[], []]      # mode-coefficient propagation is row (f1) of the scope table: not built
+
+    # ------------------------------------------------------------------ readout (rcwa.py:300-524)
+    def _matching_indices(self, orders):
+        # clamps out-of-range orders to the truncation edge, in place like the reference (rcwa.py:1115-1122)
+        orders[orders[:, 0] < -self.order[0], 0] = int(-self.order[0])
+        orders[orders[:, 0] > self.order[0], 0] = int(self.order[0])
+        orders[orders[:, 1] < -self.order[1], 1] = int(-self.order[1])
+        orders[orders[:, 1] > self.order[1], 1] = int(self.order[1])
+        return len(self.order_y) * (orders[:, 0] + int(self.order[0])) + orders[:, 1] + int(self.order[1])
+
+    def _kz_power(self, eps, mu, evanscent, abs_when_evanescent=False):
+        kzc = torch.sqrt((self._b(eps) * self._b(mu))[:, None] - self._kx ** 2 - self._ky ** 2)
+        ev = torch.abs(kzc.real / kzc.imag) < evanscent
+        repl = torch.abs(kzc.real) if abs_when_evanescent else torch.zeros_like(kzc.real)
+        k = torch.where(ev, repl, kzc.real)
+        return torch.cat((k, k), dim=1)
+
+    def S_parameters(self, orders, *, direction='forward', port='transmission', polarization='xx',
+                     ref_order=[0, 0], power_norm=True, evanscent=1e-3):
+        orders = torch.as_tensor(orders, dtype=torch.int64, device=self._device).reshape([-1, 2])
+        if direction in ['f', 'forward']:
+            direction = 'forward'
+        elif direction in ['b', 'backward']:
+            direction = 'backward'
+        else:
+            warnings.warn('Invalid propagation direction. Set as forward.', UserWarning)
+            direction = 'forward'
+        if port in ['t', 'transmission']:
+            port = 'transmission'
+        elif port in ['r', 'reflection']:
+            port = 'reflection'
+        else:
+            warnings.warn('Invalid port. Set as tramsmission.', UserWarning)
+            port = 'transmission'
+        if polarization not in ['xx', 'yx', 'xy', 'yy', 'pp', 'sp', 'ps', 'ss']:
+            warnings.warn('Invalid polarization. Set as xx.', UserWarning)
+            polarization = 'xx'
+        ref_order = torch.as_tensor(ref_order, dtype=torch.int64, device=self._device).reshape([1, 2])
+        oi = self._matching_indices(orders)
+        ri = self._matching_indices(ref_order)
+        N = self.order_N
+        blk = {('forward', 'transmission'): 0, ('forward', 'reflection'): 1,
+               ('backward', 'reflection'): 2, ('backward', 'transmission'): 3}[(direction, port)]
+        S = self._S[blk]
+        side = {0: ('out', 'in'), 1: ('in', 'in'), 2: ('out', 'out'), 3: ('in', 'out')}[blk]
+        kx, ky = self._kx, self._ky
+
+        if polarization in ['xx', 'yx', 'xy', 'yy']:
+            oi2 = oi + N if polarization[0] == 'y' else oi
+            ri2 = ri + N if polarization[1] == 'y' else ri
+            out = S[:, oi2, ri2]
+            if power_norm:
+                kzs = {'in': self._kz_power(self.eps_in, self.mu_in, evanscent),
+                       'out': self._kz_power(self.eps_out, self.mu_out, evanscent)}
+                kx2 = torch.cat((kx.real, kx.real), dim=1)
+                ky2 = torch.cat((ky.real, ky.real), dim=1)
+                num_pol = kx2 if polarization[0] == 'x' else ky2
+                den_pol = kx2 if polarization[1] == 'x' else ky2
+                num_kz, den_kz = kzs[side[0]], kzs[side[1]]
+                norm = torch.sqrt((1 + (num_pol[:, oi2] / num_kz[:, oi2]) ** 2) / (1 + (den_pol[:, ri2] / den_kz[:, ri2]) ** 2))
+                norm = norm * torch.sqrt(num_kz[:, oi2] / den_kz[:, ri2])
+                out = out * norm
+            out = torch.where(torch.isinf(out), torch.zeros_like(out), out)
+            out = torch.where(torch.isnan(out), torch.zeros_like(out), out)
+            return self._pub(out)
+
+        osign, rsign = {0: (1, 1), 1: (-1, 1), 2: (1, -1), 3: (-1, -1)}[blk]
+        em = {'in': self._b(self.eps_in) * self._b(self.mu_in), 'out': self._b(self.eps_out) * self._b(self.mu_out)}
+
+        def angles(idx, k2, sign):
+            kxs, kys = kx[:, idx], ky[:, idx]
+            kt = torch.sqrt(kxs ** 2 + kys ** 2)
+            kzc = torch.sqrt(k2[:, None] - kxs ** 2 - kys ** 2)
+            kz = sign * torch.abs(kzc.real)
+            ev = torch.abs(kzc.real / kzc.imag) < evanscent
+            return torch.atan2(kt.real, kz), torch.atan2(kys.real, kxs.real), ev
+
+        o_inc, o_azi, o_ev = angles(oi, em[side[0]], osign)
+        r_inc, r_azi, r_ev = angles(ri, em[side[1]], rsign)
+
+        def pick(a, b):
+            v = S[:, a, b]
+            return torch.where(o_ev, torch.zeros_like(v), v)
+
+        xx, xy = pick(oi, ri), pick(oi, ri + N)
+        yx, yy = pick(oi + N, ri), pick(oi + N, ri + N)
+        co, so, ci = torch.cos(o_azi), torch.sin(o_azi), torch.cos(o_inc)
+        cr, sr, cri = torch.cos(r_azi), torch.sin(r_azi), torch.cos(r_inc)
+        if polarization == 'pp':
+            out = (co / ci) * cri * cr * xx + (so / ci) * cri * cr * yx + (co / ci) * cri * sr * xy + (so / ci) * cri * sr * yy
+        elif polarization == 'ps':
+            out = (co / ci) * (-sr) * xx + (so / ci) * (-sr) * yx + (co / ci) * cr * xy + (so / ci) * cr * yy
+        elif polarization == 'sp':
+            out = -so * cri * cr * xx + co * cri * cr * yx - so * cri * sr * xy + co * cri * sr * yy
+        else:
+            out = -so * (-sr) * xx + co * (-sr) * yx - so * cr * xy + co * cr * yy
+        out = torch.where(torch.isinf(out), torch.zeros_like(out), out)
+        out = torch.where(torch.isnan(out), torch.zeros_like(out), out)
+        if power_norm:
+            kzs = {'in': self._kz_power(self.eps_in, self.mu_in, evanscent),
+                   'out': self._kz_power(self.eps_out, self.mu_out, evanscent, abs_when_evanescent=True)}
+            out = out * torch.sqrt(kzs[side[0]][:, oi] / kzs[side[1]][:, ri])
+        # an evanescent reference order gives zeros (rcwa.py:447-449), here per design point
+        out = torch.where(r_ev, torch.zeros_like(out), out)
+        return self._pub(out)
+
+
+class _LazyDense:
+    """List-like view that materialises dense [2N,2N] tensors from 2x2-block-diagonal storage on
+    access (the reference's ``Sin`` / ``Sout`` are lists of four dense matrices)."""
+
+    def __init__(self, sim, blocks):
+        self._sim, self._blocks = sim, blocks
+
+    def __len__(self):
+        return len(self._blocks)
+
+    def __getitem__(self, k):
+        return self._sim._pub(_lib.blockdiag_dense(self._blocks[k].contiguous()))
