@@ -87,6 +87,10 @@ int rcwa_pq_assemble(const void* eta, const void* E, const void* Mc, const void*
 size_t rcwa_eig_workspace_bytes(int n, int nb);
 int rcwa_eig(void* A, int n, int nb, void* w, void* V, void* ws, size_t ws_bytes, int* info,
              void* host_flag, void* stream);
+/* First phase of rcwa_eig on its own (profiling / building block): A[b] -> H[b] upper Hessenberg in
+ * place, Z[b] unitary with A_in = Z H Z^H.  Workspace as for rcwa_eig.  This is the HBM-bound
+ * streaming kernel of the eigen stage (one fused pass over [A; Z] per column). */
+int rcwa_hessenberg(void* A, int n, int nb, void* Z, void* ws, size_t ws_bytes, void* stream);
 /* kz = sqrt(lambda), negated where Im < 0 (rcwa.py:1240-1241). total = nb*n elements. */
 int rcwa_kz_branch(const void* lam, void* kz, long long total, void* stream);
 

@@ -1,0 +1,100 @@
+"""CPU emulation of the phase-structured single-CTA kernels (tests/_emu/librcwa_emu.so, built from
+the same .cu sources with -DRCWA_EMU): control flow and index arithmetic of the LU panel, the
+windowed multishift QR (deflation, shifts, bulge chains, small-block solves) and the triangular
+eigenvector solve, checked against numpy/scipy LAPACK.  The emulation library is test
+infrastructure only; the product never loads it."""
+import ctypes
+
+import numpy as np
+import pytest
+import scipy.linalg as sl
+import torch
+
+from oracle import cases as C
+from oracle.rcwa_oracle import OracleSim
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from torcwa_b200 import build
+    return ctypes.CDLL(build.build_emu())
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def crand(rng, *shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+@pytest.mark.parametrize("n", [1, 5, 32, 33, 97])
+def test_lu_right_solve(emu, n):
+    rng = np.random.default_rng(n)
+    A = crand(rng, n, n)
+    LU = A.copy()
+    ipiv, perm, info = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(1, np.int32)
+    emu.emu_lu_factor(P(LU), n, n, P(ipiv), P(perm), P(info))
+    assert info[0] == 0
+    B = crand(rng, 6, n)
+    X = np.zeros_like(B)
+    emu.emu_lu_solve(P(LU), n, n, P(perm), P(B), 6, n, P(X), n)
+    assert np.abs(X @ A - B).max() < 1e-11 * max(1, n)
+
+
+def schur_and_vectors(emu, A):
+    n = A.shape[0]
+    if n > 2:
+        H, Z = sl.hessenberg(A, calc_q=True)
+    else:
+        H, Z = A.copy(), np.eye(n, dtype=complex)
+    H, Z = np.ascontiguousarray(H), np.ascontiguousarray(Z)
+    stats = np.zeros(4, np.int32)
+    info = emu.emu_qr(P(H), P(Z), n, 10 ** 6, P(stats))
+    assert info == 0
+    T = np.triu(H)
+    assert np.abs(np.tril(H, -1)).max() == 0.0
+    X = np.zeros((n, n), complex)
+    emu.emu_trevc(P(np.ascontiguousarray(T)), n, P(X))
+    V = Z @ X
+    V /= np.linalg.norm(V, axis=0)
+    return T, Z, V, stats
+
+
+@pytest.mark.parametrize("n", [2, 3, 16, 17, 48, 49, 64, 65, 130])
+def test_qr_and_eigenvectors_random(emu, n):
+    rng = np.random.default_rng(1000 + n)
+    A = crand(rng, n, n)
+    T, Z, V, stats = schur_and_vectors(emu, A)
+    assert np.abs(Z @ T @ Z.conj().T - A).max() < 1e-12 * n
+    assert np.abs(Z.conj().T @ Z - np.eye(n)).max() < 1e-12 * n
+    w = np.diag(T)
+    assert np.abs(A @ V - V * w).max() < 1e-11 * n
+
+
+def test_qr_on_rcwa_matrix_and_degenerate_cell(emu):
+    for name in ("ex1_o3", "square_o4"):
+        case = C.CASES[name]
+        sim = OracleSim(freq=C.freq_of(case, torch.complex128), order=case["order"], L=case["L"], dtype=torch.complex128)
+        sim.add_input_layer(eps=case["eps_in"])
+        sim.set_incident_angle(0.0, 0.0)
+        d, e = C.build_layers(case, torch.complex128)[0]
+        sim.add_layer(d, e)
+        A = (sim.P[0] @ sim.Q[0]).numpy()
+        T, Z, V, stats = schur_and_vectors(emu, A)
+        w = np.diag(T)
+        assert np.abs(A @ V - V * w).max() < 1e-10 * np.abs(A).max()
+        ref = np.sort_complex((sim.kz_norm[0].numpy()) ** 2)
+        assert np.abs(np.sort_complex(w) - ref).max() < 1e-9 * np.abs(ref).max()
+        assert np.linalg.cond(V) < 1e8
+        assert stats[0] < 3 * A.shape[0] / 16 + 10      # sweeps stay ~ n/16 * small constant
+
+
+def test_tiny_shift_solver(emu):
+    rng = np.random.default_rng(5)
+    for m in (1, 2, 3, 7, 16):
+        T = np.triu(crand(rng, m, m), -1).copy()
+        w = np.zeros(m, complex)
+        assert emu.emu_tiny_eigs(P(T.copy()), m, P(w)) == 0
+        ref = np.linalg.eigvals(T)
+        assert max(np.min(np.abs(ref - x)) for x in w) < 1e-12

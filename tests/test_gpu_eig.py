@@ -1,0 +1,97 @@
+"""CUDA eigensolver (C ABI rcwa_hessenberg / rcwa_eig) against fp64 LAPACK through torch."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.complex(torch.randn(*shape, generator=g, dtype=torch.float64),
+                         torch.randn(*shape, generator=g, dtype=torch.float64)).to(dev())
+
+
+def match_sorted(a, b):
+    """max distance between two multisets of complex numbers after greedy nearest matching."""
+    a, b = list(a), list(b)
+    worst = 0.0
+    for x in a:
+        d = [abs(x - y) for y in b]
+        k = int(np.argmin(d))
+        worst = max(worst, d[k])
+        b.pop(k)
+    return worst
+
+
+@pytest.mark.parametrize("n", [3, 4, 17, 63, 64, 65, 130, 200])
+def test_hessenberg(n):
+    from torcwa_b200 import _lib
+    A = rnd(3, n, n, seed=n)
+    H = A.clone()
+    Z = _lib.hessenberg_(H)
+    torch.cuda.synchronize()
+    eye = torch.eye(n, dtype=torch.complex128, device=dev())
+    assert float((Z.conj().transpose(1, 2) @ Z - eye).abs().max()) < 1e-12
+    assert float(torch.tril(H, -2).abs().max()) == 0.0
+    back = Z @ H @ Z.conj().transpose(1, 2)
+    assert float((back - A).abs().max() / A.abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 16, 17, 48, 49, 64, 65, 100, 150, 242])
+def test_eig_random(n):
+    from torcwa_b200 import _lib
+    nb = 3
+    A = rnd(nb, n, n, seed=100 + n)
+    w, V, info = _lib.eig(A.clone())
+    torch.cuda.synchronize()
+    assert int(info.abs().max()) == 0, info
+    res = (A @ V - V * w[:, None, :]).abs().max() / A.abs().max()
+    assert float(res) < 1e-11
+    assert float(((V.abs() ** 2).sum(dim=1) - 1).abs().max()) < 1e-12
+    ref = torch.linalg.eigvals(A.cpu())
+    for b in range(nb):
+        assert match_sorted(w[b].cpu().numpy(), ref[b].numpy()) < 1e-10 * float(ref[b].abs().max())
+
+
+def test_eig_batch_entries_independent():
+    """A batch of different sizes of difficulty must give the same answer as one at a time."""
+    from torcwa_b200 import _lib
+    A = rnd(4, 90, 90, seed=7)
+    A[1] = torch.diag(torch.arange(1, 91, dtype=torch.float64, device=dev()).to(torch.complex128))   # already triangular
+    A[2] = A[2] * 1e-3
+    w, V, info = _lib.eig(A.clone())
+    for b in range(4):
+        w1, V1, i1 = _lib.eig(A[b:b + 1].clone())
+        assert int(i1[0]) == 0 and int(info[b]) == 0
+        assert match_sorted(w[b].cpu().numpy(), w1[0].cpu().numpy()) < 1e-10 * float(w1.abs().max())
+
+
+@pytest.mark.parametrize("name", ["ex1_o3", "ex1_o5", "square_o4"])
+def test_eig_rcwa_matrix(name, golden_dir):
+    """The real thing: P*Q of a patterned layer (incl. the C4v cell with degenerate pairs);
+    eigenvalues against the reference's kz^2 (golden) and residual of the eigenpairs."""
+    from oracle import cases as C
+    from oracle.rcwa_oracle import OracleSim
+    from torcwa_b200 import _lib
+    case = C.CASES[name]
+    sim = OracleSim(freq=C.freq_of(case, torch.complex128), order=case["order"], L=case["L"], dtype=torch.complex128)
+    sim.add_input_layer(eps=case["eps_in"])
+    sim.set_incident_angle(0.0, 0.0)
+    d, e = C.build_layers(case, torch.complex128)[0]
+    sim.add_layer(d, e)
+    A = (sim.P[0] @ sim.Q[0]).to(dev())[None].contiguous()
+    w, V, info = _lib.eig(A.clone())
+    assert int(info[0]) == 0
+    res = (A @ V - V * w[:, None, :]).abs().max() / A.abs().max()
+    assert float(res) < 1e-11
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    mine = np.sort_complex(w[0].cpu().numpy())
+    assert np.abs(mine - g["kz2_sorted"][0]).max() < 1e-9 * np.abs(mine).max()
+    assert float(torch.linalg.cond(V[0].cpu())) < 1e8

@@ -1,0 +1,128 @@
+"""End-to-end parity of the B200 path (torcwa_b200.rcwa -> C ABI -> CUDA) against the reference's
+stored outputs (tests/golden, generated from the unmodified reference by tools/make_golden.py).
+
+Gates: complex128 vs reference-complex128 <= 1e-10; complex64 API vs
+reference-complex128 <= 1e-4 (the reference's own complex64 run is ~3e-4 away from its complex128
+run at order 15; both distances are printed)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cases as C  # noqa: E402
+
+SMALL = ["ex1_o3", "ex1_o5", "stack_o3", "stack_o4x2", "fresnel_o2", "square_o4"]
+
+
+def b200_factory(freq, order, L, dtype):
+    import torcwa_b200
+    return torcwa_b200.rcwa(freq=freq, order=order, L=L, dtype=dtype, device=torch.device("cuda:0"))
+
+
+def to_dev(case, cdtype):
+    return case
+
+
+def run(name, cdtype):
+    case = C.CASES[name]
+    # same driver as the golden generator, tensors moved to the GPU by the solver
+    return C.run_case(b200_factory, case, cdtype)
+
+
+def relfro(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_parity_c128(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    sim = run(name, torch.complex128)
+    for info in sim.eig_info:
+        assert int(info.abs().max()) == 0
+    sp = C.probe(sim)
+    scale = np.abs(g["sparams_c128"]).max()
+    err = np.abs(sp - g["sparams_c128"]).max() / scale
+    print(name, "S-parameter max err / max|S|:", err)
+    assert err <= 1e-10
+    cols = g["S_cols_idx"]
+    for k in range(4):
+        assert relfro(sim.S[k][:, cols].cpu().numpy(), g["S_cols"][k]) <= 1e-10
+    fro = np.array([float(torch.linalg.norm(s)) for s in sim.S])
+    np.testing.assert_allclose(fro, g["S_fro"], rtol=1e-10)
+    if "S" in g:
+        for k in range(4):
+            assert relfro(sim.S[k].cpu().numpy(), g["S"][k]) <= 1e-10
+    if "eps_conv0" in g and sim.eps_conv:
+        assert relfro(sim.eps_conv[0].cpu().numpy(), g["eps_conv0"]) <= 1e-13
+        ls = [sim.layer_S11[0], sim.layer_S21[0], sim.layer_S12[0], sim.layer_S22[0]]
+        for k in range(4):
+            assert relfro(ls[k].cpu().numpy(), g["layer_S0"][k]) <= 1e-10
+    if "kz2_sorted" in g:
+        for l, kz in enumerate(sim.kz_norm):
+            mine = np.sort_complex(kz.cpu().numpy().astype(np.complex128) ** 2)
+            assert np.abs(mine - g["kz2_sorted"][l]).max() <= 1e-9 * np.abs(mine).max()
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_parity_c64_api(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    sim = run(name, torch.complex64)
+    assert sim.S[0].dtype == torch.complex64
+    sp = C.probe(sim)
+    scale = np.abs(g["sparams_c128"]).max()
+    new_vs_ref128 = np.abs(sp - g["sparams_c128"]).max() / scale
+    ref64_vs_ref128 = np.abs(g["sparams_c64"] - g["sparams_c128"]).max() / scale
+    new_vs_ref64 = np.abs(sp - g["sparams_c64"]).max() / scale
+    print(f"{name}: new-c64 vs ref-c128 {new_vs_ref128:.2e} | ref-c64 vs ref-c128 {ref64_vs_ref128:.2e} | new-c64 vs ref-c64 {new_vs_ref64:.2e}")
+    assert new_vs_ref128 <= 1e-4
+    for k in range(4):
+        assert relfro(sim.S[k][:, g["S_cols_idx"]].cpu().numpy().astype(np.complex128), g["S_cols"][k]) <= 1e-4
+
+
+def test_batched_equals_unbatched():
+    """New API surface: a [B] frequency batch with per-point grids gives, entry by
+    entry, what B separate sims give."""
+    import torcwa_b200
+    case = C.CASES["ex1_o3"]
+    cd = torch.complex128
+    lams = torch.tensor([500.0, 532.0, 610.0], dtype=torch.float64)
+    d, grid = C.build_layers(case, cd)[0]
+    grids = torch.stack([grid, grid * 0.9 + 0.1, grid]).to("cuda:0")
+    sim = torcwa_b200.rcwa(freq=1 / lams, order=case["order"], L=case["L"], dtype=cd, device=torch.device("cuda:0"))
+    sim.add_input_layer(eps=case["eps_in"])
+    sim.set_incident_angle(inc_ang=0.1, azi_ang=0.2)
+    sim.add_layer(thickness=torch.tensor([300.0, 250.0, 300.0]), eps=grids)
+    sim.add_layer(thickness=50.0, eps=2.25)
+    sim.solve_global_smatrix()
+    tb = sim.S_parameters(orders=[[0, 0], [1, 0]], polarization="xx")
+    rb = sim.S_parameters(orders=[[0, 0], [1, 0]], polarization="pp", port="reflection")
+    assert tb.shape == (3, 2)
+    for b in range(3):
+        one = torcwa_b200.rcwa(freq=1 / lams[b], order=case["order"], L=case["L"], dtype=cd, device=torch.device("cuda:0"))
+        one.add_input_layer(eps=case["eps_in"])
+        one.set_incident_angle(inc_ang=0.1, azi_ang=0.2)
+        one.add_layer(thickness=[300.0, 250.0, 300.0][b], eps=grids[b])
+        one.add_layer(thickness=50.0, eps=2.25)
+        one.solve_global_smatrix()
+        t1 = one.S_parameters(orders=[[0, 0], [1, 0]], polarization="xx")
+        r1 = one.S_parameters(orders=[[0, 0], [1, 0]], polarization="pp", port="reflection")
+        assert t1.shape == (2,)
+        assert float((tb[b] - t1).abs().max()) < 1e-11
+        assert float((rb[b] - r1).abs().max()) < 1e-11
+
+
+def test_dtype_and_device_rules():
+    import torcwa_b200
+    with pytest.raises(RuntimeError):
+        torcwa_b200.rcwa(freq=1 / 532.0, order=[1, 1], L=[300.0, 300.0], device=torch.device("cpu"))
+    sim = torcwa_b200.rcwa(freq=1 / 532.0, order=[1, 1], L=[300.0, 300.0], dtype=torch.complex128, device=torch.device("cuda:0"))
+    sim.set_incident_angle(0.0, 0.0)
+    with pytest.raises(RuntimeError):     # complex64 material in a complex128 sim (SURVEY.md finding 9)
+        sim.add_layer(10.0, torch.ones(16, 16, dtype=torch.complex64, device="cuda:0"))
+    with pytest.raises(AttributeError):   # python int has no .dim() -- same failure mode as the reference
+        sim.add_layer(10.0, 2)
+    with pytest.warns(UserWarning):
+        torcwa_b200.rcwa(freq=1 / 532.0, order=[1, 1], L=[300.0, 300.0], dtype=torch.float32, device=torch.device("cuda:0"))

@@ -1,0 +1,79 @@
+"""Host logic of torcwa_b200.rcwa on the CPU, with the C ABI replaced by the torch test double
+(tests/fake_lib.py), against the reference's stored outputs and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fake_lib import cpu_double  # noqa: F401  (fixture)
+from oracle import cases as C
+from oracle.rcwa_oracle import OracleSim
+
+SMALL = ["ex1_o3", "ex1_o5", "stack_o3", "stack_o4x2", "fresnel_o2", "square_o4"]
+CPU = torch.device("cpu")
+
+
+def relfro(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_host_path_matches_reference_c128(cpu_double, name, golden_dir):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    sim = C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, **kw), C.CASES[name], torch.complex128)
+    sp = C.probe(sim)
+    assert np.abs(sp - g["sparams_c128"]).max() <= 1e-10 * np.abs(g["sparams_c128"]).max()
+    for k in range(4):
+        assert relfro(sim.S[k][:, g["S_cols_idx"]].numpy(), g["S_cols"][k]) <= 1e-10
+    if "S" in g:
+        for k in range(4):
+            assert relfro(sim.S[k].numpy(), g["S"][k]) <= 1e-10
+
+
+def test_half_space_blocks_match_oracle_dense(cpu_double):
+    case = C.CASES["stack_o3"]
+    sim = C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, **kw), case, torch.complex128)
+    ref = C.run_case(lambda **kw: OracleSim(**kw), case, torch.complex128)
+    for k in range(4):
+        assert relfro(sim.Sin[k].numpy(), ref.Sin[k].numpy()) < 1e-12
+        assert relfro(sim.Sout[k].numpy(), ref.Sout[k].numpy()) < 1e-12
+    assert relfro(sim.Vf.numpy(), ref.Vf.numpy()) < 1e-13
+    assert relfro(sim.Kx_norm.numpy(), ref.Kx_norm.numpy()) < 1e-15
+    # homogeneous lossy layer (index 3 of the stack): analytic 2x2-block path vs dense oracle
+    for li in (1, 3):
+        for k, blk in enumerate((sim.layer_S11[li], sim.layer_S21[li], sim.layer_S12[li], sim.layer_S22[li])):
+            assert relfro(blk.numpy(), ref.layer_S[li][k].numpy()) < 1e-11, (li, k)
+        assert relfro(sim.kz_norm[li].numpy(), ref.kz_norm[li].numpy()) < 1e-13
+
+
+def test_batched_shapes_and_values(cpu_double):
+    case = C.CASES["ex1_o3"]
+    cd = torch.complex128
+    lams = torch.tensor([500.0, 532.0], dtype=torch.float64)
+    d, grid = C.build_layers(case, cd)[0]
+    sim = cpu_double.rcwa(freq=1 / lams, order=case["order"], L=case["L"], dtype=cd, device=CPU)
+    sim.add_input_layer(eps=case["eps_in"])
+    sim.set_incident_angle(0.0, 0.0)
+    sim.add_layer(thickness=d, eps=grid)
+    sim.solve_global_smatrix()
+    t = sim.S_parameters(orders=[[0, 0], [1, 0], [0, 1]], polarization="xx")
+    assert t.shape == (2, 3) and sim.S[0].shape == (2, 98, 98)
+    ref = C.run_case(lambda **kw: OracleSim(**kw), case, cd)
+    assert abs(complex(t[1, 0]) - complex(ref.S_parameters([0, 0])[0])) < 1e-11
+
+
+def test_warnings_match_reference_messages(cpu_double):
+    sim = cpu_double.rcwa(freq=1 / 532.0, order=[1, 1], L=[300.0, 300.0], dtype=torch.complex128, device=CPU)
+    with pytest.warns(UserWarning, match="Invalid angle layer"):
+        sim.set_incident_angle(0.0, 0.0, angle_layer="sideways")
+    sim.solve_global_smatrix()
+    with pytest.warns(UserWarning, match="Invalid polarization"):
+        sim.S_parameters([0, 0], polarization="zz")
+    with pytest.warns(UserWarning, match="Invalid port"):
+        sim.S_parameters([0, 0], port="sideways")
+    with pytest.warns(UserWarning, match="Invalid propagation direction"):
+        sim.S_parameters([0, 0], direction="up")
+    o = torch.tensor([[9, 0]])
+    sim.S_parameters(o)
+    assert o.tolist() == [[1, 0]]           # out-of-range orders are clamped in place (rcwa.py:1115-1122)

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "librcwa_b200.so")
 EXPORTS = [
     "rcwa_b200_abi_version", "rcwa_gemm_scratch_bytes", "rcwa_convmat_workspace_bytes", "rcwa_convmat",
     "rcwa_zgemm_batched", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
-    "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_kz_branch", "rcwa_layer_smatrix_workspace_bytes",
+    "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_hessenberg", "rcwa_kz_branch", "rcwa_layer_smatrix_workspace_bytes",
     "rcwa_layer_smatrix", "rcwa_redheffer_workspace_bytes", "rcwa_redheffer", "rcwa_blockdiag_dense",
 ]
 
@@ -30,6 +30,7 @@ _SIGS = {
     "rcwa_pq_assemble": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "rcwa_eig_workspace_bytes": (_sz, [_i, _i]),
     "rcwa_eig": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "rcwa_hessenberg": (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),
     "rcwa_kz_branch": (_i, [_vp, _vp, _ll, _vp]),
     "rcwa_layer_smatrix_workspace_bytes": (_sz, [_i, _i]),
     "rcwa_layer_smatrix": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
@@ -197,6 +198,18 @@ def eig(A):
     _check(lib.rcwa_eig(_ptr(A), n, nb, _ptr(w), _ptr(V), _ptr(ws), nbytes, _ptr(info),
                         ctypes.c_void_p(_host_flag.data_ptr()), _stream()), "rcwa_eig")
     return w, V, info
+
+
+def hessenberg_(A):
+    """A [nb,n,n] -> Hessenberg in place; returns Z [nb,n,n] with A_in = Z H Z^H."""
+    lib = load()
+    _c128(A, "A")
+    nb, n = A.shape[0], A.shape[1]
+    Z = torch.empty_like(A)
+    nbytes = lib.rcwa_eig_workspace_bytes(n, nb)
+    ws = _ws(nbytes, A.device)
+    _check(lib.rcwa_hessenberg(_ptr(A), n, nb, _ptr(Z), _ptr(ws), nbytes, _stream()), "rcwa_hessenberg")
+    return Z
 
 
 def kz_branch(lam):

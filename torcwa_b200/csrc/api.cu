@@ -108,6 +108,15 @@ int rcwa_eig(void* A, int n, int nb, void* w, void* V, void* ws, size_t ws_bytes
     return cu(eig((cplx*)A, n, nb, (cplx*)w, (cplx*)V, (char*)ws, ws_bytes, info, (volatile int*)host_flag, S(stream)));
 }
 
+int rcwa_hessenberg(void* A, int n, int nb, void* Z, void* ws, size_t ws_bytes, void* stream) {
+    if (!A) return -1;
+    if (n <= 0) return -2;
+    if (nb <= 0) return -3;
+    if (!Z) return -4;
+    if (!ws || ws_bytes < eig_workspace_bytes(n, nb)) return -5;
+    return cu(hessenberg((cplx*)A, n, nb, (cplx*)Z, (char*)ws, ws_bytes, S(stream)));
+}
+
 int rcwa_kz_branch(const void* lam, void* kz, long long total, void* stream) {
     if (!lam) return -1;
     if (!kz) return -2;

@@ -36,12 +36,14 @@
 #define QR_W 64            // window size
 #define QR_LD 65           // shared-memory leading dimension (odd: conflict-free column access)
 #define QR_NS 16           // max simultaneous shifts / bulges
+#define QR_SMALL 48         // active blocks up to this size are Schur-factored directly in shared memory
+#define QR_SLICE_ROT 160    // rotations per launch of a small-block solve (time slice: keeps the batch in lockstep)
 #define QR_MAXSTALL 40     // sweeps without deflation before giving up on a matrix
 #define TV_NB 32           // eigenvector back-substitution block
 
 struct QrState {
     int lo, hi;          // active block [lo, hi] (inclusive); done when hi < 1
-    int phase;           // 0: start a new sweep (deflation scan + shifts); 1: chain in flight
+    int phase;           // 0: start a new sweep (deflation scan + shifts); 1: chain in flight; 2: small-block solve
     int p;               // window start of the next pass
     int nbulge;          // bulges currently in flight
     int nintro;          // bulges introduced so far in this sweep
@@ -50,7 +52,11 @@ struct QrState {
     int sweeps, passes;  // statistics
     int done, info;
     int hi_prev;
-    int pad;
+    int ss_i;            // small-block solve (phase 2): current bottom row of the unconverged part (local)
+    int ss_its;          //   QR iterations spent on the current eigenvalue
+    int ss_fresh;        //   1: U must be initialised to identity at the next slice
+    int small_solves;    // statistics
+    int pad0;
     int kpos[QR_NS];     // column of each bulge (leading first): bulge element is H[k+2][k]
     cplx shifts[QR_NS];
 };
@@ -162,6 +168,73 @@ DEV int tiny_hqr_eigs(int lane, int nlanes, cplx* T, int ldt, int m, cplx* wout)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Resumable single-shift QR (zlahqr with Schur vectors) on an m x m upper-Hessenberg block held in
+// shared memory (Hs, Us with leading dimension QR_LD; Us accumulates the unitary).  Runs at most
+// `budget` rotations, then returns; state (i, its) lives in QrState so the next launch continues.
+// Returns 1 when the block is upper triangular, 0 if more slices are needed, -1 on failure.
+DEV int small_schur_slice(const Cta& c, cplx* Hs, cplx* Us, int m, int* pi, int* pits, int budget) {
+    int i = *pi, its = *pits, used = 0;
+    while (i >= 1) {
+        // ---- deflation scan (uniform scalar code; every thread reads the same shared values)
+        int l;
+        for (l = i; l > 0; --l) {
+            cplx h10 = Hs[l * QR_LD + l - 1];
+            if (cis_zero(h10)) break;
+            double extra = 0.0;
+            if (l - 2 >= 0) extra += cabs1(Hs[(l - 1) * QR_LD + l - 2]);
+            if (l + 1 <= i) extra += cabs1(Hs[(l + 1) * QR_LD + l]);
+            if (negligible_subdiag(h10, Hs[(l - 1) * QR_LD + l - 1], Hs[l * QR_LD + l], Hs[(l - 1) * QR_LD + l], extra)) break;
+        }
+        CTA_SYNC();
+        if (l > 0 && c.tid == 0) Hs[l * QR_LD + l - 1] = C(0, 0);
+        CTA_SYNC();
+        if (l >= i) { --i; its = 0; continue; }
+        if (its > 60) { *pi = i; *pits = its; return -1; }
+        if (used + (i - l) > budget && used > 0) break;       // out of time: resume at the next launch
+        // ---- shift
+        cplx sig;
+        if (its == 10 || its == 30) sig = cadd(Hs[l * QR_LD + l], C(0.75 * cabs1(Hs[(l + 1) * QR_LD + l]), 0.0));
+        else if (its == 20 || its == 40) sig = cadd(Hs[i * QR_LD + i], C(0.75 * cabs1(Hs[i * QR_LD + i - 1]), 0.0));
+        else {
+            cplx a = Hs[(i - 1) * QR_LD + i - 1], b = Hs[(i - 1) * QR_LD + i], cc = Hs[i * QR_LD + i - 1], d = Hs[i * QR_LD + i];
+            cplx tr2 = cscale(csub(a, d), 0.5);
+            cplx disc = csqrt_(cadd(cmul(tr2, tr2), cmul(b, cc)));
+            cplx den1 = cadd(tr2, disc), den2 = csub(tr2, disc);
+            cplx den = (cabs2(den1) >= cabs2(den2)) ? den1 : den2;
+            sig = cis_zero(den) ? d : csub(d, cdiv(cmul(b, cc), den));
+        }
+        // ---- one QR sweep l..i with Schur-vector accumulation (full rows/columns of the block)
+        for (int k = l; k < i; ++k) {
+            cplx a, b;
+            if (k == l) { a = csub(Hs[k * QR_LD + k], sig); b = Hs[(k + 1) * QR_LD + k]; }
+            else { a = Hs[k * QR_LD + k - 1]; b = Hs[(k + 1) * QR_LD + k - 1]; }
+            double cs; cplx sn, r;
+            givens(a, b, cs, sn, r);
+            CTA_SYNC();
+            if (k > l && c.tid == 0) { Hs[k * QR_LD + k - 1] = r; Hs[(k + 1) * QR_LD + k - 1] = C(0, 0); }
+            for (int j = k + c.tid; j < m; j += c.nthreads) {
+                cplx x = Hs[k * QR_LD + j], y = Hs[(k + 1) * QR_LD + j];
+                Hs[k * QR_LD + j] = cadd(cscale(x, cs), cmul(sn, y));
+                Hs[(k + 1) * QR_LD + j] = csub(cscale(y, cs), cmul(cconj(sn), x));
+            }
+            CTA_SYNC();
+            const int rmax = (k + 2 < i) ? k + 2 : i;
+            for (int idx = c.tid; idx < (rmax + 1) + m; idx += c.nthreads) {
+                cplx* base = (idx <= rmax) ? (Hs + idx * QR_LD) : (Us + (idx - rmax - 1) * QR_LD);
+                cplx x = base[k], y = base[k + 1];
+                base[k] = cadd(cscale(x, cs), cmul(y, cconj(sn)));
+                base[k + 1] = csub(cscale(y, cs), cmul(x, sn));
+            }
+            CTA_SYNC();      // the next rotation reads the bulge this right-update just created
+        }
+        used += i - l;
+        ++its;
+    }
+    *pi = i; *pits = its;
+    return (i < 1) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // One window pass of the multishift QR for one matrix.  H: n x n (ldh), state in global memory.
 // Outputs: U (QR_W x QR_W, ld QR_W, global), three GEMM problems (rows, cols, Z) -- M = 0 if idle.
 // Shared memory: Hs[QR_W*QR_LD] + Us[QR_W*QR_LD] cplx + small scratch (see qr_pass_smem_bytes()).
@@ -226,7 +299,12 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
             return;
         }
         const int m = hi - lo + 1;
+        if (m <= QR_SMALL) {
+            // small active block: Schur-factor it directly in shared memory (time-sliced)
+            st.phase = 2; st.p = lo; st.ss_i = m - 1; st.ss_its = 0; st.ss_fresh = 1; st.small_solves++;
+        }
         const int ns = (m < QR_NS) ? m : QR_NS;
+        if (st.phase != 2) {
         // ---------------- shifts: eigenvalues of the trailing ns x ns block (warp 0)
         for (int idx = c.tid; idx < ns * ns; idx += c.nthreads) {
             int r = idx / ns, q = idx % ns;
@@ -252,9 +330,47 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
             for (int j = 0; j < ns; ++j) st.shifts[j] = cadd(H[(size_t)hi * ldh + hi], C(mag * ((j & 1) ? -1.0 : 1.0), mag * 0.5 * (j % 3 - 1)));
         }
         st.ns = ns; st.nintro = 0; st.nbulge = 0; st.p = lo; st.phase = 1; st.sweeps++;
+        }
 #ifdef RCWA_EMU
-        if (getenv("RCWA_EMU_DEBUG")) fprintf(stderr, "sweep %d: lo=%d hi=%d ns=%d stall=%d sub=%.3e\n", st.sweeps, lo, hi, ns, st.stall, cabs1(H[(size_t)hi * ldh + hi - 1]));
+        if (getenv("RCWA_EMU_DEBUG")) fprintf(stderr, "sweep %d: lo=%d hi=%d ns=%d stall=%d sub=%.3e small=%d\n", st.sweeps, lo, hi, ns, st.stall, cabs1(H[(size_t)hi * ldh + hi - 1]), st.small_solves);
 #endif
+    }
+
+    if (st.phase == 2) {
+        // ---------------- one time slice of the small-block solve on [lo, hi]
+        const int p2 = st.lo, m2 = st.hi - st.lo + 1;
+        for (int idx = c.tid; idx < m2 * m2; idx += c.nthreads) {
+            int r = idx / m2, q = idx % m2;
+            Hs[r * QR_LD + q] = H[(size_t)(p2 + r) * ldh + (p2 + q)];
+            Us[r * QR_LD + q] = st.ss_fresh ? C(r == q ? 1.0 : 0.0, 0.0) : Ug[r * QR_W + q];
+        }
+        CTA_SYNC();
+        int si = st.ss_i, sits = st.ss_its;
+        const int rc = small_schur_slice(c, Hs, Us, m2, &si, &sits, QR_SLICE_ROT);
+        st.ss_i = si; st.ss_its = sits; st.ss_fresh = 0;
+        for (int idx = c.tid; idx < m2 * m2; idx += c.nthreads) {
+            int r = idx / m2, q = idx % m2;
+            H[(size_t)(p2 + r) * ldh + (p2 + q)] = Hs[r * QR_LD + q];
+            Ug[r * QR_W + q] = Us[r * QR_LD + q];
+        }
+        if (c.tid == 0) {
+            st.passes++;
+            if (rc != 0) {
+                // finished (or failed): apply the accumulated unitary to the off-diagonal panels and Z
+                const int wend2 = st.hi + 1;
+                ZGemmProblem g;
+                g.A = Ug; g.lda = QR_W; g.B = H + (size_t)p2 * ldh + wend2; g.ldb = ldh; g.C = H + (size_t)p2 * ldh + wend2; g.ldc = ldh;
+                g.M = (n - wend2 > 0) ? m2 : 0; g.N = n - wend2; g.K = m2; *prob_rows = g;
+                g.A = H + p2; g.lda = ldh; g.B = Ug; g.ldb = QR_W; g.C = H + p2; g.ldc = ldh;
+                g.M = p2; g.N = m2; g.K = m2; *prob_cols = g;
+                g.A = Zm + p2; g.lda = ldz; g.B = Ug; g.ldb = QR_W; g.C = Zm + p2; g.ldc = ldz;
+                g.M = n; g.N = m2; g.K = m2; *prob_z = g;
+                st.phase = 0;
+                if (rc < 0) { st.done = 1; st.info = st.lo + si + 1; }
+            }
+            *stg = st;
+        }
+        return;
     }
 
     // ---------------- window [p, wend)
@@ -301,9 +417,10 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
             cplx a, b;
             if (rcol0[t] < 0) { a = csub(Hs[0], st.shifts[st.nintro]); b = Hs[1 * QR_LD + 0]; }
             else { a = Hs[r1 * QR_LD + rcol0[t]]; b = Hs[(r1 + 1) * QR_LD + rcol0[t]]; }
-            // a collapsed bulge / already-deflated top: rotating on round-off would scramble converged
-            // rows, so an element that is negligible against the local diagonal counts as zero
-            if (cabs1(b) <= RCWA_EPS * (cabs1(Hs[r1 * QR_LD + r1]) + cabs1(Hs[(r1 + 1) * QR_LD + r1 + 1]))) b = C(0, 0);
+            // (a, b) both at round-off level (the chain runs over an already converged spot): a rotation
+            // built from noise would scramble converged rows -> identity.  A tiny b next to a
+            // non-negligible a is kept: small bulges still carry the shifts.
+            if (cabs1(a) + cabs1(b) <= RCWA_EPS * (cabs1(Hs[r1 * QR_LD + r1]) + cabs1(Hs[(r1 + 1) * QR_LD + r1 + 1]))) { a = C(0, 0); b = C(0, 0); }
             double cs; cplx sn, r;
             givens(a, b, cs, sn, r);
             sc->cs[t] = cs; sc->sn[t] = sn;
@@ -318,9 +435,10 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
             cplx a, b;
             if (rcol0[t] < 0) { a = csub(Hs[0], st.shifts[st.nintro]); b = Hs[1 * QR_LD + 0]; }
             else { a = Hs[r1 * QR_LD + rcol0[t]]; b = Hs[(r1 + 1) * QR_LD + rcol0[t]]; }
-            // a collapsed bulge / already-deflated top: rotating on round-off would scramble converged
-            // rows, so an element that is negligible against the local diagonal counts as zero
-            if (cabs1(b) <= RCWA_EPS * (cabs1(Hs[r1 * QR_LD + r1]) + cabs1(Hs[(r1 + 1) * QR_LD + r1 + 1]))) b = C(0, 0);
+            // (a, b) both at round-off level (the chain runs over an already converged spot): a rotation
+            // built from noise would scramble converged rows -> identity.  A tiny b next to a
+            // non-negligible a is kept: small bulges still carry the shifts.
+            if (cabs1(a) + cabs1(b) <= RCWA_EPS * (cabs1(Hs[r1 * QR_LD + r1]) + cabs1(Hs[(r1 + 1) * QR_LD + r1 + 1]))) { a = C(0, 0); b = C(0, 0); }
             double cs; cplx sn, r;
             givens(a, b, cs, sn, r);
             sc->cs[t] = cs; sc->sn[t] = sn;
@@ -452,7 +570,7 @@ extern "C" int emu_qr(cplx* H, cplx* Z, int n, int max_passes, int* stats) {
         qr_pass_body(c, H, n, n, Z, n, &st, U.data(), &pr, &pc, &pz);
         emu_gemm(pr, 2); emu_gemm(pc, 0); emu_gemm(pz, 0);
     }
-    stats[0] = st.sweeps; stats[1] = st.passes; stats[2] = st.done;
+    stats[0] = st.sweeps; stats[1] = st.passes; stats[2] = st.done; stats[3] = st.small_solves;
     return st.done ? st.info : -1;
 }
 
@@ -818,13 +936,8 @@ size_t eig_workspace_bytes(int n, int nb) { return carve(nullptr, n, nb).total; 
 
 #define EK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
 
-cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t ws_bytes, int* info, volatile int* host_flag, cudaStream_t st) {
-    EigWs ws = carve(wsb, n, nb);
-    if (ws_bytes < ws.total) return cudaErrorInvalidValue;
+static cudaError_t hessenberg_phase(cplx* A, int n, int nb, const EigWs& ws, cudaStream_t st) {
     const long long ms = (long long)n * n;
-    const cplx one = C(1, 0), zero = C(0, 0);
-
-    // ---------------- phase 1: Hessenberg, Z accumulated alongside
     EK(set_identity(ws.Z, n, n, ms, nb, st));
     if (n >= 3) {
         const dim3 fgrid(ws.nbands, nb);
@@ -839,6 +952,25 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
         }
         EK(cudaGetLastError());
     }
+    return cudaSuccess;
+}
+
+// A -> H (upper Hessenberg, in place), Zout = accumulated reflectors (A_in = Z H Z^H)
+cudaError_t hessenberg(cplx* A, int n, int nb, cplx* Zout, char* wsb, size_t ws_bytes, cudaStream_t st) {
+    EigWs ws = carve(wsb, n, nb);
+    if (ws_bytes < ws.total) return cudaErrorInvalidValue;
+    EK(hessenberg_phase(A, n, nb, ws, st));
+    return cudaMemcpyAsync(Zout, ws.Z, sizeof(cplx) * (size_t)n * n * nb, cudaMemcpyDeviceToDevice, st);
+}
+
+cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t ws_bytes, int* info, volatile int* host_flag, cudaStream_t st) {
+    EigWs ws = carve(wsb, n, nb);
+    if (ws_bytes < ws.total) return cudaErrorInvalidValue;
+    const long long ms = (long long)n * n;
+    const cplx one = C(1, 0), zero = C(0, 0);
+
+    // ---------------- phase 1: Hessenberg, Z accumulated alongside
+    EK(hessenberg_phase(A, n, nb, ws, st));
 
     // ---------------- phase 2: QR passes (host enqueues, polls the pinned flag every `poll` passes)
     qr_init_kernel<<<(nb + 127) / 128, 128, 0, st>>>(ws.states, n, nb);

@@ -44,6 +44,7 @@ cudaError_t lu_solve_right(const cplx* LU, long long lustride, int n, int lda, c
 
 // ---- eig.cu
 size_t eig_workspace_bytes(int n, int nb);
+cudaError_t hessenberg(cplx* A, int n, int nb, cplx* Zout, char* ws, size_t ws_bytes, cudaStream_t st);
 cudaError_t eig(cplx* A, int n, int nb, cplx* w, cplx* V, char* ws, size_t ws_bytes, int* info, volatile int* host_flag, cudaStream_t st);
 
 }  // namespace rcwa

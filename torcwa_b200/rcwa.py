@@ -29,6 +29,11 @@ pi = 3.141592652589793
 
 _C = torch.complex128
 
+# Test hook only: tests/fake_lib.py swaps `_lib` for a torch-on-CPU double of the C ABI to exercise
+# this file's host logic without a GPU, and sets this flag so the constructor accepts a CPU device.
+# With the real `_lib` a non-CUDA tensor is rejected by every wrapper, so there is no CPU fallback.
+_TEST_ALLOW_NON_CUDA = False
+
 
 def vf_inverse_diagonals(kx, ky):
     """Four diagonals of Vf^-1 (free-space E->H matrix, torcwa/rcwa.py:1143-1147) as [B,4,N]."""
@@ -54,7 +59,7 @@ class rcwa:
         if device is None:
             device = torch.device('cuda')
         self._device = torch.device(device)
-        if self._device.type != 'cuda':
+        if self._device.type != 'cuda' and not _TEST_ALLOW_NON_CUDA:
             raise RuntimeError('torcwa_b200 runs on CUDA devices only (no CPU path); got device=%s' % device)
         _lib.load()   # fail loudly, now, if the CUDA library is missing
 
@@ -73,7 +78,9 @@ class rcwa:
         self._B = f.numel() if self._batched else 1
         self.freq = torch.as_tensor(freq, dtype=self._dtype, device=self._device)
         self.omega = 2 * pi * freq                     # raw argument, as the reference (rcwa.py:61)
-        self._omega64 = torch.as_tensor(self.omega).to(device=self._device).real.to(torch.float64).reshape(-1)
+        om = self.omega
+        om = om.to(self._device).real.to(torch.float64) if isinstance(om, torch.Tensor) else torch.tensor(om, dtype=torch.float64, device=self._device)
+        self._omega64 = om.reshape(-1)
         self._freq128 = self.freq.to(_C).reshape(-1)   # widened *after* the cast to the sim dtype (rcwa.py:60)
         self.L = L
         self.order = order
@@ -101,7 +108,9 @@ class rcwa:
     # ------------------------------------------------------------------ helpers
     def _b(self, v):
         """scalar or [B] -> complex128 [B] on the device."""
-        t = torch.as_tensor(v, device=self._device).to(_C).reshape(-1)
+        # python scalars must be widened directly: torch.as_tensor(0.3) would round to float32 first
+        t = v.to(device=self._device, dtype=_C) if isinstance(v, torch.Tensor) else torch.tensor(v, dtype=_C, device=self._device)
+        t = t.reshape(-1)
         if t.numel() == 1:
             t = t.expand(self._B)
         elif t.numel() != self._B:
@@ -218,7 +227,8 @@ class rcwa:
         he, hm = self._is_homogeneous(eps), self._is_homogeneous(mu)
         B, N = self._B, self.order_N
         kx, ky = self._kx, self._ky
-        thick = torch.as_tensor(thickness, device=self._device).to(torch.float64).reshape(-1)
+        thick = (thickness.to(device=self._device, dtype=torch.float64) if isinstance(thickness, torch.Tensor)
+                 else torch.tensor(thickness, dtype=torch.float64, device=self._device)).reshape(-1)
         thick = (thick.expand(B) if thick.numel() == 1 else thick).contiguous()
         omega = (self._omega64.expand(B) if self._omega64.numel() == 1 else self._omega64).contiguous()
 
