@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- layers/sec of the RCWA hot path on BASELINE.json configs[1]
+(order 15x15, 1 patterned layer, 512-wavelength sweep, complex64 API) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--points P] [--order O]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's own CPU path (oracle port), host cores
+
+One "step" = one chunk of P wavelengths of the 512-point sweep (Example1 cell, a-Si:H pillar with a
+synthetic linear dispersion, SiO2 half space) through
+    rcwa() -> add_input_layer -> set_incident_angle -> add_layer -> solve_global_smatrix -> S_parameters
+i.e. Fourier factorisation -> eigendecomposition -> layer S-matrix -> Redheffer product with the
+substrate -> t_xx(0,0).  Every step takes the next chunk of wavelengths (new inputs, working set
+>> L2).  `value` times steps whose inputs are already resident in HBM; `e2e` times the same steps
+fed from pinned HOST buffers with the S-parameters read back.  Multi-GPU: ranks take disjoint
+contiguous slices of the sweep (weak scaling: P points per rank per step), the only collective is
+the final all_gather of the S-parameters.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from oracle import cases as C  # noqa: E402  (input builders only; the oracle itself is used by the reference legs)
+
+N_SWEEP = 512
+LAM0, LAM1 = 400.0, 700.0
+
+
+def eps_si(lam):
+    """Synthetic linear dispersion through the two a-Si:H points of oracle/cases.py."""
+    a, b = C.SI_EPS[532.0], C.SI_EPS[650.0]
+    return a + (lam - 532.0) / (650.0 - 532.0) * (b - a)
+
+
+def sweep_inputs(order):
+    case = dict(C.CASES["ex1_o15"])
+    case["order"] = [order, order]
+    mask = C.rectangle_grid(300.0, 300.0, 300, 300, 180.0, 100.0, 150.0, 150.0, 0.0, 1000.0, torch.float32)
+    lams = torch.linspace(LAM0, LAM1, N_SWEEP, dtype=torch.float32)
+    return case, mask, lams
+
+
+def make_grids(mask, lams):
+    e = torch.tensor([eps_si(float(l)) for l in lams], dtype=torch.complex64)
+    return mask[None] * e[:, None, None] + (1.0 - mask)[None]
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- B200 arm
+def run_step(grids_dev, freq_dev, case, device):
+    import torcwa_b200
+    sim = torcwa_b200.rcwa(freq=freq_dev, order=case["order"], L=case["L"], dtype=torch.complex64, device=device)
+    sim.add_input_layer(eps=case["eps_in"])
+    sim.set_incident_angle(inc_ang=0.0, azi_ang=0.0)
+    sim.add_layer(thickness=300.0, eps=grids_dev)
+    sim.solve_global_smatrix()
+    return sim.S_parameters(orders=[0, 0], direction="forward", port="transmission", polarization="xx", ref_order=[0, 0])
+
+
+def count_my_launches(fn):
+    """Kernels of librcwa_b200.so launched by one step (CUPTI through torch.profiler)."""
+    mine = ("zgemm_grouped", "fill_strided", "dft_rows", "dft_cols", "toeplitz", "pq_assemble", "kz_branch", "layer_form", "layer_finish",
+            "blockdiag_dense", "identity_kernel", "axpby", "lu_panel", "lu_perm", "lu_colswap", "trsm_rows", "gather_cols", "hess_step",
+            "hess_fused", "hess_advance", "hb_col", "hb_matvec", "hb_zero", "bd_left_mul", "bd_right_mul", "bd_add", "qr_pass", "qr_init", "qr_count", "qr_finish", "qr_stats", "diag_extract", "tnorm", "trevc_block",
+            "colnorm", "colscale")
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        per = {}
+        for e in prof.events():
+            nm = e.name
+            for m in mine:
+                if m in nm:
+                    d = per.setdefault(m, [0, 0.0])
+                    d[0] += 1
+                    d[1] += float(getattr(e, "device_time", 0.0) or getattr(e, "cuda_time", 0.0) or 0.0)
+                    break
+        return sum(v[0] for v in per.values()), per
+    except Exception as ex:        # CUPTI missing: report honestly that it was not counted
+        return None, {"error": str(ex)}
+
+
+def bench_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run)" % (args.gpus, world))
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    case, mask, lams = sweep_inputs(args.order)
+    P = args.points
+    # this rank's slice of the sweep; chunks of P wavelengths, cycled if K*P exceeds the slice
+    per_rank = N_SWEEP // world
+    my = torch.arange(rank * per_rank, (rank + 1) * per_rank)
+    n_chunks = max(per_rank // P, 1)
+    grids_host = make_grids(mask, lams[my]).pin_memory()                 # [per_rank,300,300] c64, pinned
+    freq_host = (1.0 / lams[my]).pin_memory()
+    grids_res = grids_host.to(device)                                    # resident copy for the device-timed leg
+    freq_res = freq_host.to(device)
+
+    def chunk(s):
+        c = (s % n_chunks) * P
+        return slice(c, c + P)
+
+    def step_resident(s):
+        sl = chunk(s)
+        return run_step(grids_res[sl], freq_res[sl], case, device)
+
+    def step_e2e(s):
+        sl = chunk(s)
+        g = grids_host[sl].to(device, non_blocking=True)
+        f = freq_host[sl].to(device, non_blocking=True)
+        out = run_step(g, f, case, device)
+        if world > 1:
+            full = torch.empty((world,) + tuple(torch.view_as_real(out).shape), dtype=torch.float32, device=device)
+            dist.all_gather_into_tensor(full, torch.view_as_real(out).contiguous())
+            out = full
+        return out.cpu()                                                  # device->host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, K, W, s0=0):
+        for s in range(W):
+            fn(s0 + s)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(K):
+            fn(s0 + W + s)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    K, W = args.steps, args.warmup
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms_res = timed(step_resident, K, W)
+    clk = clocks.stop()
+    ms_e2e = timed(step_e2e, K, 1, s0=K + W)
+    layers_per_step = P * world                                           # one patterned layer per design point
+    value = layers_per_step * K / (ms_res * 1e-3)
+    e2e_value = layers_per_step * K / (ms_e2e * 1e-3)
+
+    out = None
+    if rank == 0:
+        n = 2 * (2 * args.order + 1) ** 2
+        # ---- stage split and roofline of the eigen stage (untimed extra step on rank 0)
+        from torcwa_b200 import _lib
+        launches, per_kernel = count_my_launches(lambda: step_resident(0))
+        sim_stage = stage_times(case, grids_res[chunk(0)], freq_res[chunk(0)], device)
+        b_eig = 16.0 * (n ** 3 / 3.0 + 2.0 * n * n)                      # SURVEY.md 8d, s = 16 (fp64 internals)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+        dom = max(per_kernel.items(), key=lambda kv: kv[1][1])[0] if launches else None
+        t_h = sim_stage["hessenberg_alone_ms"]
+        achieved_h = P * b_eig / (t_h * 1e-3) / 1e9
+        achieved_eig = P * b_eig / (sim_stage["eig_ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "hb_matvec_kernel (streaming mat-vec of the blocked Hessenberg phase of rcwa_eig; phase timed alone with CUDA events)",
+                "achieved": achieved_h, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_h / hbm_peak,
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_matrix": b_eig,
+                "eig_stage_whole": {"achieved": achieved_eig, "frac": achieved_eig / hbm_peak, "ms_per_batch": sim_stage["eig_ms"]}}
+        cpu = cpu_baseline(args.order, args.ref_dtype) if args.cpu_baseline else None
+        out = {
+            "metric": "layers/sec (order %dx%d, c64)" % (args.order, args.order), "value": value, "unit": "layers/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 (complex128 internals behind the complex64 API; results rounded to c64)",
+            "data": "synthetic (Example1 cell, linear a-Si:H dispersion, 512 wavelengths 400-700 nm)",
+            "config": {"workload": "BASELINE configs[1]: order %dx%d (n=%d), 1 patterned layer + SiO2 half space, 512-wavelength sweep, complex64 API"
+                                   % (args.order, args.order, n), "points_per_step_per_gpu": P, "layers_per_point": 1,
+                       "l2": "working set per step >> 126 MB L2; every step takes new wavelengths", "parallelism": "dp%d (sweep sharded, final all_gather)" % world},
+            "e2e": {"value": e2e_value, "unit": "layers/s", "h2d_bytes_per_step": int(P * (300 * 300 * 8 + 4)), "d2h_bytes_per_step": int(P * world * 8),
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": (launches * K) if launches else None,
+            "gpu_launches_per_step": launches,
+            "clocks": clk,
+            "roofline": roof,
+            "stage_ms_per_batch": sim_stage,
+            "dominant_kernel_by_time": dom,
+            "kernel_time_share": {k: round(v[1] / max(sum(x[1] for x in per_kernel.values()), 1e-9), 4) for k, v in
+                                  sorted(per_kernel.items(), key=lambda kv: -kv[1][1])[:8]} if launches else per_kernel,
+            "kernel_launches_and_avg_us": {k: [v[0], round(v[1] / max(v[0], 1), 1)] for k, v in
+                                           sorted(per_kernel.items(), key=lambda kv: -kv[1][1])[:8]} if launches else None,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def stage_times(case, grids, freq, device):
+    """CUDA-event timing of the stages of one batch through the C ABI wrappers (rank 0, untimed region)."""
+    import torcwa_b200
+    from torcwa_b200 import _lib
+    P = grids.shape[0]
+    sim = torcwa_b200.rcwa(freq=freq, order=case["order"], L=case["L"], dtype=torch.complex64, device=device)
+    sim.add_input_layer(eps=case["eps_in"])
+    sim.set_incident_angle(0.0, 0.0)
+    o = case["order"][0]
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+    res = {}
+    for _ in range(2):
+        e = [ev()]
+        E = _lib.convmat(grids, o, o, nb=P); e.append(ev())
+        eta, _i = _lib.inverse(E); e.append(ev())
+        Pm, Q = _lib.pq_assemble(eta, E, sim._kx, sim._ky, mu_scalar=torch.ones(P, dtype=torch.complex128, device=device))
+        A = _lib.zgemm(Pm, Q); e.append(ev())
+        H = A.clone(); e.append(ev())
+        _lib.hessenberg_(H); e.append(ev())
+        del H
+        lam, Wv, info = _lib.eig(A); e.append(ev())
+        kz = _lib.kz_branch(lam)
+        om = sim._omega64.expand(P).contiguous()
+        th = torch.full((P,), 300.0, dtype=torch.float64, device=device)
+        S11, S21, _i = _lib.layer_smatrix(Wv, kz, Q, sim._Vf_inv, om, th); e.append(ev())
+        _lib.redheffer_bdleft(sim._Sin, [S11, S21, S21, S11]); e.append(ev())
+        torch.cuda.synchronize()
+        names = ["convmat_ms", "inv_eps_ms", "pq_and_product_ms", "_clone", "hessenberg_alone_ms", "eig_ms", "layer_smatrix_ms", "redheffer_ms"]
+        res = {names[i]: e[i].elapsed_time(e[i + 1]) for i in range(len(names)) if not names[i].startswith("_")}
+        st = _lib.last_eig_stats.cpu().numpy()
+        res["qr_sweeps_per_matrix"] = float(st[:, 0].mean())
+        res["qr_passes_max"] = int(st[:, 1].max())
+        res["eig_info_max"] = int(info.abs().max())
+    return res
+
+
+# ------------------------------------------------------------------------------------------- CPU legs
+def oracle_point(order, cdtype, lam=532.0):
+    """One design point (one patterned layer) through the oracle = the reference's dense CPU algebra."""
+    from oracle.rcwa_oracle import OracleSim
+    case = dict(C.CASES["ex1_o15"])
+    case["order"] = [order, order]
+    case["lam"] = lam
+    t0 = time.perf_counter()
+    sim = C.run_case(lambda **kw: OracleSim(**kw), case, cdtype)
+    t = sim.S_parameters([0, 0])
+    return time.perf_counter() - t0, complex(t[0])
+
+
+REF_DTYPE_NOTE = ("reference CPU arithmetic timed in complex128: its complex64 path hits an MKL cgetri/cgetrf slow path on the 4N x 4N "
+                  "coupling matrix (51 s/point on 8 cores in the build container, 455 s/point on this pool's 128-thread host, both measured), "
+                  "so complex128 (17 s/point on 8 cores) is the FASTER, i.e. more favourable, reference")
+
+
+def ref_threads():
+    """MKL/LAPACK at this size (4N = 3844) gets SLOWER with very many threads: on this pool's 128-thread
+    host the same design point took 358.8 s with 128 threads (measured 2026-09-25) against 17 s with 8
+    threads in the build container.  The CPU legs therefore use at most 16 threads -- the setting that
+    favours the reference -- and say so in their JSON."""
+    return min(os.cpu_count() or 1, 16)
+
+
+def cpu_baseline(order, ref_dtype="c128"):
+    torch.set_num_threads(ref_threads())
+    cd = torch.complex128 if ref_dtype == "c128" else torch.complex64
+    dt, _ = oracle_point(order, cd)
+    return {"value": 1.0 / dt, "unit": "layers/s", "cores": torch.get_num_threads(), "host_cores": os.cpu_count(), "kind": "port",
+            "sample": "1 design point (1 patterned layer, order %dx%d, %s) through oracle/rcwa_oracle.py (the reference's dense algebra on torch/MKL), "
+                      "%d threads (of %d; 128 threads measured 20x slower), %.1f s. %s"
+                      % (order, order, ref_dtype, torch.get_num_threads(), os.cpu_count(), dt, REF_DTYPE_NOTE if ref_dtype == "c128" else "")}
+
+
+def bench_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(ref_threads())
+    K, W = args.steps, min(args.warmup, 1)
+    budget = args.ref_budget_s
+    t_start = time.perf_counter()
+    lams = np.linspace(LAM0, LAM1, N_SWEEP)
+    cd = torch.complex128 if args.ref_dtype == "c128" else torch.complex64
+    for s in range(W):
+        oracle_point(args.order, cd, float(lams[s]))
+    done, total = 0, 0.0
+    for s in range(K):
+        dt, _ = oracle_point(args.order, cd, float(lams[(W + s) % N_SWEEP]))
+        total += dt
+        done += 1
+        if time.perf_counter() - t_start + dt > budget:
+            break
+    value = done / total
+    n = 2 * (2 * args.order + 1) ** 2
+    print(json.dumps({
+        "impl": "reference", "metric": "layers/sec (order %dx%d, c64)" % (args.order, args.order), "value": value, "unit": "layers/s",
+        "n_gpus": args.gpus, "steps": done, "requested_steps": K, "warmup": W, "ms_per_step": 1e3 * total / done, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.ref_dtype, "data": "synthetic (same cell and sweep as the B200 arm)",
+        "note": REF_DTYPE_NOTE if args.ref_dtype == "c128" else "",
+        "config": {"workload": "BASELINE configs[1] unit: order %dx%d (n=%d), 1 patterned layer + SiO2 half space, one wavelength per step"
+                               % (args.order, args.order, n), "points_per_step": 1},
+        "cpu_baseline": {"value": value, "unit": "layers/s", "cores": torch.get_num_threads(), "host_cores": os.cpu_count(), "kind": "port",
+                         "sample": "%d x 1 design point through oracle/rcwa_oracle.py on %d torch threads" % (done, torch.get_num_threads())},
+        "e2e": {"value": value, "unit": "layers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=32, help="wavelengths per step per GPU")
+    ap.add_argument("--order", type=int, default=15)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0)
+    ap.add_argument("--ref-dtype", default="c128", choices=["c64", "c128"], help="arithmetic of the CPU reference legs (see REF_DTYPE_NOTE)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_b200(args)
+
+
+if __name__ == "__main__":
+    main()

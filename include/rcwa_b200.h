@@ -87,6 +87,9 @@ int rcwa_pq_assemble(const void* eta, const void* E, const void* Mc, const void*
 size_t rcwa_eig_workspace_bytes(int n, int nb);
 int rcwa_eig(void* A, int n, int nb, void* w, void* V, void* ws, size_t ws_bytes, int* info,
              void* host_flag, void* stream);
+/* Diagnostics of the last rcwa_eig that used workspace `ws`: out[4*b..] = {QR sweeps, window passes,
+ * AED windows, info} of matrix b (device int32 [nb,4]). */
+int rcwa_eig_stats(const void* ws, int n, int nb, int* out, void* stream);
 /* First phase of rcwa_eig on its own (profiling / building block): A[b] -> H[b] upper Hessenberg in
  * place, Z[b] unitary with A_in = Z H Z^H.  Workspace as for rcwa_eig.  This is the HBM-bound
  * streaming kernel of the eigen stage (one fused pass over [A; Z] per column). */
@@ -111,6 +114,13 @@ int rcwa_layer_smatrix(const void* W, const void* kz, const void* Q, const void*
 size_t rcwa_redheffer_workspace_bytes(int n, int nb);
 int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const out[4],
                    int nb, int n, void* ws, int* info, void* stream);
+
+/* Same product when the LEFT factor is a half-space / homogeneous-layer S-matrix, i.e. each of its four
+ * blocks is itself four diagonals: Sm_bd[k] = [nb,4,N] (order 11,12,21,22 inside each block; the
+ * reference builds these densely, rcwa.py:1157-1164).  Six of the eight GEMMs become O(n^2) row/column
+ * combinations.  n = 2N; workspace as rcwa_redheffer. */
+int rcwa_redheffer_bdleft(const void* const Sm_bd[4], const void* const Sn[4], void* const out[4],
+                          int nb, int N, void* ws, int* info, void* stream);
 
 /* dense [nb,2N,2N] from four diagonals d4 [nb,4,N] (order 11,12,21,22): half-space and
  * homogeneous-layer blocks (rcwa.py:1157-1181, :1206-1222). */

@@ -81,6 +81,10 @@ def redheffer(Sm, Sn):
     return [Y1 @ Sm[0], Sm[1] + Sm[3] @ (Y2 @ Sm[0]), Sn[2] + Y1 @ G, Sm[3] @ (Sn[3] + Y2 @ G)], torch.zeros(Sm[0].shape[0], dtype=torch.int32)
 
 
+def redheffer_bdleft(Sm_bd, Sn):
+    return redheffer([blockdiag_dense(x) for x in Sm_bd], Sn)
+
+
 @pytest.fixture
 def cpu_double(monkeypatch):
     import sys

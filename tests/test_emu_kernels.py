@@ -49,7 +49,7 @@ def schur_and_vectors(emu, A):
     else:
         H, Z = A.copy(), np.eye(n, dtype=complex)
     H, Z = np.ascontiguousarray(H), np.ascontiguousarray(Z)
-    stats = np.zeros(4, np.int32)
+    stats = np.zeros(8, np.int32)
     info = emu.emu_qr(P(H), P(Z), n, 10 ** 6, P(stats))
     assert info == 0
     T = np.triu(H)

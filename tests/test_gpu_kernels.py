@@ -145,6 +145,19 @@ def test_redheffer_vs_oracle():
         assert rel(out2[k][1].cpu(), ref2[k]) < 1e-11
 
 
+def test_redheffer_bdleft_vs_dense():
+    from torcwa_b200 import _lib
+    case, sim = _oracle_layer("stack_o3")
+    d = dev()
+    N = sim.order_N
+    bd = [rnd(2, 4, N, seed=20 + k) * 0.3 for k in range(4)]
+    Sn = [torch.stack([s, 0.5 * s]).to(d).contiguous() for s in sim.layer_S[0]]
+    out, info = _lib.redheffer_bdleft(bd, Sn)
+    ref, _ = _lib.redheffer([_lib.blockdiag_dense(x) for x in bd], Sn)
+    for k in range(4):
+        assert rel(out[k], ref[k]) < 1e-12
+
+
 def test_blockdiag_dense():
     from torcwa_b200 import _lib
     d4 = rnd(2, 4, 9, seed=11)

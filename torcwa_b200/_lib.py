@@ -14,8 +14,8 @@ LIB_PATH = os.path.join(_HERE, "librcwa_b200.so")
 EXPORTS = [
     "rcwa_b200_abi_version", "rcwa_gemm_scratch_bytes", "rcwa_convmat_workspace_bytes", "rcwa_convmat",
     "rcwa_zgemm_batched", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
-    "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_hessenberg", "rcwa_kz_branch", "rcwa_layer_smatrix_workspace_bytes",
-    "rcwa_layer_smatrix", "rcwa_redheffer_workspace_bytes", "rcwa_redheffer", "rcwa_blockdiag_dense",
+    "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_eig_stats", "rcwa_hessenberg", "rcwa_kz_branch", "rcwa_layer_smatrix_workspace_bytes",
+    "rcwa_layer_smatrix", "rcwa_redheffer_workspace_bytes", "rcwa_redheffer", "rcwa_redheffer_bdleft", "rcwa_blockdiag_dense",
 ]
 
 _vp, _i, _ll, _d, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_size_t
@@ -30,12 +30,14 @@ _SIGS = {
     "rcwa_pq_assemble": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "rcwa_eig_workspace_bytes": (_sz, [_i, _i]),
     "rcwa_eig": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "rcwa_eig_stats": (_i, [_vp, _i, _i, _vp, _vp]),
     "rcwa_hessenberg": (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),
     "rcwa_kz_branch": (_i, [_vp, _vp, _ll, _vp]),
     "rcwa_layer_smatrix_workspace_bytes": (_sz, [_i, _i]),
     "rcwa_layer_smatrix": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "rcwa_redheffer_workspace_bytes": (_sz, [_i, _i]),
     "rcwa_redheffer": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "rcwa_redheffer_bdleft": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "rcwa_blockdiag_dense": (_i, [_vp, _i, _i, _vp, _vp]),
 }
 
@@ -197,7 +199,14 @@ def eig(A):
         _host_flag = torch.zeros(16, dtype=torch.int32).pin_memory()
     _check(lib.rcwa_eig(_ptr(A), n, nb, _ptr(w), _ptr(V), _ptr(ws), nbytes, _ptr(info),
                         ctypes.c_void_p(_host_flag.data_ptr()), _stream()), "rcwa_eig")
+    global last_eig_stats
+    stats = torch.empty((nb, 4), dtype=torch.int32, device=A.device)
+    _check(lib.rcwa_eig_stats(_ptr(ws), n, nb, _ptr(stats), _stream()), "rcwa_eig_stats")
+    last_eig_stats = stats
     return w, V, info
+
+
+last_eig_stats = None
 
 
 def hessenberg_(A):
@@ -248,6 +257,22 @@ def redheffer(Sm, Sn):
     a_n = arr(*[t.data_ptr() for t in (_c128(x, "Sn") for x in Sn)])
     a_o = arr(*[t.data_ptr() for t in out])
     _check(lib.rcwa_redheffer(a_m, a_n, a_o, nb, n, _ptr(ws), _ptr(info), _stream()), "rcwa_redheffer")
+    return out, info
+
+
+def redheffer_bdleft(Sm_bd, Sn):
+    """Star product with a 2x2-block-diagonal left factor: Sm_bd = four [nb,4,N] tensors, Sn dense."""
+    lib = load()
+    nb, n = Sn[0].shape[0], Sn[0].shape[1]
+    out = [torch.empty_like(Sn[0]) for _ in range(4)]
+    info = torch.zeros((nb,), dtype=torch.int32, device=Sn[0].device)
+    ws = _ws(lib.rcwa_redheffer_workspace_bytes(n, nb), Sn[0].device)
+    arr = ctypes.c_void_p * 4
+    keep = [_c128(x.contiguous(), "Sm_bd") for x in Sm_bd]
+    a_m = arr(*[t.data_ptr() for t in keep])
+    a_n = arr(*[t.data_ptr() for t in (_c128(x, "Sn") for x in Sn)])
+    a_o = arr(*[t.data_ptr() for t in out])
+    _check(lib.rcwa_redheffer_bdleft(a_m, a_n, a_o, nb, n // 2, _ptr(ws), _ptr(info), _stream()), "rcwa_redheffer_bdleft")
     return out, info
 
 

@@ -108,6 +108,14 @@ int rcwa_eig(void* A, int n, int nb, void* w, void* V, void* ws, size_t ws_bytes
     return cu(eig((cplx*)A, n, nb, (cplx*)w, (cplx*)V, (char*)ws, ws_bytes, info, (volatile int*)host_flag, S(stream)));
 }
 
+int rcwa_eig_stats(const void* ws, int n, int nb, int* out, void* stream) {
+    if (!ws) return -1;
+    if (n <= 0) return -2;
+    if (nb <= 0) return -3;
+    if (!out) return -4;
+    return cu(eig_stats((const char*)ws, n, nb, out, S(stream)));
+}
+
 int rcwa_hessenberg(void* A, int n, int nb, void* Z, void* ws, size_t ws_bytes, void* stream) {
     if (!A) return -1;
     if (n <= 0) return -2;
@@ -230,6 +238,56 @@ int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const
     GEMM(Y2, G, one, D);
     GEMM(Sm22, D, zero, O22);
 #undef GEMM
+    return 0;
+}
+
+int rcwa_redheffer_bdleft(const void* const Sm_bd[4], const void* const Sn[4], void* const out[4], int nb, int N, void* ws, int* info, void* stream) {
+    if (!Sm_bd) return -1;
+    if (!Sn) return -2;
+    if (!out) return -3;
+    for (int k = 0; k < 4; ++k) {
+        if (!Sm_bd[k]) return -1;
+        if (!Sn[k]) return -2;
+        if (!out[k]) return -3;
+    }
+    if (nb <= 0) return -4;
+    if (N <= 0) return -5;
+    if (!ws) return -6;
+    if (!info) return -7;
+    cudaStream_t st = S(stream);
+    const int n = 2 * N;
+    const long long ms = (long long)n * n;
+    const size_t mat = align256((size_t)ms * nb * sizeof(cplx));
+    char* p = (char*)ws;
+    cplx* D = (cplx*)p; p += mat;
+    cplx* Y1 = (cplx*)p; p += mat;
+    cplx* Y2 = (cplx*)p; p += mat;
+    cplx* G = (cplx*)p; p += mat;
+    cplx* T = (cplx*)p; p += mat;
+    int* ipiv = (int*)p; p += align256((size_t)n * nb * sizeof(int));
+    int* perm = (int*)p; p += align256((size_t)n * nb * sizeof(int));
+    ZGemmProblem* gs = (ZGemmProblem*)p;
+    const cplx *m11 = (const cplx*)Sm_bd[0], *m21 = (const cplx*)Sm_bd[1], *m12 = (const cplx*)Sm_bd[2], *m22 = (const cplx*)Sm_bd[3];
+    const cplx *Sn11 = (const cplx*)Sn[0], *Sn21 = (const cplx*)Sn[1], *Sn12 = (const cplx*)Sn[2], *Sn22 = (const cplx*)Sn[3];
+    cplx *O11 = (cplx*)out[0], *O21 = (cplx*)out[1], *O12 = (cplx*)out[2], *O22 = (cplx*)out[3];
+    const cplx one = C(1, 0), zero = C(0, 0), mone = C(-1, 0);
+    const size_t bytes = (size_t)ms * nb * sizeof(cplx);
+    // D = I - Sm12 Sn21          (Sm12 is four diagonals: an O(n^2) row combination, not a GEMM)
+    CK(set_identity(D, n, n, ms, nb, st));
+    CK(bd_left_mul(m12, Sn21, nb, N, n, mone, one, D, st));
+    CK(lu_factor(D, ms, n, n, nb, ipiv, perm, info, gs, st));
+    CK(lu_solve_right(D, ms, n, n, perm, Sn11, ms, n, n, Y1, ms, n, nb, gs, st));      // Y1 = Sn11 D^-1
+    CK(lu_solve_right(D, ms, n, n, perm, Sn21, ms, n, n, Y2, ms, n, nb, gs, st));      // Y2 = Sn21 D^-1
+    CK(bd_left_mul(m12, Sn22, nb, N, n, one, zero, G, st));                             // G = Sm12 Sn22
+    CK(bd_right_mul(m11, Y1, nb, N, n, one, zero, O11, st));                            // S11 = Y1 Sm11
+    CK(cudaMemcpyAsync(O12, Sn12, bytes, cudaMemcpyDeviceToDevice, st));                // S12 = Sn12 + Y1 G
+    CK(zgemm_strided(OP_N, OP_N, n, n, n, one, Y1, n, ms, G, n, ms, one, O12, n, ms, nb, gs, st));
+    CK(bd_right_mul(m11, Y2, nb, N, n, one, zero, T, st));                              // S21 = Sm21 + Sm22 (Y2 Sm11)
+    CK(bd_left_mul(m22, T, nb, N, n, one, zero, O21, st));
+    CK(bd_add(m21, nb, N, one, O21, st));
+    CK(cudaMemcpyAsync(T, Sn22, bytes, cudaMemcpyDeviceToDevice, st));                  // S22 = Sm22 (Sn22 + Y2 G)
+    CK(zgemm_strided(OP_N, OP_N, n, n, n, one, Y2, n, ms, G, n, ms, one, T, n, ms, nb, gs, st));
+    CK(bd_left_mul(m22, T, nb, N, n, one, zero, O22, st));
     return 0;
 }
 

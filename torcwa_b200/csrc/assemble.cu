@@ -110,6 +110,48 @@ __global__ void blockdiag_dense_kernel(const cplx* __restrict__ d4, int N, cplx*
     D[((size_t)b * n + i) * n + j] = v;
 }
 
+// Y = alpha * BD * X + beta * Y   (BD = four diagonals [B,4,N]; X, Y dense [B,2N,ncols]); grid (ceil(ncols/256), N, B)
+__global__ void bd_left_mul_kernel(const cplx* __restrict__ d4, const cplx* __restrict__ X, int N, int ncols, cplx alpha, cplx beta,
+                                   cplx* __restrict__ Y) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+    if (j >= ncols) return;
+    const cplx* d = d4 + (size_t)b * 4 * N;
+    const size_t base = (size_t)b * 2 * N * ncols;
+    const size_t e0 = base + (size_t)i * ncols + j, e1 = base + (size_t)(i + N) * ncols + j;
+    const cplx x0 = X[e0], x1 = X[e1];
+    cplx y0 = cmul(alpha, cadd(cmul(d[i], x0), cmul(d[N + i], x1)));
+    cplx y1 = cmul(alpha, cadd(cmul(d[2 * N + i], x0), cmul(d[3 * N + i], x1)));
+    if (!(beta.x == 0.0 && beta.y == 0.0)) { y0 = cadd(y0, cmul(beta, Y[e0])); y1 = cadd(y1, cmul(beta, Y[e1])); }
+    Y[e0] = y0; Y[e1] = y1;
+}
+
+// Y = alpha * X * BD + beta * Y   (X, Y dense [B,nrows,2N]); grid (ceil(N/256), nrows, B)
+__global__ void bd_right_mul_kernel(const cplx* __restrict__ d4, const cplx* __restrict__ X, int N, int nrows, cplx alpha, cplx beta,
+                                    cplx* __restrict__ Y) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+    if (j >= N) return;
+    const cplx* d = d4 + (size_t)b * 4 * N;
+    const size_t e0 = ((size_t)b * nrows + i) * 2 * N + j, e1 = e0 + N;
+    const cplx x0 = X[e0], x1 = X[e1];
+    cplx y0 = cmul(alpha, cadd(cmul(x0, d[j]), cmul(x1, d[2 * N + j])));
+    cplx y1 = cmul(alpha, cadd(cmul(x0, d[N + j]), cmul(x1, d[3 * N + j])));
+    if (!(beta.x == 0.0 && beta.y == 0.0)) { y0 = cadd(y0, cmul(beta, Y[e0])); y1 = cadd(y1, cmul(beta, Y[e1])); }
+    Y[e0] = y0; Y[e1] = y1;
+}
+
+// D += alpha * dense(BD)   (adds the four diagonals); grid (ceil(N/256), 1, B)
+__global__ void bd_add_kernel(const cplx* __restrict__ d4, int N, cplx alpha, cplx* __restrict__ D) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.z;
+    if (i >= N) return;
+    const int n = 2 * N;
+    const cplx* d = d4 + (size_t)b * 4 * N;
+    cplx* m = D + (size_t)b * n * n;
+    m[(size_t)i * n + i] = cadd(m[(size_t)i * n + i], cmul(alpha, d[i]));
+    m[(size_t)i * n + i + N] = cadd(m[(size_t)i * n + i + N], cmul(alpha, d[N + i]));
+    m[(size_t)(i + N) * n + i] = cadd(m[(size_t)(i + N) * n + i], cmul(alpha, d[2 * N + i]));
+    m[(size_t)(i + N) * n + i + N] = cadd(m[(size_t)(i + N) * n + i + N], cmul(alpha, d[3 * N + i]));
+}
+
 __global__ void identity_kernel(cplx* __restrict__ A, int n, int lda, long long stride) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
     if (j >= n) return;
@@ -147,6 +189,18 @@ cudaError_t layer_finish(const cplx* Tp, const cplx* Tm, int nb, int n, cplx* S1
 }
 cudaError_t blockdiag_dense(const cplx* d4, int nb, int N, cplx* D, cudaStream_t st) {
     blockdiag_dense_kernel<<<dim3((2 * N + 255) / 256, 2 * N, nb), 256, 0, st>>>(d4, N, D);
+    return cudaGetLastError();
+}
+cudaError_t bd_left_mul(const cplx* d4, const cplx* X, int nb, int N, int ncols, cplx alpha, cplx beta, cplx* Y, cudaStream_t st) {
+    bd_left_mul_kernel<<<dim3((ncols + 255) / 256, N, nb), 256, 0, st>>>(d4, X, N, ncols, alpha, beta, Y);
+    return cudaGetLastError();
+}
+cudaError_t bd_right_mul(const cplx* d4, const cplx* X, int nb, int N, int nrows, cplx alpha, cplx beta, cplx* Y, cudaStream_t st) {
+    bd_right_mul_kernel<<<dim3((N + 255) / 256, nrows, nb), 256, 0, st>>>(d4, X, N, nrows, alpha, beta, Y);
+    return cudaGetLastError();
+}
+cudaError_t bd_add(const cplx* d4, int nb, int N, cplx alpha, cplx* D, cudaStream_t st) {
+    bd_add_kernel<<<dim3((N + 255) / 256, 1, nb), 256, 0, st>>>(d4, N, alpha, D);
     return cudaGetLastError();
 }
 cudaError_t set_identity(cplx* A, int n, int lda, long long stride, int nb, cudaStream_t st) {

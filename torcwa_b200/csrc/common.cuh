@@ -71,13 +71,21 @@ HD cplx csqrt_(cplx z) {
 
 // ------------------------------------------------------------------ CTA context (device or emulated)
 struct Cta {
-    int tid, nthreads;   // thread index / CTA size
+    int tid, nthreads;   // thread index / number of cooperating threads
     int bid;             // which batch entry (matrix) this CTA owns
     char* smem;          // dynamic shared memory base
+    int warp_only;       // 1: the cooperating group is ONE warp (tid = lane, nthreads = 32): GROUP_SYNC is __syncwarp
 };
+// barrier of the cooperating group of a Cta context (whole CTA, or a single warp for the latency-bound
+// small-matrix solvers where a 512-thread barrier per Givens rotation would dominate)
+#ifdef RCWA_EMU
+#define GROUP_SYNC(c) ((void)0)
+#else
+#define GROUP_SYNC(c) do { if ((c).warp_only) __syncwarp(); else __syncthreads(); } while (0)
+#endif
 
 #ifndef RCWA_EMU
-DEV Cta make_cta(int bid, char* smem) { Cta c; c.tid = threadIdx.x; c.nthreads = blockDim.x; c.bid = bid; c.smem = smem; return c; }
+DEV Cta make_cta(int bid, char* smem) { Cta c; c.tid = threadIdx.x; c.nthreads = blockDim.x; c.bid = bid; c.smem = smem; c.warp_only = 0; return c; }
 
 DEV double warp_sum(double v) {
 #pragma unroll

@@ -2,14 +2,10 @@
 // Replaces torch.linalg.eig in Eig.forward (/root/reference/torcwa/torch_eig.py:11-17; LAPACK
 // zgeev on CPU, cuSOLVER/MAGMA hybrid on CUDA).  Four phases per batch of matrices:
 //
-//  (1) Hessenberg reduction  A = Z H Z^H   by Householder reflectors H_k = I - u u^H (|u|^2 = 2).
-//      One fused streaming pass per column over the stacked matrix [A; Z]:
-//          a_ij <- a_ij - u_i w~_j - y~_i conj(u_j)          (two-sided rank-2 update of step k)
-//      while the same pass accumulates  y' = A_new u'  and  w' = u'^H A_new  for step k+1
-//      (u' is built first from the updated column k+1 by a small per-matrix kernel).  Rows of Z
-//      ride along with u_i = 0 (right-multiplication only).  HBM-bound: one read + one write of
-//      the trailing region per column; row dot-products by warp shuffles, column sums as
-//      per-row-band partials (deterministic, no atomics).
+//  (1) Blocked Householder Hessenberg reduction  A = Z H Z^H  (hess.cu): per column one read-only
+//      streaming mat-vec over the trailing matrix (the HBM-bound kernel of the stage, exactly the
+//      algorithmic 16 n^3/3 bytes), per 32-column panel compact-WY block updates of A and Z on the
+//      DMMA GEMM.
 //  (2) Windowed multishift QR  H -> T (upper triangular), Z <- Z U:  chains of up to QR_NS
 //      single-shift Givens bulges (spacing 2) are chased through a QR_W x QR_W diagonal window held
 //      in shared memory by ONE CTA per matrix, all bulges advancing one position per step; the
@@ -37,13 +33,16 @@
 #define QR_LD 65           // shared-memory leading dimension (odd: conflict-free column access)
 #define QR_NS 16           // max simultaneous shifts / bulges
 #define QR_SMALL 48         // active blocks up to this size are Schur-factored directly in shared memory
-#define QR_SLICE_ROT 160    // rotations per launch of a small-block solve (time slice: keeps the batch in lockstep)
+#define QR_AED_W 48         // aggressive-early-deflation window
+#define QR_AED_SLICE 300    // rotations per launch while Schur-factoring the AED window
+#define QR_AED_SWAPS 160    // eigenvalue swaps per launch during the AED deflation scan
+#define QR_SLICE_ROT 400    // rotations per launch of a small-block solve (time slice: keeps the batch in lockstep)
 #define QR_MAXSTALL 40     // sweeps without deflation before giving up on a matrix
 #define TV_NB 32           // eigenvector back-substitution block
 
 struct QrState {
     int lo, hi;          // active block [lo, hi] (inclusive); done when hi < 1
-    int phase;           // 0: start a new sweep (deflation scan + shifts); 1: chain in flight; 2: small-block solve
+    int phase;           // 0: start a new sweep (deflation scan + shifts); 1: chain in flight; 2: small-block solve; 3: AED window Schur
     int p;               // window start of the next pass
     int nbulge;          // bulges currently in flight
     int nintro;          // bulges introduced so far in this sweep
@@ -56,7 +55,14 @@ struct QrState {
     int ss_its;          //   QR iterations spent on the current eigenvalue
     int ss_fresh;        //   1: U must be initialised to identity at the next slice
     int small_solves;    // statistics
-    int pad0;
+    int aed_kw, aed_nw;  // AED window [aed_kw, aed_kw + aed_nw) (phase 3)
+    int p_last;          // window start of the previous chase pass (its column update may still be in flight)
+    int aed_off;         // AED disabled for this matrix (its window failed to converge)
+    int aed_stage;       // 0: Schur slices, 1: deflation scan slices (then restore + finish)
+    int aed_prog[4];     // scan progress: ns, ilst, knt, kcur
+    int shifts_ready;    // phase 1 may start with st.shifts as they are (supplied by AED)
+    int aeds, aed_deflated;   // statistics
+    int pad0, pad1;
     int kpos[QR_NS];     // column of each bulge (leading first): bulge element is H[k+2][k]
     cplx shifts[QR_NS];
 };
@@ -66,6 +72,17 @@ struct QrState {
 HD void givens(cplx a, cplx b, double& c, cplx& s, cplx& r) {
     if (cis_zero(b)) { c = 1.0; s = C(0, 0); r = a; return; }
     if (cis_zero(a)) { c = 0.0; double nb = cabs_(b); s = cscale(cconj(b), 1.0 / nb); r = C(nb, 0); return; }
+    const double na2 = cabs2(a), nb2 = cabs2(b), n2 = na2 + nb2;
+    if (na2 > 1e-280 && nb2 > 1e-280 && n2 < 1e280) {
+        // common, well-scaled case: two square roots and two divisions (this sits on the serial critical
+        // path of every chase step; hypot-based scaling is several times more expensive in fp64)
+        const double na = sqrt(na2), nrm = sqrt(n2);
+        const double inv = 1.0 / (na * nrm);
+        c = na / nrm;
+        s = cscale(cmul(a, cconj(b)), inv);
+        r = cscale(a, nrm / na);
+        return;
+    }
     const double na = cabs_(a), nb = cabs_(b);
     const double sc = fmax(na, nb);
     const double nrm = sc * sqrt((na / sc) * (na / sc) + (nb / sc) * (nb / sc));
@@ -185,9 +202,9 @@ DEV int small_schur_slice(const Cta& c, cplx* Hs, cplx* Us, int m, int* pi, int*
             if (l + 1 <= i) extra += cabs1(Hs[(l + 1) * QR_LD + l]);
             if (negligible_subdiag(h10, Hs[(l - 1) * QR_LD + l - 1], Hs[l * QR_LD + l], Hs[(l - 1) * QR_LD + l], extra)) break;
         }
-        CTA_SYNC();
+        GROUP_SYNC(c);
         if (l > 0 && c.tid == 0) Hs[l * QR_LD + l - 1] = C(0, 0);
-        CTA_SYNC();
+        GROUP_SYNC(c);
         if (l >= i) { --i; its = 0; continue; }
         if (its > 60) { *pi = i; *pits = its; return -1; }
         if (used + (i - l) > budget && used > 0) break;       // out of time: resume at the next launch
@@ -210,14 +227,14 @@ DEV int small_schur_slice(const Cta& c, cplx* Hs, cplx* Us, int m, int* pi, int*
             else { a = Hs[k * QR_LD + k - 1]; b = Hs[(k + 1) * QR_LD + k - 1]; }
             double cs; cplx sn, r;
             givens(a, b, cs, sn, r);
-            CTA_SYNC();
+            GROUP_SYNC(c);
             if (k > l && c.tid == 0) { Hs[k * QR_LD + k - 1] = r; Hs[(k + 1) * QR_LD + k - 1] = C(0, 0); }
             for (int j = k + c.tid; j < m; j += c.nthreads) {
                 cplx x = Hs[k * QR_LD + j], y = Hs[(k + 1) * QR_LD + j];
                 Hs[k * QR_LD + j] = cadd(cscale(x, cs), cmul(sn, y));
                 Hs[(k + 1) * QR_LD + j] = csub(cscale(y, cs), cmul(cconj(sn), x));
             }
-            CTA_SYNC();
+            GROUP_SYNC(c);
             const int rmax = (k + 2 < i) ? k + 2 : i;
             for (int idx = c.tid; idx < (rmax + 1) + m; idx += c.nthreads) {
                 cplx* base = (idx <= rmax) ? (Hs + idx * QR_LD) : (Us + (idx - rmax - 1) * QR_LD);
@@ -225,7 +242,7 @@ DEV int small_schur_slice(const Cta& c, cplx* Hs, cplx* Us, int m, int* pi, int*
                 base[k] = cadd(cscale(x, cs), cmul(y, cconj(sn)));
                 base[k + 1] = csub(cscale(y, cs), cmul(x, sn));
             }
-            CTA_SYNC();      // the next rotation reads the bulge this right-update just created
+            GROUP_SYNC(c);      // the next rotation reads the bulge this right-update just created
         }
         used += i - l;
         ++its;
@@ -239,13 +256,19 @@ DEV int small_schur_slice(const Cta& c, cplx* Hs, cplx* Us, int m, int* pi, int*
 // Outputs: U (QR_W x QR_W, ld QR_W, global), three GEMM problems (rows, cols, Z) -- M = 0 if idle.
 // Shared memory: Hs[QR_W*QR_LD] + Us[QR_W*QR_LD] cplx + small scratch (see qr_pass_smem_bytes()).
 struct QrScratch {
-    double cs[QR_NS + 1];
-    cplx sn[QR_NS + 1];
-    int rot_row[QR_NS + 1];     // local upper row index of each rotation this step
-    int rot_col0[QR_NS + 1];    // first local column of the left update
-    int nrot;
-    int moved_any;
-    int flag;
+    QrState st;                 // working copy of the per-matrix state (thread 0 mutates, barriers publish)
+    double cs[QR_NS];
+    cplx sn[QR_NS];
+    int act[QR_NS];             // rotation of bulge slot b exists in the current step
+    int rr1[QR_NS];             // its upper local row (0 for an introduction)
+    int start[QR_NS];           // closed-form schedule of the pass: first step of slot b,
+    int q0[QR_NS];              //   local column at that step (-1 = virtual column of an introduction),
+    int nrot[QR_NS];            //   number of rotations it performs in this pass,
+    int shift_id[QR_NS];        //   shift used by an introduction
+    int nslots, tmax;
+    int aed_ns;                 // result of the AED deflation analysis
+    int ss_rc, ss_i, ss_its;    // results of a small-Schur slice run by warp 0
+    cplx hv[QR_W];              // Householder vector (AED restore)
     double red[40];
 };
 
@@ -253,118 +276,355 @@ HD size_t qr_pass_smem_bytes(int n) {
     return 2 * (size_t)QR_W * QR_LD * sizeof(cplx) + sizeof(QrScratch) + (size_t)(QR_NS * (QR_NS + 1)) * sizeof(cplx) + (size_t)(n + 16) + 64;
 }
 
+// ------------------------------------------------------------------------------------------------
+// AED helpers.  T (upper triangular Schur form of the window, nw x nw) in Hs, its Schur vectors in Us.
+//
+// Deflation analysis (LAPACK zlaqr2): the window's coupling to the rest of H is the "spike"
+// s * conj(V[0,:]); eigenvalues whose spike entry is negligible are converged; the others are moved
+// to the top with adjacent swaps (ztrexc).  Returns ns = number of undeflatable eigenvalues, which
+// then occupy T[0:ns, 0:ns].
+// Resumable: at most `budget` swaps per call; progress (ns, ilst, knt, kcur) lives in `prog[4]`.
+// Returns 1 when the scan is complete (prog[0] = ns), 0 if it must be continued.
+DEV int aed_deflation_scan(const Cta& c, cplx* T, cplx* V, int nw, cplx s, int* prog, int budget) {
+    const double smlnum = RCWA_SAFMIN * (1.0 / RCWA_EPS);
+    int ns = prog[0], ilst = prog[1], knt = prog[2], kcur = prog[3], used = 0;
+    while (knt < nw) {
+        if (kcur < 0) {
+            double foo = cabs1(T[(ns - 1) * QR_LD + ns - 1]);
+            if (foo == 0.0) foo = cabs1(s);
+            if (cabs1(s) * cabs1(V[ns - 1]) <= fmax(smlnum, RCWA_EPS * foo)) { --ns; ++knt; continue; }
+            kcur = ns - 2;            // undeflatable: move position ns-1 up to ilst by adjacent swaps
+        }
+        while (kcur >= ilst) {
+            if (used >= budget) { GROUP_SYNC(c); prog[0] = ns; prog[1] = ilst; prog[2] = knt; prog[3] = kcur; return 0; }
+            const int k = kcur;
+            const cplx t11 = T[k * QR_LD + k], t22 = T[(k + 1) * QR_LD + k + 1];
+            double cs; cplx sn, r;
+            givens(T[k * QR_LD + k + 1], csub(t22, t11), cs, sn, r);
+            // rows (k,k+1) x cols k+2..nw-1 | cols (k,k+1) x rows 0..k-1 of T | cols (k,k+1) x all rows of V
+            const int n_left = nw - (k + 2), n_right = k;
+            for (int idx = c.tid; idx < n_left + n_right + nw; idx += c.nthreads) {
+                if (idx < n_left) {
+                    const int j = k + 2 + idx;
+                    cplx x = T[k * QR_LD + j], y = T[(k + 1) * QR_LD + j];
+                    T[k * QR_LD + j] = cadd(cscale(x, cs), cmul(sn, y));
+                    T[(k + 1) * QR_LD + j] = csub(cscale(y, cs), cmul(cconj(sn), x));
+                } else {
+                    cplx* base = (idx < n_left + n_right) ? (T + (idx - n_left) * QR_LD) : (V + (idx - n_left - n_right) * QR_LD);
+                    cplx x = base[k], y = base[k + 1];
+                    base[k] = cadd(cscale(x, cs), cmul(y, cconj(sn)));
+                    base[k + 1] = csub(cscale(y, cs), cmul(x, sn));
+                }
+            }
+            GROUP_SYNC(c);
+            if (c.tid == 0) { T[k * QR_LD + k] = t22; T[(k + 1) * QR_LD + k + 1] = t11; }
+            GROUP_SYNC(c);
+            --kcur; ++used;
+        }
+        ++ilst; ++knt; kcur = -1;
+    }
+    prog[0] = ns; prog[1] = ilst; prog[2] = knt; prog[3] = kcur;
+    return 1;
+}
+
+// Hermitian unitary reflector H = I - u u^H (|u|^2 = 2) with H x = beta e_1 for x = M[r0.., col] (rows
+// r0..r1-1 of column `col`, stride QR_LD), or for an explicit vector when M == nullptr (then `u`
+// holds x on entry).  Thread 0 builds u (indexed by absolute row) into `u`; returns beta via *beta.
+DEV void small_reflector(const Cta& c, cplx* u, int r0, int r1, cplx* beta_out) {
+    if (c.tid == 0) {
+        double ss = 0.0;
+        for (int r = r0; r < r1; ++r) ss += cabs2(u[r]);
+        const double sigma = sqrt(ss);
+        const cplx x1 = u[r0];
+        const double ax = cabs_(x1);
+        if (sigma == 0.0) { for (int r = r0; r < r1; ++r) u[r] = C(0, 0); *beta_out = x1; }
+        else {
+            const cplx ph = (ax == 0.0) ? C(1, 0) : cscale(x1, 1.0 / ax);
+            const cplx beta = cscale(ph, -sigma);
+            const double scl = 1.0 / sqrt(sigma * (sigma + ax));
+            u[r0] = csub(u[r0], beta);
+            for (int r = r0; r < r1; ++r) u[r] = cscale(u[r], scl);
+            *beta_out = beta;
+        }
+    }
+    GROUP_SYNC(c);
+}
+
+// M <- (I - u u^H) M on rows r0..r1-1, columns c0..c1-1 (one thread per column: dot then update)
+DEV void small_hh_left(const Cta& c, cplx* M, const cplx* u, int r0, int r1, int c0, int c1) {
+    for (int j = c0 + c.tid; j < c1; j += c.nthreads) {
+        cplx w = C(0, 0);
+        for (int r = r0; r < r1; ++r) w = cadd(w, cmulc(u[r], M[r * QR_LD + j]));
+        for (int r = r0; r < r1; ++r) M[r * QR_LD + j] = csub(M[r * QR_LD + j], cmul(u[r], w));
+    }
+}
+// M <- M (I - u u^H) on rows q0..q1-1, columns r0..r1-1 (one thread per row)
+DEV void small_hh_right(const Cta& c, cplx* M, const cplx* u, int q0, int q1, int r0, int r1) {
+    for (int i = q0 + c.tid; i < q1; i += c.nthreads) {
+        cplx y = C(0, 0);
+        for (int r = r0; r < r1; ++r) y = cfma(M[i * QR_LD + r], u[r], y);
+        for (int r = r0; r < r1; ++r) M[i * QR_LD + r] = csub(M[i * QR_LD + r], cmul(y, cconj(u[r])));
+    }
+}
+
+// After the scan: fold the remaining spike s*conj(V[0,0:ns]) back into Hessenberg form.
+// T[0:ns,0:ns] <- Hessenberg, T[0:ns, ns:nw] and V[:,0:ns] updated accordingly (LAPACK zlaqr2:
+// zlarfg on the spike, zlarf x3, zgehrd, zunmhr -- done here with Hermitian reflectors).
+DEV void aed_restore_hessenberg(const Cta& c, cplx* T, cplx* V, int nw, int ns, cplx* u) {
+    if (ns <= 1) return;
+    cplx beta;
+    // reflector that maps the spike direction conj(V[0,0:ns]) onto e_0
+    for (int r = c.tid; r < ns; r += c.nthreads) u[r] = cconj(V[r]);
+    GROUP_SYNC(c);
+    small_reflector(c, u, 0, ns, &beta);
+    small_hh_left(c, T, u, 0, ns, 0, nw);
+    GROUP_SYNC(c);
+    small_hh_right(c, T, u, 0, ns, 0, ns);
+    small_hh_right(c, V, u, 0, nw, 0, ns);
+    GROUP_SYNC(c);
+    // Hessenberg reduction of T[0:ns,0:ns]; reflectors act on indices >= 1, so the spike stays on e_0
+    for (int j = 0; j + 2 < ns; ++j) {
+        for (int r = j + 1 + c.tid; r < ns; r += c.nthreads) u[r] = T[r * QR_LD + j];
+        GROUP_SYNC(c);
+        small_reflector(c, u, j + 1, ns, &beta);
+        if (c.tid == 0) {
+            T[(j + 1) * QR_LD + j] = beta;
+            for (int r = j + 2; r < ns; ++r) T[r * QR_LD + j] = C(0, 0);
+        }
+        small_hh_left(c, T, u, j + 1, ns, j + 1, nw);
+        GROUP_SYNC(c);
+        small_hh_right(c, T, u, 0, ns, j + 1, ns);
+        small_hh_right(c, V, u, 0, nw, j + 1, ns);
+        GROUP_SYNC(c);
+    }
+}
+
+// emit the three GEMM problems that apply the window unitary U (wl x wl at Ug) to the off-diagonal
+// row panel, column panel and Z for the window [p, p+wl)
+DEV void emit_window_gemms(cplx* H, int ldh, int n, cplx* Zm, int ldz, cplx* Ug, int p, int wl,
+                           ZGemmProblem* prob_rows, ZGemmProblem* prob_cols, ZGemmProblem* prob_z) {
+    const int wend = p + wl;
+    ZGemmProblem g;
+    g.A = Ug; g.lda = QR_W; g.B = H + (size_t)p * ldh + wend; g.ldb = ldh; g.C = H + (size_t)p * ldh + wend; g.ldc = ldh;
+    g.M = (n - wend > 0) ? wl : 0; g.N = n - wend; g.K = wl; *prob_rows = g;          // H[p:wend, wend:n] <- U^H * (.)
+    g.A = H + p; g.lda = ldh; g.B = Ug; g.ldb = QR_W; g.C = H + p; g.ldc = ldh;
+    g.M = p; g.N = wl; g.K = wl; *prob_cols = g;                                         // H[0:p, p:wend] <- (.) * U
+    g.A = Zm + p; g.lda = ldz; g.B = Ug; g.ldb = QR_W; g.C = Zm + p; g.ldc = ldz;
+    g.M = n; g.N = wl; g.K = wl; *prob_z = g;                                            // Z[:, p:wend] <- (.) * U
+}
+
 DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, QrState* stg,
-                      cplx* Ug, ZGemmProblem* prob_rows, ZGemmProblem* prob_cols, ZGemmProblem* prob_z) {
+                      cplx* Ug, cplx* Vg, cplx* Tg, ZGemmProblem* prob_rows, ZGemmProblem* prob_cols_main,
+                      ZGemmProblem* prob_cols, ZGemmProblem* prob_z) {
+    // Ug: this pass's window unitary (double-buffered by the host: its GEMMs may still run while the next
+    //     pass works); Vg/Tg: persistent copies for the time-sliced AED / small-block solves.
+    // prob_rows, prob_cols_main run on the main stream before the next pass; prob_cols, prob_z on the side
+    // stream (they touch only rows above / columns of Z that later passes of a downward-moving chase never
+    // read).  AED and small-block solves may be followed by a window that reaches upwards, so their column
+    // update goes to the main stream.
     cplx* Hs = reinterpret_cast<cplx*>(c.smem);
     cplx* Us = Hs + QR_W * QR_LD;
     QrScratch* sc = reinterpret_cast<QrScratch*>(Us + QR_W * QR_LD);
     cplx* Ts = reinterpret_cast<cplx*>(sc + 1);                         // [QR_NS][QR_NS+1] shift block
     unsigned char* negl = reinterpret_cast<unsigned char*>(Ts + QR_NS * (QR_NS + 1));   // [n] deflation flags
+    QrState& st = sc->st;
 
-    // default: idle problems
-    if (c.tid == 0) { prob_rows->M = 0; prob_cols->M = 0; prob_z->M = 0; }
-    QrState st = *stg;          // every thread holds a private copy; thread 0 writes it back
+    if (c.tid == 0) { prob_rows->M = 0; prob_cols_main->M = 0; prob_cols->M = 0; prob_z->M = 0; st = *stg; }
     CTA_SYNC();
     if (st.done) return;
 
     if (st.phase == 0) {
         // ---------------- new sweep: deflation scan over the whole remaining matrix [1..hi]
-        for (int k = 1 + c.tid; k <= st.hi; k += c.nthreads) {
+        const int hi0 = st.hi;
+        for (int k = 1 + c.tid; k <= hi0; k += c.nthreads) {
             cplx h10 = H[(size_t)k * ldh + k - 1];
             bool z = cis_zero(h10);
             if (!z) {
                 double extra = 0.0;
                 if (k - 2 >= 0) extra += cabs1(H[(size_t)(k - 1) * ldh + k - 2]);
-                if (k + 1 <= st.hi) extra += cabs1(H[(size_t)(k + 1) * ldh + k]);
-                z = negligible_subdiag(h10, H[(size_t)(k - 1) * ldh + k - 1], H[(size_t)k * ldh + k], H[(size_t)(k - 1) * ldh + k], extra);
+                if (k + 1 <= hi0) extra += cabs1(H[(size_t)(k + 1) * ldh + k]);
+                // H[k-1][k] belongs to the side-stream column update of the window that started at k; if that
+                // window was the previous pass, it may still be in flight: use the plain criterion there
+                const cplx h01 = (k == st.p_last) ? h10 : H[(size_t)(k - 1) * ldh + k];
+                z = negligible_subdiag(h10, H[(size_t)(k - 1) * ldh + k - 1], H[(size_t)k * ldh + k], h01, extra);
                 if (z) H[(size_t)k * ldh + k - 1] = C(0, 0);
             }
             negl[k] = z ? 1 : 0;
         }
         CTA_SYNC();
-        // walk down from hi (uniform scalar code on shared flags)
-        int hi = st.hi;
-        while (hi >= 1 && negl[hi]) --hi;
-        int lo = hi;
-        while (lo >= 1 && !negl[lo]) --lo;
-        if (hi < 1) {
-            if (c.tid == 0) { st.done = 1; st.hi = hi; *stg = st; }
-            return;
-        }
-        if (hi < st.hi_prev || lo > st.lo) st.stall = 0; else st.stall++;
-        st.hi_prev = hi;
-        st.lo = lo; st.hi = hi;
-        if (st.stall > QR_MAXSTALL) {
-            if (c.tid == 0) { st.done = 1; st.info = hi + 1; *stg = st; }
-            return;
-        }
-        const int m = hi - lo + 1;
-        if (m <= QR_SMALL) {
-            // small active block: Schur-factor it directly in shared memory (time-sliced)
-            st.phase = 2; st.p = lo; st.ss_i = m - 1; st.ss_its = 0; st.ss_fresh = 1; st.small_solves++;
-        }
-        const int ns = (m < QR_NS) ? m : QR_NS;
-        if (st.phase != 2) {
-        // ---------------- shifts: eigenvalues of the trailing ns x ns block (warp 0)
-        for (int idx = c.tid; idx < ns * ns; idx += c.nthreads) {
-            int r = idx / ns, q = idx % ns;
-            Ts[r * (QR_NS + 1) + q] = (r <= q + 1) ? H[(size_t)(hi - ns + 1 + r) * ldh + (hi - ns + 1 + q)] : C(0, 0);
+        if (c.tid == 0) {
+            int hi = hi0;
+            while (hi >= 1 && negl[hi]) --hi;
+            int lo = hi;
+            while (lo >= 1 && !negl[lo]) --lo;
+            if (hi < 1) { st.done = 1; st.hi = hi; }
+            else {
+                if (hi < st.hi_prev || lo > st.lo) st.stall = 0; else st.stall++;
+                st.hi_prev = hi; st.lo = lo; st.hi = hi;
+                if (st.stall > QR_MAXSTALL) { st.done = 1; st.info = hi + 1; }
+                else if (hi - lo + 1 <= QR_SMALL) {
+                    // small active block: Schur-factor it directly in shared memory (time-sliced)
+                    st.phase = 2; st.p = lo; st.ss_i = hi - lo; st.ss_its = 0; st.ss_fresh = 1; st.small_solves++;
+                } else if (!st.aed_off) {
+                    // aggressive early deflation on the trailing window before (or instead of) a sweep
+                    const int nw = (QR_AED_W < hi - lo) ? QR_AED_W : hi - lo;     // spike entry H[kw][kw-1] stays inside the block
+                    st.phase = 3; st.aed_stage = 0; st.aed_nw = nw; st.aed_kw = hi - nw + 1; st.ss_i = nw - 1; st.ss_its = 0; st.ss_fresh = 1; st.aeds++;
+                } else {
+                    st.ns = QR_NS; st.nintro = 0; st.nbulge = 0; st.p = lo; st.phase = 1; st.sweeps++; st.shifts_ready = 0;
+                }
+            }
+            if (st.done) *stg = st;
         }
         CTA_SYNC();
-        const bool exceptional = (st.stall % 6 == 5);
+        if (st.done) return;
+        if (st.phase == 1 && !st.shifts_ready) {
+            // ---------------- shifts: eigenvalues of the trailing ns x ns block (warp 0)
+            const int ns = st.ns, hi = st.hi;
+            for (int idx = c.tid; idx < ns * ns; idx += c.nthreads) {
+                int r = idx / ns, q = idx % ns;
+                Ts[r * (QR_NS + 1) + q] = (r <= q + 1) ? H[(size_t)(hi - ns + 1 + r) * ldh + (hi - ns + 1 + q)] : C(0, 0);
+            }
+            CTA_SYNC();
 #ifndef RCWA_EMU
-        if (c.tid < 32) {
-            tiny_hqr_eigs(c.tid, 32, Ts, QR_NS + 1, ns, st.shifts);
-        }
-        // broadcast the shifts computed by warp 0 through shared memory
-        CTA_SYNC();
-        if (c.tid < 32) { for (int j = c.tid; j < ns; j += 32) Ts[j] = st.shifts[j]; }
-        CTA_SYNC();
-        for (int j = 0; j < ns; ++j) st.shifts[j] = Ts[j];
-        CTA_SYNC();
+            if (c.tid < 32) tiny_hqr_eigs(c.tid, 32, Ts, QR_NS + 1, ns, st.shifts);
 #else
-        tiny_hqr_eigs(0, 1, Ts, QR_NS + 1, ns, st.shifts);
+            tiny_hqr_eigs(0, 1, Ts, QR_NS + 1, ns, st.shifts);
 #endif
-        if (exceptional) {
-            const double mag = 0.75 * cabs1(H[(size_t)hi * ldh + hi - 1]);
-            for (int j = 0; j < ns; ++j) st.shifts[j] = cadd(H[(size_t)hi * ldh + hi], C(mag * ((j & 1) ? -1.0 : 1.0), mag * 0.5 * (j % 3 - 1)));
+            CTA_SYNC();
+            if (c.tid == 0 && (st.stall % 6 == 5)) {
+                // exceptional shifts (LAPACK-style) when the block has not deflated for a while
+                const double mag = 0.75 * cabs1(H[(size_t)hi * ldh + hi - 1]);
+                for (int j = 0; j < ns; ++j) st.shifts[j] = cadd(H[(size_t)hi * ldh + hi], C(mag * ((j & 1) ? -1.0 : 1.0), mag * 0.5 * (j % 3 - 1)));
+            }
+            CTA_SYNC();
         }
-        st.ns = ns; st.nintro = 0; st.nbulge = 0; st.p = lo; st.phase = 1; st.sweeps++;
+    }
+
+    if (st.phase == 3) {
+        // ---------------- AED: time slices of the window's Schur factorisation on a COPY (Tg, Ug), then
+        // the deflation analysis; H itself is only touched if something deflates
+        const int kw = st.aed_kw, nw = st.aed_nw;
+        const int fresh = st.ss_fresh;
+        for (int idx = c.tid; idx < nw * nw; idx += c.nthreads) {
+            int r = idx / nw, q = idx % nw;
+            Hs[r * QR_LD + q] = fresh ? ((r <= q + 1) ? H[(size_t)(kw + r) * ldh + (kw + q)] : C(0, 0)) : Tg[r * QR_W + q];
+            Us[r * QR_LD + q] = fresh ? C(r == q ? 1.0 : 0.0, 0.0) : Vg[r * QR_W + q];
         }
-#ifdef RCWA_EMU
-        if (getenv("RCWA_EMU_DEBUG")) fprintf(stderr, "sweep %d: lo=%d hi=%d ns=%d stall=%d sub=%.3e small=%d\n", st.sweeps, lo, hi, ns, st.stall, cabs1(H[(size_t)hi * ldh + hi - 1]), st.small_solves);
-#endif
+        CTA_SYNC();
+        // latency-bound serial work: one warp with __syncwarp (a 512-thread barrier per rotation would dominate)
+        Cta w1 = c; w1.warp_only = 1; w1.nthreads = (c.nthreads < 32) ? c.nthreads : 32;
+        if (st.aed_stage == 0) {
+            if (c.tid < w1.nthreads) {
+                int si = st.ss_i, sits = st.ss_its;
+                const int rc1 = small_schur_slice(w1, Hs, Us, nw, &si, &sits, QR_AED_SLICE);
+                if (c.tid == 0) { sc->ss_rc = rc1; sc->ss_i = si; sc->ss_its = sits; }
+            }
+            CTA_SYNC();
+            const int rc = sc->ss_rc;
+            if (rc < 0) {               // the window did not converge: fall back to plain sweeps for this matrix
+                if (c.tid == 0) { st.aed_off = 1; st.phase = 0; st.passes++; *stg = st; }
+                return;
+            }
+            // park the copy; the deflation scan starts at the next launch
+            for (int idx = c.tid; idx < nw * nw; idx += c.nthreads) {
+                int r = idx / nw, q = idx % nw;
+                Tg[r * QR_W + q] = Hs[r * QR_LD + q];
+                Vg[r * QR_W + q] = Us[r * QR_LD + q];
+            }
+            if (c.tid == 0) {
+                st.ss_i = sc->ss_i; st.ss_its = sc->ss_its; st.ss_fresh = 0; st.passes++;
+                if (rc == 1) { st.aed_stage = 1; st.aed_prog[0] = nw; st.aed_prog[1] = 0; st.aed_prog[2] = 0; st.aed_prog[3] = -1; }
+                *stg = st;
+            }
+            return;
+        }
+        // ---- stage 1: deflation scan in time slices, then restore + finish in the launch that completes it
+        const cplx spike = H[(size_t)kw * ldh + kw - 1];
+        if (c.tid < w1.nthreads) {
+            int prog[4] = {st.aed_prog[0], st.aed_prog[1], st.aed_prog[2], st.aed_prog[3]};
+            const int done1 = aed_deflation_scan(w1, Hs, Us, nw, spike, prog, QR_AED_SWAPS);
+            if (c.tid == 0) { sc->ss_rc = done1; sc->aed_ns = prog[0]; sc->ss_i = prog[1]; sc->ss_its = prog[2]; sc->nslots = prog[3]; }
+        }
+        CTA_SYNC();
+        if (!sc->ss_rc) {
+            for (int idx = c.tid; idx < nw * nw; idx += c.nthreads) {
+                int r = idx / nw, q = idx % nw;
+                Tg[r * QR_W + q] = Hs[r * QR_LD + q];
+                Vg[r * QR_W + q] = Us[r * QR_LD + q];
+            }
+            if (c.tid == 0) {
+                st.aed_prog[0] = sc->aed_ns; st.aed_prog[1] = sc->ss_i; st.aed_prog[2] = sc->ss_its; st.aed_prog[3] = sc->nslots;
+                st.passes++; *stg = st;
+            }
+            return;
+        }
+        const int ns = sc->aed_ns;
+        const int nd = nw - ns;
+        const int nsh = (ns < QR_NS) ? ns : QR_NS;              // shifts offered to the next sweep:
+        if (c.tid == 0) {                                        // trailing undeflated eigenvalues of the window
+            for (int j = 0; j < nsh; ++j) st.shifts[j] = Hs[(ns - nsh + j) * QR_LD + (ns - nsh + j)];
+        }
+        CTA_SYNC();
+        if (nd > 0) {
+            if (c.tid < w1.nthreads) aed_restore_hessenberg(w1, Hs, Us, nw, ns, sc->hv);
+            CTA_SYNC();
+            for (int idx = c.tid; idx < nw * nw; idx += c.nthreads) {
+                int r = idx / nw, q = idx % nw;
+                const bool below = (q < ns) ? (r > q + 1) : (r > q);        // exact zeros below the (quasi-)triangle
+                H[(size_t)(kw + r) * ldh + (kw + q)] = below ? C(0, 0) : Hs[r * QR_LD + q];
+                Ug[r * QR_W + q] = Us[r * QR_LD + q];
+            }
+        }
+        if (c.tid == 0) {
+            st.passes++;
+            if (nd > 0) {
+                H[(size_t)kw * ldh + kw - 1] = (ns > 0) ? cmul(spike, cconj(Us[0])) : C(0, 0);
+                emit_window_gemms(H, ldh, n, Zm, ldz, Ug, kw, nw, prob_rows, prob_cols_main, prob_z);
+                st.aed_deflated += nd;
+                st.hi = kw + ns - 1;          // the nd trailing eigenvalues are converged
+                st.stall = 0;
+            }
+            const int m_new = st.hi - st.lo + 1;
+            if (m_new <= QR_SMALL || ns == 0 || nd * 100 > 14 * nw) {
+                st.phase = 0;                 // good harvest (or tiny rest): look again before sweeping
+            } else {
+                st.ns = nsh; st.nintro = 0; st.nbulge = 0; st.p = st.lo; st.phase = 1; st.sweeps++; st.shifts_ready = 1;
+            }
+            *stg = st;
+        }
+        return;
     }
 
     if (st.phase == 2) {
         // ---------------- one time slice of the small-block solve on [lo, hi]
         const int p2 = st.lo, m2 = st.hi - st.lo + 1;
+        const int fresh = st.ss_fresh;
         for (int idx = c.tid; idx < m2 * m2; idx += c.nthreads) {
             int r = idx / m2, q = idx % m2;
             Hs[r * QR_LD + q] = H[(size_t)(p2 + r) * ldh + (p2 + q)];
-            Us[r * QR_LD + q] = st.ss_fresh ? C(r == q ? 1.0 : 0.0, 0.0) : Ug[r * QR_W + q];
+            Us[r * QR_LD + q] = fresh ? C(r == q ? 1.0 : 0.0, 0.0) : Vg[r * QR_W + q];
         }
         CTA_SYNC();
-        int si = st.ss_i, sits = st.ss_its;
-        const int rc = small_schur_slice(c, Hs, Us, m2, &si, &sits, QR_SLICE_ROT);
-        st.ss_i = si; st.ss_its = sits; st.ss_fresh = 0;
+        Cta w1 = c; w1.warp_only = 1; w1.nthreads = (c.nthreads < 32) ? c.nthreads : 32;
+        if (c.tid < w1.nthreads) {
+            int si1 = st.ss_i, sits1 = st.ss_its;
+            const int rc1 = small_schur_slice(w1, Hs, Us, m2, &si1, &sits1, QR_SLICE_ROT);
+            if (c.tid == 0) { sc->ss_rc = rc1; sc->ss_i = si1; sc->ss_its = sits1; }
+        }
+        CTA_SYNC();
+        const int rc = sc->ss_rc, si = sc->ss_i, sits = sc->ss_its;
         for (int idx = c.tid; idx < m2 * m2; idx += c.nthreads) {
             int r = idx / m2, q = idx % m2;
             H[(size_t)(p2 + r) * ldh + (p2 + q)] = Hs[r * QR_LD + q];
-            Ug[r * QR_W + q] = Us[r * QR_LD + q];
+            Vg[r * QR_W + q] = Us[r * QR_LD + q];
+            if (rc != 0) Ug[r * QR_W + q] = Us[r * QR_LD + q];
         }
         if (c.tid == 0) {
+            st.ss_i = si; st.ss_its = sits; st.ss_fresh = 0;
             st.passes++;
             if (rc != 0) {
                 // finished (or failed): apply the accumulated unitary to the off-diagonal panels and Z
-                const int wend2 = st.hi + 1;
-                ZGemmProblem g;
-                g.A = Ug; g.lda = QR_W; g.B = H + (size_t)p2 * ldh + wend2; g.ldb = ldh; g.C = H + (size_t)p2 * ldh + wend2; g.ldc = ldh;
-                g.M = (n - wend2 > 0) ? m2 : 0; g.N = n - wend2; g.K = m2; *prob_rows = g;
-                g.A = H + p2; g.lda = ldh; g.B = Ug; g.ldb = QR_W; g.C = H + p2; g.ldc = ldh;
-                g.M = p2; g.N = m2; g.K = m2; *prob_cols = g;
-                g.A = Zm + p2; g.lda = ldz; g.B = Ug; g.ldb = QR_W; g.C = Zm + p2; g.ldc = ldz;
-                g.M = n; g.N = m2; g.K = m2; *prob_z = g;
+                emit_window_gemms(H, ldh, n, Zm, ldz, Ug, p2, m2, prob_rows, prob_cols_main, prob_z);
                 st.phase = 0;
                 if (rc < 0) { st.done = 1; st.info = st.lo + si + 1; }
             }
@@ -373,7 +633,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         return;
     }
 
-    // ---------------- window [p, wend)
+    // ---------------- window [p, wend): chase the chain of bulges through it
     const int p = st.p;
     const int wend = (p + QR_W < st.hi + 1) ? p + QR_W : st.hi + 1;
     const int wl = wend - p;
@@ -383,108 +643,85 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         Hs[r * QR_LD + q] = H[(size_t)(p + r) * ldh + (p + q)];
         Us[r * QR_LD + q] = C(r == q ? 1.0 : 0.0, 0.0);
     }
+    // closed-form schedule: slot b performs rotations at steps start[b] .. start[b]+nrot[b]-1, the
+    // i-th of them on rows (q0[b]+i+1, q0[b]+i+2) (an introduction starts from the virtual column -1).
+    if (c.tid == 0) {
+        int slots = 0, tmax = 0;
+        for (int b = 0; b < st.nbulge; ++b) {               // bulges already in flight (leading first)
+            const int q = st.kpos[b] - p;
+            const int fin = at_bottom ? (wl - 2) : (wl - 3 - 2 * b);
+            int m = fin - q; if (m < 0) m = 0;
+            sc->start[slots] = 0; sc->q0[slots] = q; sc->nrot[slots] = m; sc->shift_id[slots] = 0;
+            if (m > tmax) tmax = m;
+            ++slots;
+        }
+        if (p == st.lo && st.nbulge == 0) {                 // first window of the sweep: introduce the chain
+            int j = 0;
+            for (; st.nintro + j < st.ns && slots < QR_NS; ++j) {
+                const int fin = at_bottom ? (wl - 2) : (wl - 3 - 2 * j);
+                if (fin < 1) break;                           // no room for another bulge in this window
+                sc->start[slots] = 2 * j; sc->q0[slots] = -1; sc->nrot[slots] = 1 + fin; sc->shift_id[slots] = st.nintro + j;
+                if (2 * j + 1 + fin > tmax) tmax = 2 * j + 1 + fin;
+                ++slots;
+            }
+        }
+        sc->nslots = slots; sc->tmax = tmax;
+    }
     CTA_SYNC();
-
-    // local bulge columns (relative to p); -1 marks the virtual column of an introduction
-    for (;;) {
-        // ---- decide which rotations happen this step (uniform scalar code, every thread)
-        int nrot = 0;
-        int new_k[QR_NS];
-        int prev_new = 1 << 30;      // new position of the bulge ahead
-        int nb_after = 0;
-        int rrow[QR_NS + 1], rcol0[QR_NS + 1], rb[QR_NS + 1];
-        for (int b = 0; b < st.nbulge; ++b) {
-            const int k = st.kpos[b] - p;          // local column of the bulge (>= 0)
-            bool can = false, exits = false;
-            if (at_bottom) { if (k + 2 <= wl - 1) { can = true; exits = (k + 2 == wl - 1); } }
-            else if (k + 3 <= wl - 1) can = true;
-            if (can && !exits && !(k + 1 + 2 <= prev_new)) can = false;
-            if (can) { rrow[nrot] = k + 1; rcol0[nrot] = k; rb[nrot] = b; ++nrot; new_k[b] = exits ? -999 : k + 1; }
-            else new_k[b] = k;
-            if (new_k[b] != -999) prev_new = new_k[b];
-        }
-        // introduction of the next bulge at the top of the active block
-        bool intro = false;
-        if (p == st.lo && st.nintro < st.ns && wl >= 2) {
-            // rows (0,1) must be free this step and the new bulge (column 0) needs spacing 2 behind the
-            // trailing one: new position of the trailing bulge >= 2 (prev_new is huge when none is left)
-            if (prev_new >= 2) { intro = true; rrow[nrot] = 0; rcol0[nrot] = -1; rb[nrot] = -1; ++nrot; }
-        }
-        if (nrot == 0) break;
-        // ---- rotation parameters
-        if (c.tid < nrot) {
-            const int t = c.tid, r1 = rrow[t];
-            cplx a, b;
-            if (rcol0[t] < 0) { a = csub(Hs[0], st.shifts[st.nintro]); b = Hs[1 * QR_LD + 0]; }
-            else { a = Hs[r1 * QR_LD + rcol0[t]]; b = Hs[(r1 + 1) * QR_LD + rcol0[t]]; }
+    const int nslots = sc->nslots, tmax = sc->tmax;
+    for (int t = 0; t < tmax; ++t) {
+        // ---- rotation parameters (one thread per bulge slot)
+        for (int b = c.tid; b < nslots; b += c.nthreads) {
+            const int i = t - sc->start[b];
+            const bool on = (i >= 0 && i < sc->nrot[b]);
+            sc->act[b] = on ? 1 : 0;
+            if (!on) continue;
+            const int pos = sc->q0[b] + i, r1 = pos + 1;
+            cplx a, bb;
+            if (pos < 0) { a = csub(Hs[0], st.shifts[sc->shift_id[b]]); bb = Hs[1 * QR_LD + 0]; }
+            else { a = Hs[r1 * QR_LD + pos]; bb = Hs[(r1 + 1) * QR_LD + pos]; }
             // (a, b) both at round-off level (the chain runs over an already converged spot): a rotation
             // built from noise would scramble converged rows -> identity.  A tiny b next to a
             // non-negligible a is kept: small bulges still carry the shifts.
-            if (cabs1(a) + cabs1(b) <= RCWA_EPS * (cabs1(Hs[r1 * QR_LD + r1]) + cabs1(Hs[(r1 + 1) * QR_LD + r1 + 1]))) { a = C(0, 0); b = C(0, 0); }
+            if (cabs1(a) + cabs1(bb) <= RCWA_EPS * (cabs1(Hs[r1 * QR_LD + r1]) + cabs1(Hs[(r1 + 1) * QR_LD + r1 + 1]))) { a = C(0, 0); bb = C(0, 0); }
             double cs; cplx sn, r;
-            givens(a, b, cs, sn, r);
-            sc->cs[t] = cs; sc->sn[t] = sn;
-            if (rcol0[t] >= 0) { Hs[r1 * QR_LD + rcol0[t]] = r; Hs[(r1 + 1) * QR_LD + rcol0[t]] = C(0, 0); }
-#ifdef RCWA_EMU
-            if (getenv("RCWA_EMU_DEBUG2")) fprintf(stderr, "  rot t=%d r1=%d col0=%d nintro=%d shift=(%g,%g) a=(%g,%g) b=(%g,%g) c=%g s=(%g,%g)\n", t, r1, rcol0[t], st.nintro, st.shifts[st.nintro].x, st.shifts[st.nintro].y, a.x, a.y, b.x, b.y, cs, sn.x, sn.y);
-#endif
+            givens(a, bb, cs, sn, r);
+            sc->cs[b] = cs; sc->sn[b] = sn; sc->rr1[b] = r1;
+            if (pos >= 0) { Hs[r1 * QR_LD + pos] = r; Hs[(r1 + 1) * QR_LD + pos] = C(0, 0); }
         }
-#ifdef RCWA_EMU
-        for (int t = 1; t < nrot; ++t) {     // the single emulated thread plays threads 1..nrot-1
-            const int r1 = rrow[t];
-            cplx a, b;
-            if (rcol0[t] < 0) { a = csub(Hs[0], st.shifts[st.nintro]); b = Hs[1 * QR_LD + 0]; }
-            else { a = Hs[r1 * QR_LD + rcol0[t]]; b = Hs[(r1 + 1) * QR_LD + rcol0[t]]; }
-            // (a, b) both at round-off level (the chain runs over an already converged spot): a rotation
-            // built from noise would scramble converged rows -> identity.  A tiny b next to a
-            // non-negligible a is kept: small bulges still carry the shifts.
-            if (cabs1(a) + cabs1(b) <= RCWA_EPS * (cabs1(Hs[r1 * QR_LD + r1]) + cabs1(Hs[(r1 + 1) * QR_LD + r1 + 1]))) { a = C(0, 0); b = C(0, 0); }
-            double cs; cplx sn, r;
-            givens(a, b, cs, sn, r);
-            sc->cs[t] = cs; sc->sn[t] = sn;
-            if (rcol0[t] >= 0) { Hs[r1 * QR_LD + rcol0[t]] = r; Hs[(r1 + 1) * QR_LD + rcol0[t]] = C(0, 0); }
-        }
-#endif
         CTA_SYNC();
-        // ---- left: rows (r1, r1+1), columns from col0+1 (or 0 for an introduction) to wl-1
-        for (int idx = c.tid; idx < nrot * QR_W; idx += c.nthreads) {
-            const int t = idx / QR_W, j = idx % QR_W, r1 = rrow[t];
-            if (j <= rcol0[t] || j >= wl) continue;
-            const double cs = sc->cs[t]; const cplx sn = sc->sn[t];
+        // ---- left: rows (r1, r1+1), columns r1 .. wl-1 (column r1-1 was set explicitly above)
+        for (int idx = c.tid; idx < nslots * QR_W; idx += c.nthreads) {
+            const int b = idx / QR_W, j = idx % QR_W;
+            if (!sc->act[b]) continue;
+            const int r1 = sc->rr1[b];
+            if (j < r1 || j >= wl) continue;
+            const double cs = sc->cs[b]; const cplx sn = sc->sn[b];
             cplx x = Hs[r1 * QR_LD + j], y = Hs[(r1 + 1) * QR_LD + j];
             Hs[r1 * QR_LD + j] = cadd(cscale(x, cs), cmul(sn, y));
             Hs[(r1 + 1) * QR_LD + j] = csub(cscale(y, cs), cmul(cconj(sn), x));
         }
         CTA_SYNC();
         // ---- right: columns (r1, r1+1), rows 0..min(r1+2, wl-1) of H and all rows of U
-        for (int idx = c.tid; idx < nrot * 2 * QR_W; idx += c.nthreads) {
-            const int t = idx / (2 * QR_W), rem = idx % (2 * QR_W), r1 = rrow[t];
-            const double cs = sc->cs[t]; const cplx sn = sc->sn[t];
+        for (int idx = c.tid; idx < nslots * 2 * QR_W; idx += c.nthreads) {
+            const int b = idx / (2 * QR_W), rem = idx % (2 * QR_W);
+            if (!sc->act[b]) continue;
+            const int r1 = sc->rr1[b];
+            const double cs = sc->cs[b]; const cplx sn = sc->sn[b];
+            cplx* base;
             if (rem < QR_W) {
-                const int i = rem;
                 const int imax = (r1 + 2 < wl - 1) ? r1 + 2 : wl - 1;
-                if (i > imax) continue;
-                cplx x = Hs[i * QR_LD + r1], y = Hs[i * QR_LD + r1 + 1];
-                Hs[i * QR_LD + r1] = cadd(cscale(x, cs), cmul(y, cconj(sn)));
-                Hs[i * QR_LD + r1 + 1] = csub(cscale(y, cs), cmul(x, sn));
+                if (rem > imax) continue;
+                base = Hs + rem * QR_LD;
             } else {
-                const int i = rem - QR_W;
-                if (i >= wl) continue;
-                cplx x = Us[i * QR_LD + r1], y = Us[i * QR_LD + r1 + 1];
-                Us[i * QR_LD + r1] = cadd(cscale(x, cs), cmul(y, cconj(sn)));
-                Us[i * QR_LD + r1 + 1] = csub(cscale(y, cs), cmul(x, sn));
+                if (rem - QR_W >= wl) continue;
+                base = Us + (rem - QR_W) * QR_LD;
             }
+            cplx x = base[r1], y = base[r1 + 1];
+            base[r1] = cadd(cscale(x, cs), cmul(y, cconj(sn)));
+            base[r1 + 1] = csub(cscale(y, cs), cmul(x, sn));
         }
         CTA_SYNC();
-        // ---- bookkeeping (uniform)
-        nb_after = 0;
-        for (int b = 0; b < st.nbulge; ++b) if (new_k[b] != -999) st.kpos[nb_after++] = new_k[b] + p;
-        if (intro) {
-            ++st.nintro;
-            if (wl >= 3) st.kpos[nb_after++] = p + 0;        // bulge element now at H[p+2][p]
-        }
-        st.nbulge = nb_after;
-        (void)rb;
     }
 
     // ---------------- write back window and U, emit GEMM problems, advance state
@@ -494,25 +731,23 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         Ug[r * QR_W + q] = Us[r * QR_LD + q];
     }
     if (c.tid == 0) {
-        ZGemmProblem g;
-        // rows: H[p:wend, wend:n] <- U^H * H[p:wend, wend:n]
-        g.A = Ug; g.lda = QR_W; g.B = H + (size_t)p * ldh + wend; g.ldb = ldh; g.C = H + (size_t)p * ldh + wend; g.ldc = ldh;
-        g.M = (n - wend > 0) ? wl : 0; g.N = n - wend; g.K = wl; *prob_rows = g;
-        // cols: H[0:p, p:wend] <- H[0:p, p:wend] * U
-        g.A = H + p; g.lda = ldh; g.B = Ug; g.ldb = QR_W; g.C = H + p; g.ldc = ldh;
-        g.M = p; g.N = wl; g.K = wl; *prob_cols = g;
-        // Z[:, p:wend] <- Z[:, p:wend] * U
-        g.A = Zm + p; g.lda = ldz; g.B = Ug; g.ldb = QR_W; g.C = Zm + p; g.ldc = ldz;
-        g.M = n; g.N = wl; g.K = wl; *prob_z = g;
-        st.passes++;
-        if (st.nbulge == 0 && (st.nintro >= st.ns)) st.phase = 0;       // chain gone: next pass starts a new sweep
-        else if (st.nbulge == 0) st.phase = 0;                            // nothing could be introduced (tiny block)
-        else {
-            // next window starts at the trailing bulge (or stays at lo while bulges remain to be introduced)
-            int trail = st.kpos[st.nbulge - 1];
-            st.p = (st.nintro < st.ns && p == st.lo) ? trail : trail;
-            if (st.nintro < st.ns && p == st.lo) st.ns = st.nintro;      // window full: cap this sweep's shifts
+        int nb_after = 0, introduced = 0;
+        for (int b = 0; b < nslots; ++b) {
+            if (sc->q0[b] < 0) ++introduced;
+            if (at_bottom) continue;                          // every bulge ran off the bottom
+            const int fin = sc->q0[b] + sc->nrot[b];          // column after its last rotation
+            st.kpos[nb_after++] = p + fin;
         }
+        // the pass that ends a sweep is followed by a deflation scan / AED window that may reach above this
+        // window: its column update must be complete by then -> main stream; otherwise side stream
+        emit_window_gemms(H, ldh, n, Zm, ldz, Ug, p, wl, prob_rows, (nb_after == 0) ? prob_cols_main : prob_cols, prob_z);
+        st.p_last = (nb_after == 0) ? -1 : p;
+        st.nintro += introduced;
+        if (p == st.lo && st.nintro < st.ns) st.ns = st.nintro;      // window could not take more: cap this sweep
+        st.nbulge = nb_after;
+        st.passes++;
+        if (nb_after == 0) { st.phase = 0; st.shifts_ready = 0; }   // chain gone: next pass starts a new sweep
+        else st.p = st.kpos[nb_after - 1];                    // next window starts at the trailing bulge
         *stg = st;
     }
 }
@@ -560,17 +795,18 @@ static void emu_gemm(const ZGemmProblem& g, int opa) {
 // H (upper Hessenberg, n x n) -> T in place, Z <- Z U.  Returns info; stats[0..2] = sweeps, passes, done.
 extern "C" int emu_qr(cplx* H, cplx* Z, int n, int max_passes, int* stats) {
     std::vector<char> smem(qr_pass_smem_bytes(n));
-    std::vector<cplx> U((size_t)QR_W * QR_W);
+    std::vector<cplx> U((size_t)QR_W * QR_W), Tgbuf((size_t)QR_W * QR_W), Vgbuf((size_t)QR_W * QR_W);
     QrState st; memset(&st, 0, sizeof(st));
-    st.lo = 0; st.hi = n - 1; st.hi_prev = n - 1;
-    Cta c; c.tid = 0; c.nthreads = 1; c.bid = 0; c.smem = smem.data();
-    ZGemmProblem pr, pc, pz;
+    st.lo = 0; st.hi = n - 1; st.hi_prev = n - 1; st.p_last = -1;
+    Cta c; c.tid = 0; c.nthreads = 1; c.bid = 0; c.smem = smem.data(); c.warp_only = 0;
+    ZGemmProblem pr, pcm, pc, pz;
     int it = 0;
     for (; it < max_passes && !st.done; ++it) {
-        qr_pass_body(c, H, n, n, Z, n, &st, U.data(), &pr, &pc, &pz);
-        emu_gemm(pr, 2); emu_gemm(pc, 0); emu_gemm(pz, 0);
+        qr_pass_body(c, H, n, n, Z, n, &st, U.data(), Vgbuf.data(), Tgbuf.data(), &pr, &pcm, &pc, &pz);
+        emu_gemm(pr, 2); emu_gemm(pcm, 0); emu_gemm(pc, 0); emu_gemm(pz, 0);
     }
     stats[0] = st.sweeps; stats[1] = st.passes; stats[2] = st.done; stats[3] = st.small_solves;
+    stats[4] = st.aeds; stats[5] = st.aed_deflated;
     return st.done ? st.info : -1;
 }
 
@@ -609,214 +845,16 @@ extern "C" int emu_trevc(const cplx* T, int n, cplx* X) {
 // =============================================================================== device code
 namespace {
 
-// ---------------------------------------------------------------- phase 1: Hessenberg reduction
-// Extended row space: rows [0,n) = A, rows [n,2n) = Z.
-#define HS_ROWS_PER_CTA 64     // row band per CTA in the fused pass (8 warps x 8 rows)
-#define HS_CHUNK 4             // columns per lane per chunk (=> 128 columns per warp iteration)
-
-// Per-matrix vectors, all length 2n unless noted (workspace layout, complex):
-//   u[n], unext[n], wt[n] (w~), y[2n] (raw y of the *next* step, written by the fused pass),
-//   yt[2n] (y~ of the current step), wpart[nbands][n] (raw partial w of the next step)
-struct HessVecs { cplx *u, *unext, *wt, *y, *yt, *wpart; cplx* beta; };
-
-__device__ __forceinline__ HessVecs hess_vecs(cplx* base, int n, int nbands) {
-    HessVecs v;
-    v.u = base; v.unext = v.u + n; v.wt = v.unext + n; v.y = v.wt + n; v.yt = v.y + 2 * n; v.wpart = v.yt + 2 * n;
-    v.beta = v.wpart + (size_t)nbands * n;
-    return v;
-}
-__host__ __device__ inline size_t hess_vec_elems(int n, int nbands) { return (size_t)n * 3 + 4 * (size_t)n + (size_t)nbands * n + 8; }
-
-// Step kernel, one CTA per matrix.  On entry (k >= 0): u = u_k, y = raw A u_k (2n), wpart = raw
-// partial sums of u_k^H A.  Produces y~, w~ of step k, then the reflector u_{k+1} from the updated
-// column k+1.  For k == -1 (bootstrap) there is no pending update: it only builds u_0 from column 0
-// and the caller then runs a "pure accumulate" fused pass.
-__global__ void __launch_bounds__(512, 1)
-hess_step_kernel(cplx* A, long long astride, int lda, int n, int k, cplx* vecs, long long vstride, int nbands) {
-    __shared__ double red[40];
-    __shared__ cplx sh_c[2];
-    const int b = blockIdx.x;
-    cplx* Ab = A + (size_t)b * astride;
-    HessVecs v = hess_vecs(vecs + (size_t)b * vstride, n, nbands);
-    Cta c = make_cta(b, nullptr);
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int kn = k + 1;                 // column that becomes the next reflector source
-    if (k >= 0) {
-        // raw w_j = sum over bands ; gamma = sum_j w_j u_j
-        double gr = 0.0, gi = 0.0;
-        for (int j = k + 1 + tid; j < n; j += nt) {
-            cplx w = C(0, 0);
-            const int nba = (n + HS_ROWS_PER_CTA - 1) / HS_ROWS_PER_CTA;     // bands that contain rows of A
-            for (int q = 0; q < nba; ++q) w = cadd(w, v.wpart[(size_t)q * n + j]);
-            v.wt[j] = w;
-            cplx t = cmul(w, v.u[j]);
-            gr += t.x; gi += t.y;
-        }
-        gr = cta_sum(c, gr, red); gi = cta_sum(c, gi, red);
-        const cplx hg = C(0.5 * gr, 0.5 * gi);
-        for (int j = k + 1 + tid; j < n; j += nt) v.wt[j] = csub(v.wt[j], cmul(hg, cconj(v.u[j])));
-        for (int i = tid; i < 2 * n; i += nt) {
-            cplx ui = (i < n && i > k) ? v.u[i] : C(0, 0);
-            v.yt[i] = csub(v.y[i], cmul(hg, ui));
-        }
-        __syncthreads();
-    }
-    if (kn > n - 3) {       // no further reflector: mark u_next = 0
-        for (int i = tid; i < n; i += nt) v.unext[i] = C(0, 0);
-        return;
-    }
-    // updated column kn, rows i >= kn+1 (held in unext for now)
-    double ss = 0.0;
-    for (int i = kn + 1 + tid; i < n; i += nt) {
-        cplx a = Ab[(size_t)i * lda + kn];
-        if (k >= 0) {
-            a = csub(a, cmul(v.u[i], v.wt[kn]));
-            a = csub(a, cmul(v.yt[i], cconj(v.u[kn])));
-        }
-        v.unext[i] = a;
-        ss += cabs2(a);
-    }
-    for (int i = tid; i <= kn && i < n; i += nt) v.unext[i] = C(0, 0);
-    // scaled norm is unnecessary here: entries are O(|A|) and fp64 range is ample
-    ss = cta_sum(c, ss, red);
-    const double sigma = sqrt(ss);
-    if (tid == 0) {
-        cplx x1 = v.unext[kn + 1];
-        cplx beta, ph;
-        double ax = cabs_(x1);
-        if (sigma == 0.0) { sh_c[0] = C(0, 0); sh_c[1] = C(0, 0); v.beta[0] = x1; }
-        else {
-            ph = (ax == 0.0) ? C(1, 0) : cscale(x1, 1.0 / ax);
-            beta = cscale(ph, -sigma);
-            sh_c[0] = beta;
-            sh_c[1] = C(1.0 / sqrt(sigma * (sigma + ax)), 0.0);
-            v.beta[0] = beta;
-        }
-    }
-    __syncthreads();
-    const cplx beta = sh_c[0];
-    const double sc = sh_c[1].x;
-    if (sc == 0.0) {
-        for (int i = kn + 1 + tid; i < n; i += nt) v.unext[i] = C(0, 0);
-    } else {
-        for (int i = kn + 1 + tid; i < n; i += nt) {
-            cplx a = v.unext[i];
-            if (i == kn + 1) a = csub(a, beta);
-            v.unext[i] = cscale(a, sc);
-        }
-    }
-}
-
-// Fused streaming pass over rows of [A; Z], columns [k+1, n):
-//   a_ij <- a_ij - u_i w~_j - y~_i conj(u_j)      (skipped when k < 0)
-//   column k+1: rows <= k+1 keep the updated value, row k+2 <- beta', rows > k+2 <- 0  (A rows only)
-//   y'_i = sum_{j >= k+2} a_ij u'_j ;  wpart[band][j] = sum_{i in band} conj(u'_i) a_ij   (j >= k+2)
-// grid (nbands_total = ceil(2n/64), B), 256 threads.
-__global__ void __launch_bounds__(256)
-hess_fused_kernel(cplx* A, long long astride, int lda, cplx* Z, long long zstride, int ldz, int n, int k,
-                  cplx* vecs, long long vstride, int nbands) {
-    __shared__ cplx wsh[8][128];       // per-warp partial column sums of the current chunk
-    const int b = blockIdx.y, band = blockIdx.x;
-    HessVecs v = hess_vecs(vecs + (size_t)b * vstride, n, nbands);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = band * HS_ROWS_PER_CTA + warp * 8;
-    const bool a_band = (band * HS_ROWS_PER_CTA < n);     // bands never straddle A/Z when n % 64 != 0? handled per row
-    const int kn = k + 1;
-    const bool has_next = (kn <= n - 3);
-    const cplx beta_n = v.beta[0];
-    cplx* rowp[8]; cplx ui[8], uin[8], yti[8]; bool is_a[8]; int ri[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const int i = row0 + r;
-        ri[r] = i;
-        if (i < n) { rowp[r] = A + (size_t)b * astride + (size_t)i * lda; is_a[r] = true; }
-        else if (i < 2 * n) { rowp[r] = Z + (size_t)b * zstride + (size_t)(i - n) * ldz; is_a[r] = false; }
-        else { rowp[r] = nullptr; is_a[r] = false; }
-        ui[r] = (k >= 0 && i < n && i > k) ? v.u[i] : C(0, 0);
-        uin[r] = (i < n && i > kn) ? cconj(v.unext[i]) : C(0, 0);
-        yti[r] = (k >= 0 && i < 2 * n) ? v.yt[i] : C(0, 0);
-    }
-    cplx yacc[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) yacc[r] = C(0, 0);
-    const int jstart = kn - (kn % 128);        // aligned chunk start keeps 512-byte coalescing
-    (void)a_band;
-    for (int j0 = jstart; j0 < n; j0 += 128) {
-        cplx wt[HS_CHUNK], ucj[HS_CHUNK], unj[HS_CHUNK], wacc[HS_CHUNK];
-        int jj[HS_CHUNK];
-#pragma unroll
-        for (int q = 0; q < HS_CHUNK; ++q) {
-            const int j = j0 + q * 32 + lane;
-            jj[q] = j;
-            const bool in = (j >= kn && j < n);
-            wt[q] = (in && k >= 0) ? v.wt[j] : C(0, 0);
-            ucj[q] = (in && k >= 0) ? cconj(v.u[j]) : C(0, 0);
-            unj[q] = (in && j > kn) ? v.unext[j] : C(0, 0);
-            wacc[q] = C(0, 0);
-        }
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            if (!rowp[r]) continue;
-#pragma unroll
-            for (int q = 0; q < HS_CHUNK; ++q) {
-                const int j = jj[q];
-                if (j < kn || j >= n) continue;
-                cplx a = rowp[r][j];
-                if (k >= 0) {
-                    a = csub(a, cmul(ui[r], wt[q]));
-                    a = csub(a, cmul(yti[r], ucj[q]));
-                }
-                if (j == kn && is_a[r] && has_next) {
-                    // this column is the source of reflector k+1: H_{k+1} x = beta e_1
-                    if (ri[r] == kn + 1) a = beta_n;
-                    else if (ri[r] > kn + 1) a = C(0, 0);
-                }
-                if (k >= 0 || (j == kn && is_a[r] && has_next)) rowp[r][j] = a;
-                if (j > kn) {
-                    yacc[r] = cfma(a, unj[q], yacc[r]);
-                    wacc[q] = cfma(uin[r], a, wacc[q]);
-                }
-            }
-        }
-        // column partial sums of this chunk: warp-private slots, then reduce over the 8 warps
-#pragma unroll
-        for (int q = 0; q < HS_CHUNK; ++q) wsh[warp][q * 32 + lane] = wacc[q];
-        __syncthreads();
-        if (threadIdx.x < 128) {
-            const int j = j0 + threadIdx.x;
-            if (j > kn && j < n && band * HS_ROWS_PER_CTA < n) {
-                cplx s = C(0, 0);
-#pragma unroll
-                for (int w = 0; w < 8; ++w) s = cadd(s, wsh[w][threadIdx.x]);
-                v.wpart[(size_t)band * n + j] = s;
-            }
-        }
-        __syncthreads();
-    }
-    // row dot products
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        double yr = warp_sum(yacc[r].x), yi = warp_sum(yacc[r].y);
-        if (lane == 0 && ri[r] < 2 * n) v.y[ri[r]] = C(yr, yi);
-    }
-}
-
-__global__ void hess_advance_kernel(cplx* vecs, long long vstride, int n, int nbands) {
-    // u <- unext
-    HessVecs v = hess_vecs(vecs + (size_t)blockIdx.y * vstride, n, nbands);
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v.u[i] = v.unext[i];
-}
-
 // ---------------------------------------------------------------- phase 2: QR passes
 __global__ void __launch_bounds__(512, 1)
 qr_pass_kernel(cplx* H, long long hstride, int ldh, int n, cplx* Z, long long zstride, int ldz, QrState* states,
-               cplx* U, ZGemmProblem* prows, ZGemmProblem* pcolsz) {
+               cplx* U, cplx* Vg, cplx* Tg, ZGemmProblem* prows, ZGemmProblem* pcols_main, ZGemmProblem* pcolsz) {
     extern __shared__ __align__(16) char smem_raw[];
     const int b = blockIdx.x;
     Cta c = make_cta(b, smem_raw);
     qr_pass_body(c, H + (size_t)b * hstride, ldh, n, Z + (size_t)b * zstride, ldz, states + b,
-                 U + (size_t)b * QR_W * QR_W, prows + b, pcolsz + 2 * b, pcolsz + 2 * b + 1);
+                 U + (size_t)b * QR_W * QR_W, Vg + (size_t)b * QR_W * QR_W, Tg + (size_t)b * QR_W * QR_W,
+                 prows + b, pcols_main + b, pcolsz + 2 * b, pcolsz + 2 * b + 1);
 }
 
 __global__ void qr_init_kernel(QrState* states, int n, int nb) {
@@ -824,7 +862,7 @@ __global__ void qr_init_kernel(QrState* states, int n, int nb) {
     if (b >= nb) return;
     QrState st;
     memset(&st, 0, sizeof(st));
-    st.lo = 0; st.hi = n - 1; st.hi_prev = n - 1;
+    st.lo = 0; st.hi = n - 1; st.hi_prev = n - 1; st.p_last = -1;
     if (n < 2) st.done = 1;
     states[b] = st;
 }
@@ -839,6 +877,13 @@ __global__ void qr_count_kernel(const QrState* states, int nb, int* flag_dev) {
     atomicAdd(&cnt, local);
     __syncthreads();
     if (threadIdx.x == 0) *flag_dev = cnt;
+}
+
+__global__ void qr_stats_kernel(const QrState* states, int nb, int* out) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    out[4 * b + 0] = states[b].sweeps; out[4 * b + 1] = states[b].passes;
+    out[4 * b + 2] = states[b].aeds; out[4 * b + 3] = states[b].done ? states[b].info : -1;
 }
 
 __global__ void qr_finish_kernel(const QrState* states, int nb, int* info) {
@@ -905,21 +950,22 @@ __global__ void colscale_kernel(cplx* V, long long vstride, int ldv, int n, cons
 inline size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct EigWs {
-    cplx *Z, *X, *U, *vecs; QrState* states; ZGemmProblem *prows, *pcolsz, *gs; int* flag; double *tnorm, *nrm;
-    size_t total; int nbands; long long vstride;
+    cplx *Z, *X, *U, *Vg, *Tg; char* hess; QrState* states; ZGemmProblem *prows, *pcols_main, *pcolsz, *gs; int* flag; double *tnorm, *nrm;
+    size_t total;
 };
 EigWs carve(char* base, int n, int nb) {
     EigWs w; size_t off = 0;
     auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += al(bytes); return p; };
-    w.nbands = (2 * n + HS_ROWS_PER_CTA - 1) / HS_ROWS_PER_CTA;
-    w.vstride = (long long)hess_vec_elems(n, w.nbands);
     w.Z = (cplx*)take(sizeof(cplx) * (size_t)n * n * nb);
     w.X = (cplx*)take(sizeof(cplx) * (size_t)n * n * nb);
-    w.U = (cplx*)take(sizeof(cplx) * (size_t)QR_W * QR_W * nb);
-    w.vecs = (cplx*)take(sizeof(cplx) * (size_t)w.vstride * nb);
+    w.U = (cplx*)take(sizeof(cplx) * (size_t)QR_W * QR_W * nb * 2);      // double-buffered window unitaries
+    w.Vg = (cplx*)take(sizeof(cplx) * (size_t)QR_W * QR_W * nb);
+    w.Tg = (cplx*)take(sizeof(cplx) * (size_t)QR_W * QR_W * nb);
+    w.hess = take(rcwa::hessenberg_workspace_bytes(n, nb));
     w.states = (QrState*)take(sizeof(QrState) * (size_t)nb);
     w.prows = (ZGemmProblem*)take(sizeof(ZGemmProblem) * (size_t)nb);
-    w.pcolsz = (ZGemmProblem*)take(sizeof(ZGemmProblem) * (size_t)nb * 2);
+    w.pcols_main = (ZGemmProblem*)take(sizeof(ZGemmProblem) * (size_t)nb);
+    w.pcolsz = (ZGemmProblem*)take(sizeof(ZGemmProblem) * (size_t)nb * 2 * 2);   // double-buffered
     w.gs = (ZGemmProblem*)take(sizeof(ZGemmProblem) * (size_t)nb * 4);
     w.flag = (int*)take(256);
     w.tnorm = (double*)take(sizeof(double) * (size_t)nb);
@@ -937,22 +983,14 @@ size_t eig_workspace_bytes(int n, int nb) { return carve(nullptr, n, nb).total; 
 #define EK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
 
 static cudaError_t hessenberg_phase(cplx* A, int n, int nb, const EigWs& ws, cudaStream_t st) {
-    const long long ms = (long long)n * n;
-    EK(set_identity(ws.Z, n, n, ms, nb, st));
-    if (n >= 3) {
-        const dim3 fgrid(ws.nbands, nb);
-        // bootstrap: u_0 from column 0, then a pure accumulate pass (k = -1)
-        hess_step_kernel<<<nb, 512, 0, st>>>(A, ms, n, n, -1, ws.vecs, ws.vstride, ws.nbands);
-        hess_fused_kernel<<<fgrid, 256, 0, st>>>(A, ms, n, ws.Z, ms, n, n, -1, ws.vecs, ws.vstride, ws.nbands);
-        hess_advance_kernel<<<dim3((n + 255) / 256, nb), 256, 0, st>>>(ws.vecs, ws.vstride, n, ws.nbands);
-        for (int k = 0; k <= n - 3; ++k) {
-            hess_step_kernel<<<nb, 512, 0, st>>>(A, ms, n, n, k, ws.vecs, ws.vstride, ws.nbands);
-            hess_fused_kernel<<<fgrid, 256, 0, st>>>(A, ms, n, ws.Z, ms, n, n, k, ws.vecs, ws.vstride, ws.nbands);
-            hess_advance_kernel<<<dim3((n + 255) / 256, nb), 256, 0, st>>>(ws.vecs, ws.vstride, n, ws.nbands);
-        }
-        EK(cudaGetLastError());
-    }
-    return cudaSuccess;
+    return rcwa::hessenberg_blocked(A, n, nb, ws.Z, ws.hess, st);      // hess.cu
+}
+
+// diagnostics of the last eig() run that used this workspace: per matrix {sweeps, passes, AED windows, info}
+cudaError_t eig_stats(const char* wsb, int n, int nb, int* out, cudaStream_t st) {
+    EigWs ws = carve(const_cast<char*>(wsb), n, nb);
+    qr_stats_kernel<<<(nb + 127) / 128, 128, 0, st>>>(ws.states, nb, out);
+    return cudaGetLastError();
 }
 
 // A -> H (upper Hessenberg, in place), Zout = accumulated reflectors (A_in = Z H Z^H)
@@ -980,17 +1018,31 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
     const int poll = 64;
     const int max_tiles_rows = gemm_tiles(GEMM_TILE_64x128, QR_W, n);
     const int max_tiles_cz = gemm_tiles(GEMM_TILE_128x64, n, QR_W);
-    // The host polls convergence with a lag of one group: the count of group g is copied to pinned
-    // memory asynchronously and examined after group g+1 has been enqueued, so the device never idles.
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    // Two streams: the main stream carries the serial chain  pass -> row-panel GEMM -> next pass ; the
+    // column-panel and Z updates of a chase pass (2/3 of the flops) run on a side stream, overlapping the
+    // next pass.  Window unitaries and side-stream descriptors are double-buffered; pass k+2 waits for the
+    // side GEMMs of pass k.  The host polls convergence with a lag of one group: the count of group g is
+    // copied to pinned memory asynchronously and examined after group g+1 has been enqueued.
+    cudaStream_t sb = nullptr;
+    EK(cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking));
+    cudaEvent_t ev_pass[2], ev_side[2], ev[2] = {nullptr, nullptr};
+    for (int q = 0; q < 2; ++q) { EK(cudaEventCreateWithFlags(&ev_pass[q], cudaEventDisableTiming)); EK(cudaEventCreateWithFlags(&ev_side[q], cudaEventDisableTiming)); }
     int* hf = const_cast<int*>(host_flag);
     if (hf) { EK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming)); EK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming)); hf[0] = hf[1] = nb; }
     long long group = 0;
     bool finished = false;
+    const size_t ustride = (size_t)QR_W * QR_W * nb;
     for (long long it = 0; it < max_passes && !finished; ++it) {
-        qr_pass_kernel<<<nb, 512, smem, st>>>(A, ms, n, n, ws.Z, ms, n, ws.states, ws.U, ws.prows, ws.pcolsz);
+        const int buf = (int)(it & 1);
+        if (it >= 2) EK(cudaStreamWaitEvent(st, ev_side[buf], 0));          // U[buf] / descriptors[buf] are free again
+        qr_pass_kernel<<<nb, 512, smem, st>>>(A, ms, n, n, ws.Z, ms, n, ws.states, ws.U + buf * ustride, ws.Vg, ws.Tg,
+                                               ws.prows, ws.pcols_main, ws.pcolsz + (size_t)buf * 2 * nb);
+        EK(cudaEventRecord(ev_pass[buf], st));
         EK(zgemm_grouped(GEMM_TILE_64x128, OP_H, OP_N, ws.prows, nb, max_tiles_rows, one, zero, st));
-        EK(zgemm_grouped(GEMM_TILE_128x64, OP_N, OP_N, ws.pcolsz, 2 * nb, max_tiles_cz, one, zero, st));
+        EK(zgemm_grouped(GEMM_TILE_128x64, OP_N, OP_N, ws.pcols_main, nb, max_tiles_cz, one, zero, st));
+        EK(cudaStreamWaitEvent(sb, ev_pass[buf], 0));
+        EK(zgemm_grouped(GEMM_TILE_128x64, OP_N, OP_N, ws.pcolsz + (size_t)buf * 2 * nb, 2 * nb, max_tiles_cz, one, zero, sb));
+        EK(cudaEventRecord(ev_side[buf], sb));
         if (hf && (it % poll) == poll - 1) {
             const int slot = (int)(group & 1);
             if (group >= 1) {       // examine the previous group's count (its copy was enqueued one group ago)
@@ -1003,8 +1055,13 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
             ++group;
         }
     }
+    // join the side stream before anything reads H or Z
+    EK(cudaStreamWaitEvent(st, ev_side[0], 0));
+    EK(cudaStreamWaitEvent(st, ev_side[1], 0));
+    for (int q = 0; q < 2; ++q) { cudaEventDestroy(ev_pass[q]); cudaEventDestroy(ev_side[q]); }
     if (ev[0]) cudaEventDestroy(ev[0]);
     if (ev[1]) cudaEventDestroy(ev[1]);
+    cudaStreamDestroy(sb);
     qr_finish_kernel<<<(nb + 127) / 128, 128, 0, st>>>(ws.states, nb, info);
 
     // ---------------- phase 3: eigenvalues, eigenvectors of T, back-transformation, normalisation

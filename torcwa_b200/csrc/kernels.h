@@ -33,6 +33,9 @@ cudaError_t layer_form(const cplx* W, const cplx* QW, const cplx* kz, const cplx
                        const double* thick, int nb, int N, cplx* Mp, cplx* Mm, cplx* Rp, cplx* Rm, cudaStream_t st);
 cudaError_t layer_finish(const cplx* Tp, const cplx* Tm, int nb, int n, cplx* S11, cplx* S21, cudaStream_t st);
 cudaError_t blockdiag_dense(const cplx* d4, int nb, int N, cplx* D, cudaStream_t st);
+cudaError_t bd_left_mul(const cplx* d4, const cplx* X, int nb, int N, int ncols, cplx alpha, cplx beta, cplx* Y, cudaStream_t st);
+cudaError_t bd_right_mul(const cplx* d4, const cplx* X, int nb, int N, int nrows, cplx alpha, cplx beta, cplx* Y, cudaStream_t st);
+cudaError_t bd_add(const cplx* d4, int nb, int N, cplx alpha, cplx* D, cudaStream_t st);
 cudaError_t set_identity(cplx* A, int n, int lda, long long stride, int nb, cudaStream_t st);
 cudaError_t axpby(cplx alpha, const cplx* X, cplx beta, cplx* Y, size_t total, cudaStream_t st);
 
@@ -42,8 +45,13 @@ cudaError_t lu_factor(cplx* A, long long stride, int n, int lda, int nb, int* ip
 cudaError_t lu_solve_right(const cplx* LU, long long lustride, int n, int lda, const int* perm, const cplx* Bm, long long bstride,
                            int ldb, int nrows, cplx* X, long long xstride, int ldx, int nb, ZGemmProblem* gscratch, cudaStream_t st);
 
+// ---- hess.cu
+size_t hessenberg_workspace_bytes(int n, int nb);
+cudaError_t hessenberg_blocked(cplx* A, int n, int nb, cplx* Z, char* ws, cudaStream_t st);
+
 // ---- eig.cu
 size_t eig_workspace_bytes(int n, int nb);
+cudaError_t eig_stats(const char* ws, int n, int nb, int* out, cudaStream_t st);
 cudaError_t hessenberg(cplx* A, int n, int nb, cplx* Zout, char* ws, size_t ws_bytes, cudaStream_t st);
 cudaError_t eig(cplx* A, int n, int nb, cplx* w, cplx* V, char* ws, size_t ws_bytes, int* info, volatile int* host_flag, cudaStream_t st);
 

@@ -134,7 +134,7 @@ DEV void trsm_row(cplx* x, const cplx* T, int ldt, int nbe, int mode) {
 // ------------------------------------------------------------------ CPU emulation entry points (tests only)
 extern "C" int emu_lu_factor(cplx* A, int n, int lda, int* ipiv, int* perm, int* info) {
     char smem[65536];
-    Cta c; c.tid = 0; c.nthreads = 1; c.bid = 0; c.smem = smem;
+    Cta c; c.tid = 0; c.nthreads = 1; c.bid = 0; c.smem = smem; c.warp_only = 0;
     *info = 0;
     for (int k0 = 0; k0 < n; k0 += LU_NB) {
         int nbe = (n - k0 < LU_NB) ? n - k0 : LU_NB;

@@ -240,25 +240,33 @@ class rcwa:
                 self.E_eigvec.append(self._pub(torch.eye(2 * N, dtype=_C, device=self._device).expand(B, -1, -1)))
         else:
             E = self._b(eps)[:, None, None] * torch.eye(N, dtype=_C, device=self._device) if he else self._conv(eps)
+            E = E.contiguous()
             eta, info_e = _lib.inverse(E)
             if hm:
-                P, Q = _lib.pq_assemble(eta, E.contiguous(), kx, ky, mu_scalar=self._b(mu).contiguous())
+                P, Q = _lib.pq_assemble(eta, E, kx, ky, mu_scalar=self._b(mu).contiguous())
                 M = None
             else:
                 M = self._conv(mu)
                 nu, _ = _lib.inverse(M)
-                P, Q = _lib.pq_assemble(eta, E.contiguous(), kx, ky, Mc=M, nu=nu)
+                P, Q = _lib.pq_assemble(eta, E, kx, ky, Mc=M, nu=nu)
+                del nu
+            del eta
+            if self._store:
+                self.eps_conv.append(self._pub(E))
+                self.mu_conv.append(self._pub(M if M is not None else self._b(mu)[:, None, None] * torch.eye(N, dtype=_C, device=self._device)))
+                self.P.append(self._pub(P)); self.Q.append(self._pub(Q))
+            del E, M
             A = _lib.zgemm(P, Q)
+            del P                                  # free early: a batch chunk is sized by its peak footprint
             lam, W, info = _lib.eig(A)
             del A
             self.eig_info.append(info)
             kz = _lib.kz_branch(lam)
             S11, S21, info_s = _lib.layer_smatrix(W, kz, Q, self._Vf_inv, omega, thick)
+            del Q
             if self._store:
-                self.eps_conv.append(self._pub(E))
-                self.mu_conv.append(self._pub(M if M is not None else self._b(mu)[:, None, None] * torch.eye(N, dtype=_C, device=self._device)))
-                self.P.append(self._pub(P)); self.Q.append(self._pub(Q))
                 self.E_eigvec.append(self._pub(W))
+            del W
         self.kz_norm.append(self._pub(kz))
         self.layer_N += 1
         self.thickness.append(thickness)
@@ -300,7 +308,7 @@ class rcwa:
             zero = torch.zeros((B, n, n), dtype=_C, device=self._device)
             S = [eye, zero, zero.clone(), eye.clone()]
         if hasattr(self, 'Sin'):
-            S, _ = _lib.redheffer([_lib.blockdiag_dense(s.contiguous()) for s in self._Sin], S)
+            S, _ = _lib.redheffer_bdleft(self._Sin, S)          # Sin is four-diagonal: O(n^2) instead of 6 GEMMs
         if hasattr(self, 'Sout'):
             S, _ = _lib.redheffer(S, [_lib.blockdiag_dense(s.contiguous()) for s in self._Sout])
         self._S = S
