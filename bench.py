@@ -136,27 +136,26 @@ def bench_b200(args):
         dist.init_process_group("nccl", device_id=device)
     case, mask, lams = sweep_inputs(args.order)
     P = args.points
-    # this rank's slice of the sweep; chunks of P wavelengths, cycled if K*P exceeds the slice
-    per_rank = N_SWEEP // world
-    my = torch.arange(rank * per_rank, (rank + 1) * per_rank)
-    n_chunks = max(per_rank // P, 1)
-    grids_host = make_grids(mask, lams[my]).pin_memory()                 # [per_rank,300,300] c64, pinned
-    freq_host = (1.0 / lams[my]).pin_memory()
+    # Weak scaling: every rank solves P wavelengths per step.  Chunk c of the sweep = wavelengths
+    # [c*P, (c+1)*P) mod 512; in step s rank r takes chunk (s*world + r), so ranks and steps never share
+    # inputs until the 512-point sweep wraps around.
+    grids_host = make_grids(mask, lams).pin_memory()                     # [512,300,300] c64, pinned
+    freq_host = (1.0 / lams).pin_memory()
     grids_res = grids_host.to(device)                                    # resident copy for the device-timed leg
     freq_res = freq_host.to(device)
 
     def chunk(s):
-        c = (s % n_chunks) * P
-        return slice(c, c + P)
+        c = s * world + rank
+        return (torch.arange(P) + c * P) % N_SWEEP
 
     def step_resident(s):
-        sl = chunk(s)
+        sl = chunk(s).to(device)
         return run_step(grids_res[sl], freq_res[sl], case, device)
 
     def step_e2e(s):
         sl = chunk(s)
-        g = grids_host[sl].to(device, non_blocking=True)
-        f = freq_host[sl].to(device, non_blocking=True)
+        g = grids_host[sl].pin_memory().to(device, non_blocking=True)     # host gather of this step's wavelengths, then H2D
+        f = freq_host[sl].pin_memory().to(device, non_blocking=True)
         out = run_step(g, f, case, device)
         if world > 1:
             full = torch.empty((world,) + tuple(torch.view_as_real(out).shape), dtype=torch.float32, device=device)
@@ -202,7 +201,9 @@ def bench_b200(args):
         # ---- stage split and roofline of the eigen stage (untimed extra step on rank 0)
         from torcwa_b200 import _lib
         launches, per_kernel = count_my_launches(lambda: step_resident(0))
-        sim_stage = stage_times(case, grids_res[chunk(0)], freq_res[chunk(0)], device)
+        sl0 = chunk(0).to(device)
+        sim_stage = stage_times(case, grids_res[sl0][:min(P, 32)].contiguous(), freq_res[sl0][:min(P, 32)].contiguous(), device)
+        Ps = min(P, 32)
         b_eig = 16.0 * (n ** 3 / 3.0 + 2.0 * n * n)                      # SURVEY.md 8d, s = 16 (fp64 internals)
         peaks = {}
         try:
@@ -213,8 +214,8 @@ def bench_b200(args):
         peak_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
         dom = max(per_kernel.items(), key=lambda kv: kv[1][1])[0] if launches else None
         t_h = sim_stage["hessenberg_alone_ms"]
-        achieved_h = P * b_eig / (t_h * 1e-3) / 1e9
-        achieved_eig = P * b_eig / (sim_stage["eig_ms"] * 1e-3) / 1e9
+        achieved_h = Ps * b_eig / (t_h * 1e-3) / 1e9
+        achieved_eig = Ps * b_eig / (sim_stage["eig_ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "hb_matvec_kernel (streaming mat-vec of the blocked Hessenberg phase of rcwa_eig; phase timed alone with CUDA events)",
                 "achieved": achieved_h, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_h / hbm_peak,
                 "traffic": None, "peak_source": peak_src,
@@ -235,7 +236,7 @@ def bench_b200(args):
             "gpu_launches_per_step": launches,
             "clocks": clk,
             "roofline": roof,
-            "stage_ms_per_batch": sim_stage,
+            "stage_ms_per_batch": dict(sim_stage, batch=Ps),
             "dominant_kernel_by_time": dom,
             "kernel_time_share": {k: round(v[1] / max(sum(x[1] for x in per_kernel.values()), 1e-9), 4) for k, v in
                                   sorted(per_kernel.items(), key=lambda kv: -kv[1][1])[:8]} if launches else per_kernel,
@@ -363,10 +364,10 @@ def bench_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--points", type=int, default=32, help="wavelengths per step per GPU")
+    ap.add_argument("--points", type=int, default=96, help="wavelengths per step per GPU (peak footprint ~0.7 GB each)")
     ap.add_argument("--order", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)

@@ -60,14 +60,17 @@ int rcwa_zgemm_batched(int opa, int opb, int M, int N, int K, double alpha_re, d
                        int nb, void* gemm_scratch, void* stream);
 
 /* In-place LU with column pivoting for right-solves X*A = B (A*Pi = L*U, L lower, U unit upper).
- * ipiv, perm: int32 [nb,n]; info int32 [nb].
+ * ipiv, perm: int32 [nb,n]; info int32 [nb]; tinv: rcwa_lu_tinv_bytes(n, nb) bytes receiving the
+ * inverses of the 128 x 128 diagonal blocks of L and U (they turn the triangular solves into GEMMs).
  * Replaces torch.linalg.inv call sites (rcwa.py:1226,1230,1248,1266-1267,1271,1273,1287-1288). */
+size_t rcwa_lu_tinv_bytes(int n, int nb);
 int rcwa_lu_factor(void* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info,
-                   void* gemm_scratch, void* stream);
-/* X[b] (nrows x n) = B[b] * A[b]^-1 given rcwa_lu_factor output; X must not alias B. */
-int rcwa_lu_solve_right(const void* LU, long long lu_stride, int n, int lda, const int* perm,
+                   void* tinv, void* gemm_scratch, void* stream);
+/* X[b] (nrows x n) = B[b] * A[b]^-1 given rcwa_lu_factor output; X must not alias B; `work` is a
+ * buffer shaped and strided like X. */
+int rcwa_lu_solve_right(const void* LU, long long lu_stride, int n, int lda, const int* perm, const void* tinv,
                         const void* B, long long b_stride, int ldb, int nrows,
-                        void* X, long long x_stride, int ldx, int nb, void* gemm_scratch, void* stream);
+                        void* X, long long x_stride, int ldx, void* work, int nb, void* gemm_scratch, void* stream);
 
 /* ---- stage 1 -> 2: P, Q of the layer eigenproblem -----------------------------------------
  * eta = E^-1, optional Mc (mu conv. matrix) and nu = Mc^-1 (both NULL => homogeneous mu given per

@@ -31,7 +31,7 @@ def test_argument_checks_do_not_touch_the_gpu():
     lib = _lib.load()
     assert lib.rcwa_convmat(None, 0, 0, 16, 16, 1, 1, 1, None, None, None) == -1
     assert lib.rcwa_eig(None, 4, 1, None, None, None, 0, None, None, None) == -1
-    assert lib.rcwa_lu_factor(None, 0, 4, 4, 1, None, None, None, None, None) == -1
+    assert lib.rcwa_lu_factor(None, 0, 4, 4, 1, None, None, None, None, None, None) == -1
     assert lib.rcwa_eig_workspace_bytes(1922, 1) > 2 * 1922 * 1922 * 16
 
 

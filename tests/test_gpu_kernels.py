@@ -49,16 +49,16 @@ def test_zgemm_large():
     assert rel(_lib.zgemm(A, B), A @ B) < 1e-14
 
 
-@pytest.mark.parametrize("n", [5, 32, 33, 100, 242, 500])
+@pytest.mark.parametrize("n", [5, 32, 33, 100, 128, 129, 242, 500])
 def test_lu_right_solve(n):
     from torcwa_b200 import _lib
     nb = 3
     A = rnd(nb, n, n, seed=n) + 0.5 * torch.eye(n, dtype=torch.complex128, device=dev())
     Bm = rnd(nb, 17, n, seed=n + 1)
     LU = A.clone()
-    perm, info = _lib.lu_factor_(LU)
+    perm, info, tinv = _lib.lu_factor_(LU)
     assert int(info.abs().max()) == 0
-    X = _lib.lu_solve_right(LU, perm, Bm)
+    X = _lib.lu_solve_right(LU, perm, tinv, Bm)
     assert rel(X @ A, Bm) < 1e-11
     Ai, info = _lib.inverse(A)
     assert rel(Ai, torch.linalg.inv(A)) < 1e-10
@@ -68,7 +68,7 @@ def test_lu_singular_reports_info():
     from torcwa_b200 import _lib
     A = rnd(2, 40, 40, seed=9)
     A[1, 7, :] = 0
-    _, info = _lib.lu_factor_(A.clone())
+    _, info, _t = _lib.lu_factor_(A.clone())
     assert int(info[0]) == 0 and int(info[1]) > 0
 
 

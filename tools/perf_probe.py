@@ -31,11 +31,11 @@ for n, nb in ((1922, 8), (1922, 1), (512, 32)):
 for n, nb in ((1922, 8), (1922, 1), (961, 8)):
     A = torch.randn(nb, n, n, dtype=torch.complex128, device=d) + 3 * torch.eye(n, dtype=torch.complex128, device=d)
     def f():
-        LU = A.clone(); perm, info = _lib.lu_factor_(LU); return LU, perm
+        LU = A.clone(); perm, info, tinv = _lib.lu_factor_(LU); return LU, perm, tinv
     t = timeit(f, n=2)
-    LU, perm = f()
+    LU, perm, tinv = f()
     Bm = torch.randn(nb, n, n, dtype=torch.complex128, device=d)
-    t2 = timeit(lambda: _lib.lu_solve_right(LU, perm, Bm), n=2)
+    t2 = timeit(lambda: _lib.lu_solve_right(LU, perm, tinv, Bm), n=2)
     t3 = timeit(lambda: torch.linalg.inv(A), n=2)
     print(f"LU n={n} nb={nb}: factor {t:.1f} ms, solve(n rhs) {t2:.1f} ms | torch inv {t3:.1f} ms", flush=True)
 # fp64 real GEMM peak via cuBLAS for the roofline denominator

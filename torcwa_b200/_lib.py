@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "librcwa_b200.so")
 
 EXPORTS = [
     "rcwa_b200_abi_version", "rcwa_gemm_scratch_bytes", "rcwa_convmat_workspace_bytes", "rcwa_convmat",
-    "rcwa_zgemm_batched", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
+    "rcwa_zgemm_batched", "rcwa_lu_tinv_bytes", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
     "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_eig_stats", "rcwa_hessenberg", "rcwa_kz_branch", "rcwa_layer_smatrix_workspace_bytes",
     "rcwa_layer_smatrix", "rcwa_redheffer_workspace_bytes", "rcwa_redheffer", "rcwa_redheffer_bdleft", "rcwa_blockdiag_dense",
 ]
@@ -25,8 +25,9 @@ _SIGS = {
     "rcwa_convmat_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "rcwa_convmat": (_i, [_vp, _i, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rcwa_zgemm_batched": (_i, [_i, _i, _i, _i, _i, _d, _d, _vp, _i, _ll, _vp, _i, _ll, _d, _d, _vp, _i, _ll, _i, _vp, _vp]),
-    "rcwa_lu_factor": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "rcwa_lu_solve_right": (_i, [_vp, _ll, _i, _i, _vp, _vp, _ll, _i, _i, _vp, _ll, _i, _i, _vp, _vp]),
+    "rcwa_lu_tinv_bytes": (_sz, [_i, _i]),
+    "rcwa_lu_factor": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rcwa_lu_solve_right": (_i, [_vp, _ll, _i, _i, _vp, _vp, _vp, _ll, _i, _i, _vp, _ll, _i, _vp, _i, _vp, _vp]),
     "rcwa_pq_assemble": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "rcwa_eig_workspace_bytes": (_sz, [_i, _i]),
     "rcwa_eig": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
@@ -138,37 +139,39 @@ def zgemm(A, B, opa="N", opb="N", alpha=1.0, beta=0.0, out=None):
 
 
 def lu_factor_(A):
-    """In place on A [nb,n,n]; returns (perm, info)."""
+    """In place on A [nb,n,n]; returns (perm, info, tinv)."""
     lib = load()
     _c128(A, "A")
     nb, n = A.shape[0], A.shape[1]
     ipiv = torch.empty((nb, n), dtype=torch.int32, device=A.device)
     perm = torch.empty((nb, n), dtype=torch.int32, device=A.device)
     info = torch.zeros((nb,), dtype=torch.int32, device=A.device)
+    tinv = _ws(lib.rcwa_lu_tinv_bytes(n, nb), A.device)
     gs = _ws(lib.rcwa_gemm_scratch_bytes(nb), A.device)
-    _check(lib.rcwa_lu_factor(_ptr(A), n * n, n, n, nb, _ptr(ipiv), _ptr(perm), _ptr(info), _ptr(gs), _stream()), "rcwa_lu_factor")
-    return perm, info
+    _check(lib.rcwa_lu_factor(_ptr(A), n * n, n, n, nb, _ptr(ipiv), _ptr(perm), _ptr(info), _ptr(tinv), _ptr(gs), _stream()), "rcwa_lu_factor")
+    return perm, info, tinv
 
 
-def lu_solve_right(LU, perm, Bm):
+def lu_solve_right(LU, perm, tinv, Bm):
     """X = Bm @ inv(A) for factored LU [nb,n,n], Bm [nb,r,n]."""
     lib = load()
     _c128(LU, "LU"); _c128(Bm, "B")
     nb, n = LU.shape[0], LU.shape[1]
     r = Bm.shape[1]
     X = torch.empty_like(Bm)
+    work = torch.empty_like(Bm)
     gs = _ws(lib.rcwa_gemm_scratch_bytes(nb), LU.device)
-    _check(lib.rcwa_lu_solve_right(_ptr(LU), n * n, n, n, _ptr(perm), _ptr(Bm), r * n, n, r, _ptr(X), r * n, n, nb, _ptr(gs), _stream()),
-           "rcwa_lu_solve_right")
+    _check(lib.rcwa_lu_solve_right(_ptr(LU), n * n, n, n, _ptr(perm), _ptr(tinv), _ptr(Bm), r * n, n, r, _ptr(X), r * n, n, _ptr(work),
+                                   nb, _ptr(gs), _stream()), "rcwa_lu_solve_right")
     return X
 
 
 def inverse(A):
     """inv(A) for [nb,n,n] via X*A = I; returns (inv, info). A is preserved."""
     LU = A.clone()
-    perm, info = lu_factor_(LU)
+    perm, info, tinv = lu_factor_(LU)
     eye = torch.eye(A.shape[1], dtype=A.dtype, device=A.device).expand(A.shape[0], -1, -1).contiguous()
-    return lu_solve_right(LU, perm, eye), info
+    return lu_solve_right(LU, perm, tinv, eye), info
 
 
 def pq_assemble(eta, E, kx, ky, mu_scalar=None, Mc=None, nu=None):

@@ -53,7 +53,9 @@ int rcwa_zgemm_batched(int opa, int opb, int M, int N, int K, double alpha_re, d
                             C(beta_re, beta_im), (cplx*)Cm, ldc, sc, nb, (ZGemmProblem*)gs, S(stream)));
 }
 
-int rcwa_lu_factor(void* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info, void* gs, void* stream) {
+size_t rcwa_lu_tinv_bytes(int n, int nb) { return align256(lu_tinv_elems(n, nb > 0 ? nb : 1) * sizeof(cplx)); }
+
+int rcwa_lu_factor(void* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info, void* tinv, void* gs, void* stream) {
     if (!A) return -1;
     if (n <= 0) return -3;
     if (lda < n) return -4;
@@ -61,22 +63,25 @@ int rcwa_lu_factor(void* A, long long stride, int n, int lda, int nb, int* ipiv,
     if (!ipiv) return -6;
     if (!perm) return -7;
     if (!info) return -8;
-    if (!gs) return -9;
-    return cu(lu_factor((cplx*)A, stride, n, lda, nb, ipiv, perm, info, (ZGemmProblem*)gs, S(stream)));
+    if (!tinv) return -9;
+    if (!gs) return -10;
+    return cu(lu_factor((cplx*)A, stride, n, lda, nb, ipiv, perm, info, (cplx*)tinv, (ZGemmProblem*)gs, S(stream)));
 }
 
-int rcwa_lu_solve_right(const void* LU, long long lus, int n, int lda, const int* perm, const void* B, long long bs, int ldb,
-                        int nrows, void* X, long long xs, int ldx, int nb, void* gs, void* stream) {
+int rcwa_lu_solve_right(const void* LU, long long lus, int n, int lda, const int* perm, const void* tinv, const void* B, long long bs, int ldb,
+                        int nrows, void* X, long long xs, int ldx, void* work, int nb, void* gs, void* stream) {
     if (!LU) return -1;
     if (n <= 0) return -3;
     if (!perm) return -5;
-    if (!B) return -6;
-    if (nrows <= 0) return -9;
-    if (!X || X == B) return -10;
-    if (nb <= 0) return -13;
-    if (!gs) return -14;
-    return cu(lu_solve_right((const cplx*)LU, lus, n, lda, perm, (const cplx*)B, bs, ldb, nrows, (cplx*)X, xs, ldx, nb,
-                             (ZGemmProblem*)gs, S(stream)));
+    if (!tinv) return -6;
+    if (!B) return -7;
+    if (nrows <= 0) return -10;
+    if (!X || X == B) return -11;
+    if (!work || work == X || work == B) return -14;
+    if (nb <= 0) return -15;
+    if (!gs) return -16;
+    return cu(lu_solve_right((const cplx*)LU, lus, n, lda, perm, (const cplx*)tinv, (const cplx*)B, bs, ldb, nrows, (cplx*)X, xs, ldx,
+                             (cplx*)work, nb, (ZGemmProblem*)gs, S(stream)));
 }
 
 int rcwa_pq_assemble(const void* eta, const void* E, const void* Mc, const void* nu, const void* mu_scalar,
@@ -135,7 +140,7 @@ int rcwa_kz_branch(const void* lam, void* kz, long long total, void* stream) {
 // workspace layout helpers ---------------------------------------------------------------------
 size_t rcwa_layer_smatrix_workspace_bytes(int N, int nb) {
     const size_t n = 2 * (size_t)N, mat = align256(n * n * nb * sizeof(cplx));
-    return 5 * mat + 2 * align256(n * nb * sizeof(int)) + rcwa_gemm_scratch_bytes(nb);
+    return 6 * mat + 2 * align256(n * nb * sizeof(int)) + rcwa_lu_tinv_bytes((int)n, nb) + rcwa_gemm_scratch_bytes(nb);
 }
 
 int rcwa_layer_smatrix(const void* W, const void* kz, const void* Q, const void* vfinv, const double* omega,
@@ -162,26 +167,28 @@ int rcwa_layer_smatrix(const void* W, const void* kz, const void* Q, const void*
     cplx* b2 = (cplx*)p; p += mat;
     cplx* b3 = (cplx*)p; p += mat;
     cplx* b4 = (cplx*)p; p += mat;
+    cplx* b5 = (cplx*)p; p += mat;
     int* ipiv = (int*)p; p += align256((size_t)n * nb * sizeof(int));
     int* perm = (int*)p; p += align256((size_t)n * nb * sizeof(int));
+    cplx* tinv = (cplx*)p; p += rcwa_lu_tinv_bytes(n, nb);
     ZGemmProblem* gs = (ZGemmProblem*)p;
     // QW = Q * W
     CK(zgemm_strided(OP_N, OP_N, n, n, n, C(1, 0), (const cplx*)Q, n, ms, (const cplx*)W, n, ms, C(0, 0), b0, n, ms, nb, gs, st));
     // M+ (b1), M- (b2), R+ (b3), R- (b4)
     CK(layer_form((const cplx*)W, b0, (const cplx*)kz, (const cplx*)vfinv, omega, thickness, nb, N, b1, b2, b3, b4, st));
     // T+ = R+ M+^-1  -> b0
-    CK(lu_factor(b1, ms, n, n, nb, ipiv, perm, info, gs, st));
-    CK(lu_solve_right(b1, ms, n, n, perm, b3, ms, n, n, b0, ms, n, nb, gs, st));
+    CK(lu_factor(b1, ms, n, n, nb, ipiv, perm, info, tinv, gs, st));
+    CK(lu_solve_right(b1, ms, n, n, perm, tinv, b3, ms, n, n, b0, ms, n, b5, nb, gs, st));
     // T- = R- M-^-1  -> b3   (info keeps the first failure: the second factorisation does not clear it)
-    CK(lu_factor(b2, ms, n, n, nb, ipiv, perm, info, gs, st, false));
-    CK(lu_solve_right(b2, ms, n, n, perm, b4, ms, n, n, b3, ms, n, nb, gs, st));
+    CK(lu_factor(b2, ms, n, n, nb, ipiv, perm, info, tinv, gs, st, false));
+    CK(lu_solve_right(b2, ms, n, n, perm, tinv, b4, ms, n, n, b3, ms, n, b5, nb, gs, st));
     CK(layer_finish(b0, b3, nb, n, (cplx*)S11, (cplx*)S21, st));
     return 0;
 }
 
 size_t rcwa_redheffer_workspace_bytes(int n, int nb) {
     const size_t mat = align256((size_t)n * n * nb * sizeof(cplx));
-    return 5 * mat + 2 * align256((size_t)n * nb * sizeof(int)) + rcwa_gemm_scratch_bytes(nb);
+    return 5 * mat + 2 * align256((size_t)n * nb * sizeof(int)) + rcwa_lu_tinv_bytes(n, nb) + rcwa_gemm_scratch_bytes(nb);
 }
 
 int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const out[4], int nb, int n, void* ws, int* info, void* stream) {
@@ -208,6 +215,7 @@ int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const
     cplx* T = (cplx*)p; p += mat;
     int* ipiv = (int*)p; p += align256((size_t)n * nb * sizeof(int));
     int* perm = (int*)p; p += align256((size_t)n * nb * sizeof(int));
+    cplx* tinv = (cplx*)p; p += rcwa_lu_tinv_bytes(n, nb);
     ZGemmProblem* gs = (ZGemmProblem*)p;
     const cplx *Sm11 = (const cplx*)Sm[0], *Sm21 = (const cplx*)Sm[1], *Sm12 = (const cplx*)Sm[2], *Sm22 = (const cplx*)Sm[3];
     const cplx *Sn11 = (const cplx*)Sn[0], *Sn21 = (const cplx*)Sn[1], *Sn12 = (const cplx*)Sn[2], *Sn22 = (const cplx*)Sn[3];
@@ -218,10 +226,10 @@ int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const
     // D = I - Sm12 Sn21
     CK(set_identity(D, n, n, ms, nb, st));
     CK(zgemm_strided(OP_N, OP_N, n, n, n, mone, Sm12, n, ms, Sn21, n, ms, one, D, n, ms, nb, gs, st));
-    CK(lu_factor(D, ms, n, n, nb, ipiv, perm, info, gs, st));
-    // Y1 = Sn11 D^-1 ; Y2 = Sn21 D^-1
-    CK(lu_solve_right(D, ms, n, n, perm, Sn11, ms, n, n, Y1, ms, n, nb, gs, st));
-    CK(lu_solve_right(D, ms, n, n, perm, Sn21, ms, n, n, Y2, ms, n, nb, gs, st));
+    CK(lu_factor(D, ms, n, n, nb, ipiv, perm, info, tinv, gs, st));
+    // Y1 = Sn11 D^-1 ; Y2 = Sn21 D^-1     (T is free until later: it is the solves' work buffer)
+    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn11, ms, n, n, Y1, ms, n, T, nb, gs, st));
+    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn21, ms, n, n, Y2, ms, n, T, nb, gs, st));
     // G = Sm12 Sn22
     GEMM(Sm12, Sn22, zero, G);
     // S11 = Y1 Sm11
@@ -266,6 +274,7 @@ int rcwa_redheffer_bdleft(const void* const Sm_bd[4], const void* const Sn[4], v
     cplx* T = (cplx*)p; p += mat;
     int* ipiv = (int*)p; p += align256((size_t)n * nb * sizeof(int));
     int* perm = (int*)p; p += align256((size_t)n * nb * sizeof(int));
+    cplx* tinv = (cplx*)p; p += rcwa_lu_tinv_bytes(n, nb);
     ZGemmProblem* gs = (ZGemmProblem*)p;
     const cplx *m11 = (const cplx*)Sm_bd[0], *m21 = (const cplx*)Sm_bd[1], *m12 = (const cplx*)Sm_bd[2], *m22 = (const cplx*)Sm_bd[3];
     const cplx *Sn11 = (const cplx*)Sn[0], *Sn21 = (const cplx*)Sn[1], *Sn12 = (const cplx*)Sn[2], *Sn22 = (const cplx*)Sn[3];
@@ -275,9 +284,9 @@ int rcwa_redheffer_bdleft(const void* const Sm_bd[4], const void* const Sn[4], v
     // D = I - Sm12 Sn21          (Sm12 is four diagonals: an O(n^2) row combination, not a GEMM)
     CK(set_identity(D, n, n, ms, nb, st));
     CK(bd_left_mul(m12, Sn21, nb, N, n, mone, one, D, st));
-    CK(lu_factor(D, ms, n, n, nb, ipiv, perm, info, gs, st));
-    CK(lu_solve_right(D, ms, n, n, perm, Sn11, ms, n, n, Y1, ms, n, nb, gs, st));      // Y1 = Sn11 D^-1
-    CK(lu_solve_right(D, ms, n, n, perm, Sn21, ms, n, n, Y2, ms, n, nb, gs, st));      // Y2 = Sn21 D^-1
+    CK(lu_factor(D, ms, n, n, nb, ipiv, perm, info, tinv, gs, st));
+    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn11, ms, n, n, Y1, ms, n, T, nb, gs, st));      // Y1 = Sn11 D^-1 (T = work)
+    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn21, ms, n, n, Y2, ms, n, T, nb, gs, st));      // Y2 = Sn21 D^-1
     CK(bd_left_mul(m12, Sn22, nb, N, n, one, zero, G, st));                             // G = Sm12 Sn22
     CK(bd_right_mul(m11, Y1, nb, N, n, one, zero, O11, st));                            // S11 = Y1 Sm11
     CK(cudaMemcpyAsync(O12, Sn12, bytes, cudaMemcpyDeviceToDevice, st));                // S12 = Sn12 + Y1 G

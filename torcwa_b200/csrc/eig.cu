@@ -1023,8 +1023,21 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
     // next pass.  Window unitaries and side-stream descriptors are double-buffered; pass k+2 waits for the
     // side GEMMs of pass k.  The host polls convergence with a lag of one group: the count of group g is
     // copied to pinned memory asynchronously and examined after group g+1 has been enqueued.
-    cudaStream_t sb = nullptr;
-    EK(cudaStreamCreateWithFlags(&sb, cudaStreamNonBlocking));
+    // Priorities: the latency-bound chain (pass kernel + the GEMM the next pass needs) runs on an internal
+    // HIGH-priority stream forked from the caller's stream; the bulk column/Z GEMMs run on a low-priority side
+    // stream, so that a pass kernel's CTAs are dispatched as soon as SMs free up instead of queueing behind
+    // thousands of GEMM tiles.  Both are joined back into the caller's stream before the eigenvector phase.
+    int prio_lo = 0, prio_hi = 0;
+    EK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    cudaStream_t user_st = st, sa = nullptr, sb = nullptr;
+    EK(cudaStreamCreateWithPriority(&sa, cudaStreamNonBlocking, prio_hi));
+    EK(cudaStreamCreateWithPriority(&sb, cudaStreamNonBlocking, prio_lo));
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    EK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    EK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    EK(cudaEventRecord(ev_fork, user_st));
+    EK(cudaStreamWaitEvent(sa, ev_fork, 0));
+    st = sa;
     cudaEvent_t ev_pass[2], ev_side[2], ev[2] = {nullptr, nullptr};
     for (int q = 0; q < 2; ++q) { EK(cudaEventCreateWithFlags(&ev_pass[q], cudaEventDisableTiming)); EK(cudaEventCreateWithFlags(&ev_side[q], cudaEventDisableTiming)); }
     int* hf = const_cast<int*>(host_flag);
@@ -1055,9 +1068,14 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
             ++group;
         }
     }
-    // join the side stream before anything reads H or Z
+    // join both internal streams back into the caller's stream before anything reads H or Z
     EK(cudaStreamWaitEvent(st, ev_side[0], 0));
     EK(cudaStreamWaitEvent(st, ev_side[1], 0));
+    EK(cudaEventRecord(ev_join, st));
+    st = user_st;
+    EK(cudaStreamWaitEvent(st, ev_join, 0));
+    cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join);
+    cudaStreamDestroy(sa);
     for (int q = 0; q < 2; ++q) { cudaEventDestroy(ev_pass[q]); cudaEventDestroy(ev_side[q]); }
     if (ev[0]) cudaEventDestroy(ev[0]);
     if (ev[1]) cudaEventDestroy(ev[1]);

@@ -19,7 +19,7 @@
 #include "kernels.h"
 
 #define HB_NB 32
-#define HB_ROWS 64          // rows per CTA in the matvec (8 warps x 8 rows)
+#define HB_ROWS 32          // rows per CTA in the matvec (8 warps x 4 rows)
 
 namespace {
 
@@ -138,47 +138,45 @@ hb_col_kernel(cplx* A, long long astride, int lda, int n, int k0, int i, int fin
     }
 }
 
-// y[r] = sum_{c > j} A[r][c] u[c]  for rows r in [k0+1, n); stored to Y[r][i].  grid (ceil((n-k0-1)/64), B), 256 threads.
-__global__ void __launch_bounds__(256)
+// y[r] = sum_{c > j} A[r][c] u[c]  for rows r in [k0+1, n); stored to Y[r][i].
+// grid (ceil((n-k0-1)/HB_ROWS), B), 256 threads = 8 warps x 4 rows: small row bands keep the grid large
+// (>= 2 waves of CTAs even at batch 8) and each lane has 16 independent 16-byte loads per 128-column chunk.
+__global__ void __launch_bounds__(256, 3)
 hb_matvec_kernel(const cplx* __restrict__ A, long long astride, int lda, int n, int k0, int i, cplx* wsb, long long wstride) {
     const int b = blockIdx.y;
     HbPtrs p = hb_ptrs(wsb + (size_t)b * wstride, n);
     const cplx* Ab = A + (size_t)b * astride;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = k0 + i;
-    const int row0 = k0 + 1 + blockIdx.x * HB_ROWS + warp * 8;
-    cplx acc[8];
+    const int row0 = k0 + 1 + blockIdx.x * HB_ROWS + warp * 4;
+    cplx acc[4];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) acc[r] = C(0, 0);
+    for (int r = 0; r < 4; ++r) acc[r] = C(0, 0);
     const int cstart = (j + 1) - ((j + 1) % 128);
     for (int c0 = cstart; c0 < n; c0 += 128) {
-        cplx uc[4];
+        cplx uc[4], av[4][4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int r = row0 + rr;
+            const cplx* rp = Ab + (size_t)r * lda;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int col = c0 + q * 32 + lane;
+                av[rr][q] = (r < n && col > j && col < n) ? ld_nc(rp + col) : C(0, 0);
+            }
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int col = c0 + q * 32 + lane;
             uc[q] = (col > j && col < n) ? p.u[col] : C(0, 0);
         }
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            cplx av[4][4];
+        for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-                const int r = row0 + g * 4 + rr;
-                const cplx* rp = Ab + (size_t)r * lda;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int col = c0 + q * 32 + lane;
-                    av[rr][q] = (r < n && col > j && col < n) ? ld_nc(rp + col) : C(0, 0);
-                }
-            }
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc[g * 4 + rr] = cfma(av[rr][q], uc[q], acc[g * 4 + rr]);
-        }
+            for (int q = 0; q < 4; ++q) acc[rr] = cfma(av[rr][q], uc[q], acc[rr]);
     }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < 4; ++r) {
         const double yr = warp_sum(acc[r].x), yi = warp_sum(acc[r].y);
         const int row = row0 + r;
         if (lane == 0 && row < n) p.Y[(size_t)row * HB_NB + i] = C(yr, yi);

@@ -40,10 +40,13 @@ cudaError_t set_identity(cplx* A, int n, int lda, long long stride, int nb, cuda
 cudaError_t axpby(cplx alpha, const cplx* X, cplx beta, cplx* Y, size_t total, cudaStream_t st);
 
 // ---- lu.cu
-cudaError_t lu_factor(cplx* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info,
+size_t lu_tinv_elems(int n, int nb);     // complex elements of the inverted-diagonal-block buffer of lu_factor
+cudaError_t lu_factor(cplx* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info, cplx* tinv,
                       ZGemmProblem* gscratch, cudaStream_t st, bool clear_info = true);
-cudaError_t lu_solve_right(const cplx* LU, long long lustride, int n, int lda, const int* perm, const cplx* Bm, long long bstride,
-                           int ldb, int nrows, cplx* X, long long xstride, int ldx, int nb, ZGemmProblem* gscratch, cudaStream_t st);
+// Yw: work buffer shaped like X
+cudaError_t lu_solve_right(const cplx* LU, long long lustride, int n, int lda, const int* perm, const cplx* tinv,
+                           const cplx* Bm, long long bstride, int ldb, int nrows, cplx* X, long long xstride, int ldx,
+                           cplx* Yw, int nb, ZGemmProblem* gscratch, cudaStream_t st);
 
 // ---- hess.cu
 size_t hessenberg_workspace_bytes(int n, int nb);

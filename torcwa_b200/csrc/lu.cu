@@ -25,6 +25,7 @@
 #endif
 
 #define LU_NB 32
+#define SOLVE_NB 128        // block size of the triangular solves (diagonal blocks are inverted once per factorisation)
 
 // ------------------------------------------------------------------------------------------------
 // panel factorisation: rows [k0, k0+nbe) of A (n x n, leading dim lda), columns [k0, n)
@@ -240,6 +241,38 @@ trsm_rows_kernel(cplx* X, long long xstride, int ldx, int row0, int nrows, int c
     }
 }
 
+// Inverses of the SOLVE_NB x SOLVE_NB diagonal blocks of the factors, so that the triangular solves
+// become large-K GEMMs:  grid (nblk, B, 2): z = 0 -> unit upper U_kk^-1, z = 1 -> lower L_kk^-1.
+// One thread per column of the inverse (back-substitution down its own column; every thread reads the
+// same factor entry -> broadcast loads; the inverse column lives in the output itself).
+// Out-of-range rows/columns of the last block behave like an identity extension.
+__global__ void __launch_bounds__(SOLVE_NB)
+tri_inv_kernel(const cplx* __restrict__ LU, long long lustride, int n, int lda, cplx* __restrict__ tinv, int nblk) {
+    const int kb = blockIdx.x, b = blockIdx.y, which = blockIdx.z, j = threadIdx.x;
+    const int k0 = kb * SOLVE_NB;
+    const int w = (n - k0 < SOLVE_NB) ? n - k0 : SOLVE_NB;
+    const cplx* F = LU + (size_t)b * lustride + (size_t)k0 * lda + k0;
+    cplx* X = tinv + (((size_t)b * 2 + which) * nblk + kb) * SOLVE_NB * SOLVE_NB;
+    for (int i = 0; i < SOLVE_NB; ++i) X[i * SOLVE_NB + j] = C(i == j ? 1.0 : 0.0, 0.0);
+    if (j >= w) return;
+    if (which == 0) {
+        // U unit upper:  x_j = 1 ; x_i = -sum_{k=i+1..j} U[i][k] x_k   (i = j-1 .. 0)
+        for (int i = j - 1; i >= 0; --i) {
+            cplx acc = C(0, 0);
+            for (int k = i + 1; k <= j; ++k) acc = cfma(F[(size_t)i * lda + k], X[k * SOLVE_NB + j], acc);
+            X[i * SOLVE_NB + j] = cneg(acc);
+        }
+    } else {
+        // L lower (non-unit):  x_j = 1/L_jj ; x_i = -(sum_{k=j..i-1} L[i][k] x_k) / L_ii   (i = j+1 .. w-1)
+        X[j * SOLVE_NB + j] = cinv(F[(size_t)j * lda + j]);
+        for (int i = j + 1; i < w; ++i) {
+            cplx acc = C(0, 0);
+            for (int k = j; k < i; ++k) acc = cfma(F[(size_t)i * lda + k], X[k * SOLVE_NB + j], acc);
+            X[i * SOLVE_NB + j] = cneg(cdiv(acc, F[(size_t)i * lda + i]));
+        }
+    }
+}
+
 // grid (nrows, B): X[r][c] = Bm[r][perm[c]]
 __global__ void gather_cols_kernel(const cplx* __restrict__ Bm, long long bstride, int ldb, const int* __restrict__ perm,
                                    int n, cplx* __restrict__ X, long long xstride, int ldx) {
@@ -255,7 +288,9 @@ __global__ void gather_cols_kernel(const cplx* __restrict__ Bm, long long bstrid
 namespace rcwa {
 
 // A: [B] matrices n x n (lda, stride) overwritten by L\U; ipiv, perm: [B,n] ints; info: [B] ints
-cudaError_t lu_factor(cplx* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info,
+size_t lu_tinv_elems(int n, int nb) { return (size_t)nb * 2 * ((n + SOLVE_NB - 1) / SOLVE_NB) * SOLVE_NB * SOLVE_NB; }
+
+cudaError_t lu_factor(cplx* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info, cplx* tinv,
                       ZGemmProblem* gscratch, cudaStream_t st, bool clear_info) {
     if (clear_info) cudaMemsetAsync(info, 0, sizeof(int) * nb, st);
     const cplx one = C(1, 0), mone = C(-1, 0);
@@ -274,34 +309,44 @@ cudaError_t lu_factor(cplx* A, long long stride, int n, int lda, int nb, int* ip
         }
     }
     lu_perm_kernel<<<nb, 256, n * sizeof(int), st>>>(ipiv, n, perm);
+    const int nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
+    tri_inv_kernel<<<dim3(nblk, nb, 2), SOLVE_NB, 0, st>>>(A, stride, n, lda, tinv, nblk);
     return cudaGetLastError();
 }
 
-// X (nrows x n, ldx, xstride) = Bm * A^-1 ; X must not alias Bm
-cudaError_t lu_solve_right(const cplx* LU, long long lustride, int n, int lda, const int* perm, const cplx* Bm, long long bstride,
-                           int ldb, int nrows, cplx* X, long long xstride, int ldx, int nb, ZGemmProblem* gscratch, cudaStream_t st) {
-    const cplx one = C(1, 0), mone = C(-1, 0);
+// X (nrows x n, ldx, xstride) = Bm * A^-1 ; X must not alias Bm.  `Yw`: work buffer like X (same ld / stride).
+//   X A = B,  A Pi = L U   =>   Y U = B Pi (forward over column blocks),  X L = Y (backward).
+// Left-looking over SOLVE_NB-wide column blocks with pre-inverted diagonal blocks: every step is a
+// GEMM with K = (columns already solved) followed by a K = SOLVE_NB GEMM -- large-K DMMA work instead
+// of rank-32 updates.
+cudaError_t lu_solve_right(const cplx* LU, long long lustride, int n, int lda, const int* perm, const cplx* tinv,
+                           const cplx* Bm, long long bstride, int ldb, int nrows, cplx* X, long long xstride, int ldx,
+                           cplx* Yw, int nb, ZGemmProblem* gscratch, cudaStream_t st) {
+    const cplx one = C(1, 0), mone = C(-1, 0), zero = C(0, 0);
+    const int nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
+    const long long tstride = (long long)2 * nblk * SOLVE_NB * SOLVE_NB;      // per matrix
+    const cplx* Uinv = tinv;
+    const cplx* Linv = tinv + (size_t)nblk * SOLVE_NB * SOLVE_NB;
     gather_cols_kernel<<<dim3(nrows, nb), 256, 0, st>>>(Bm, bstride, ldb, perm, n, X, xstride, ldx);
-    for (int k0 = 0; k0 < n; k0 += LU_NB) {
-        const int nbe = (n - k0 < LU_NB) ? n - k0 : LU_NB;
-        trsm_rows_kernel<<<dim3((nrows + 31) / 32, nb), 32, 0, st>>>(X, xstride, ldx, 0, nrows, k0, LU, lustride, lda, k0, nbe, 0);
-        const int rem = n - k0 - nbe;
-        if (rem > 0) {
-            cudaError_t e = zgemm_strided(OP_N, OP_N, nrows, rem, nbe, mone, X + k0, ldx, xstride,
-                                          LU + (size_t)k0 * lda + (k0 + nbe), lda, lustride, one, X + (k0 + nbe), ldx, xstride, nb, gscratch, st);
-            if (e != cudaSuccess) return e;
-        }
+#define SK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
+    // forward:  Y_k = (Xw_k - Y_{<k} U_{<k,k}) Uinv_k          (Xw = X buffer, Y = Yw buffer)
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int c0 = kb * SOLVE_NB, w = (n - c0 < SOLVE_NB) ? n - c0 : SOLVE_NB;
+        if (kb > 0)
+            SK(zgemm_strided(OP_N, OP_N, nrows, w, c0, mone, Yw, ldx, xstride, LU + c0, lda, lustride, one, X + c0, ldx, xstride, nb, gscratch, st));
+        SK(zgemm_strided(OP_N, OP_N, nrows, w, w, one, X + c0, ldx, xstride, Uinv + (size_t)kb * SOLVE_NB * SOLVE_NB, SOLVE_NB, tstride,
+                         zero, Yw + c0, ldx, xstride, nb, gscratch, st));
     }
-    const int nblk = (n + LU_NB - 1) / LU_NB;
+    // backward: Z_k = (Y_k - Z_{>k} L_{>k,k}) Linv_k           (Z overwrites the X buffer)
     for (int kb = nblk - 1; kb >= 0; --kb) {
-        const int k0 = kb * LU_NB, nbe = (n - k0 < LU_NB) ? n - k0 : LU_NB;
-        trsm_rows_kernel<<<dim3((nrows + 31) / 32, nb), 32, 0, st>>>(X, xstride, ldx, 0, nrows, k0, LU, lustride, lda, k0, nbe, 1);
-        if (k0 > 0) {
-            cudaError_t e = zgemm_strided(OP_N, OP_N, nrows, k0, nbe, mone, X + k0, ldx, xstride,
-                                          LU + (size_t)k0 * lda, lda, lustride, one, X, ldx, xstride, nb, gscratch, st);
-            if (e != cudaSuccess) return e;
-        }
+        const int c0 = kb * SOLVE_NB, w = (n - c0 < SOLVE_NB) ? n - c0 : SOLVE_NB, c1 = c0 + w;
+        if (c1 < n)
+            SK(zgemm_strided(OP_N, OP_N, nrows, w, n - c1, mone, X + c1, ldx, xstride, LU + (size_t)c1 * lda + c0, lda, lustride, one,
+                             Yw + c0, ldx, xstride, nb, gscratch, st));
+        SK(zgemm_strided(OP_N, OP_N, nrows, w, w, one, Yw + c0, ldx, xstride, Linv + (size_t)kb * SOLVE_NB * SOLVE_NB, SOLVE_NB, tstride,
+                         zero, X + c0, ldx, xstride, nb, gscratch, st));
     }
+#undef SK
     return cudaGetLastError();
 }
 

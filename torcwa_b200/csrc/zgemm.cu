@@ -105,17 +105,26 @@ zgemm_grouped_kernel(const ZGemmProblem* __restrict__ probs, cplx alpha, cplx be
                 if (OPA == 2) a[t].y = -a[t].y;
                 if (OPB == 2) b[t].y = -b[t].y;
             }
+            // four real MMAs per complex tile, issued pass by pass so that the two MMAs that accumulate into
+            // the same registers are 16 instructions apart (back-to-back they serialise on the DMMA latency)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc_re[i][j][0], acc_re[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc_im[i][j][0], acc_im[i][j][1], a[i].x, b[j].y);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const double nai = -a[i].y;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    dmma(acc_re[i][j][0], acc_re[i][j][1], a[i].x, b[j].x);
-                    dmma(acc_re[i][j][0], acc_re[i][j][1], nai, b[j].y);
-                    dmma(acc_im[i][j][0], acc_im[i][j][1], a[i].x, b[j].y);
-                    dmma(acc_im[i][j][0], acc_im[i][j][1], a[i].y, b[j].x);
-                }
+                for (int j = 0; j < 4; ++j) dmma(acc_re[i][j][0], acc_re[i][j][1], nai, b[j].y);
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc_im[i][j][0], acc_im[i][j][1], a[i].y, b[j].x);
         }
     }
     cp_async_wait<0>();
