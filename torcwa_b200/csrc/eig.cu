@@ -399,16 +399,20 @@ DEV void aed_restore_hessenberg(const Cta& c, cplx* T, cplx* V, int nw, int ns, 
     }
 }
 
-// emit the three GEMM problems that apply the window unitary U (wl x wl at Ug) to the off-diagonal
-// row panel, column panel and Z for the window [p, p+wl)
-DEV void emit_window_gemms(cplx* H, int ldh, int n, cplx* Zm, int ldz, cplx* Ug, int p, int wl,
+// emit the three GEMM problems that apply the window unitary U (wl x wl at Ug) for the window [p, p+wl)
+// of the active block [lo, hi].  During the QR phase H is only kept current INSIDE the active block
+// (LAPACK's wantt = false): the row panel is updated up to column hi, the column panel from row lo.
+// The off-diagonal blocks of the final Schur form are recovered afterwards in two large GEMMs,
+// T = Z^H A0 Z (A0 = the input matrix, Z = all accumulated transformations) -- 2 n^3 complex MACs at full tensor rate instead of ~1/3 of all K = 64 panel updates.
+DEV void emit_window_gemms(cplx* H, int ldh, int n, cplx* Zm, int ldz, cplx* Ug, int p, int wl, int lo, int hi,
                            ZGemmProblem* prob_rows, ZGemmProblem* prob_cols, ZGemmProblem* prob_z) {
     const int wend = p + wl;
+    const int ncol = hi + 1 - wend, nrow = p - lo;
     ZGemmProblem g;
     g.A = Ug; g.lda = QR_W; g.B = H + (size_t)p * ldh + wend; g.ldb = ldh; g.C = H + (size_t)p * ldh + wend; g.ldc = ldh;
-    g.M = (n - wend > 0) ? wl : 0; g.N = n - wend; g.K = wl; *prob_rows = g;          // H[p:wend, wend:n] <- U^H * (.)
-    g.A = H + p; g.lda = ldh; g.B = Ug; g.ldb = QR_W; g.C = H + p; g.ldc = ldh;
-    g.M = p; g.N = wl; g.K = wl; *prob_cols = g;                                         // H[0:p, p:wend] <- (.) * U
+    g.M = (ncol > 0) ? wl : 0; g.N = ncol; g.K = wl; *prob_rows = g;                    // H[p:wend, wend:hi+1] <- U^H * (.)
+    g.A = H + (size_t)lo * ldh + p; g.lda = ldh; g.B = Ug; g.ldb = QR_W; g.C = H + (size_t)lo * ldh + p; g.ldc = ldh;
+    g.M = (nrow > 0) ? nrow : 0; g.N = wl; g.K = wl; *prob_cols = g;                      // H[lo:p, p:wend] <- (.) * U
     g.A = Zm + p; g.lda = ldz; g.B = Ug; g.ldb = QR_W; g.C = Zm + p; g.ldc = ldz;
     g.M = n; g.N = wl; g.K = wl; *prob_z = g;                                            // Z[:, p:wend] <- (.) * U
 }
@@ -579,7 +583,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
             st.passes++;
             if (nd > 0) {
                 H[(size_t)kw * ldh + kw - 1] = (ns > 0) ? cmul(spike, cconj(Us[0])) : C(0, 0);
-                emit_window_gemms(H, ldh, n, Zm, ldz, Ug, kw, nw, prob_rows, prob_cols_main, prob_z);
+                emit_window_gemms(H, ldh, n, Zm, ldz, Ug, kw, nw, st.lo, st.hi, prob_rows, prob_cols_main, prob_z);
                 st.aed_deflated += nd;
                 st.hi = kw + ns - 1;          // the nd trailing eigenvalues are converged
                 st.stall = 0;
@@ -624,7 +628,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
             st.passes++;
             if (rc != 0) {
                 // finished (or failed): apply the accumulated unitary to the off-diagonal panels and Z
-                emit_window_gemms(H, ldh, n, Zm, ldz, Ug, p2, m2, prob_rows, prob_cols_main, prob_z);
+                emit_window_gemms(H, ldh, n, Zm, ldz, Ug, p2, m2, st.lo, st.hi, prob_rows, prob_cols_main, prob_z);
                 st.phase = 0;
                 if (rc < 0) { st.done = 1; st.info = st.lo + si + 1; }
             }
@@ -740,7 +744,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         }
         // the pass that ends a sweep is followed by a deflation scan / AED window that may reach above this
         // window: its column update must be complete by then -> main stream; otherwise side stream
-        emit_window_gemms(H, ldh, n, Zm, ldz, Ug, p, wl, prob_rows, (nb_after == 0) ? prob_cols_main : prob_cols, prob_z);
+        emit_window_gemms(H, ldh, n, Zm, ldz, Ug, p, wl, st.lo, st.hi, prob_rows, (nb_after == 0) ? prob_cols_main : prob_cols, prob_z);
         st.p_last = (nb_after == 0) ? -1 : p;
         st.nintro += introduced;
         if (p == st.lo && st.nintro < st.ns) st.ns = st.nintro;      // window could not take more: cap this sweep
@@ -796,6 +800,16 @@ static void emu_gemm(const ZGemmProblem& g, int opa) {
 extern "C" int emu_qr(cplx* H, cplx* Z, int n, int max_passes, int* stats) {
     std::vector<char> smem(qr_pass_smem_bytes(n));
     std::vector<cplx> U((size_t)QR_W * QR_W), Tgbuf((size_t)QR_W * QR_W), Vgbuf((size_t)QR_W * QR_W);
+    // the QR phase keeps H current only inside active blocks; the caller's Z holds the Hessenberg
+    // transformation Z0 on entry, so the input matrix is A0 = Z0 H0 Z0^H
+    std::vector<cplx> H0(H, H + (size_t)n * n), Z0(Z, Z + (size_t)n * n), A0((size_t)n * n);
+    {
+        std::vector<cplx> t0((size_t)n * n), Z0h((size_t)n * n);
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) Z0h[(size_t)i * n + j] = cconj(Z0[(size_t)j * n + i]);
+        ZGemmProblem g; g.M = n; g.N = n; g.K = n; g.lda = n; g.ldb = n; g.ldc = n;
+        g.A = Z0.data(); g.B = H0.data(); g.C = t0.data(); emu_gemm(g, 0);
+        g.A = t0.data(); g.B = Z0h.data(); g.C = A0.data(); emu_gemm(g, 0);
+    }
     QrState st; memset(&st, 0, sizeof(st));
     st.lo = 0; st.hi = n - 1; st.hi_prev = n - 1; st.p_last = -1;
     Cta c; c.tid = 0; c.nthreads = 1; c.bid = 0; c.smem = smem.data(); c.warp_only = 0;
@@ -804,6 +818,13 @@ extern "C" int emu_qr(cplx* H, cplx* Z, int n, int max_passes, int* stats) {
     for (; it < max_passes && !st.done; ++it) {
         qr_pass_body(c, H, n, n, Z, n, &st, U.data(), Vgbuf.data(), Tgbuf.data(), &pr, &pcm, &pc, &pz);
         emu_gemm(pr, 2); emu_gemm(pcm, 0); emu_gemm(pc, 0); emu_gemm(pz, 0);
+    }
+    {   // T = Z^H A0 Z (as the device path does); strictly lower part set to exact zero
+        std::vector<cplx> tmp((size_t)n * n);
+        ZGemmProblem g; g.M = n; g.N = n; g.K = n; g.lda = n; g.ldb = n; g.ldc = n;
+        g.A = A0.data(); g.B = Z; g.C = tmp.data(); emu_gemm(g, 0);
+        g.A = Z; g.B = tmp.data(); g.C = H; emu_gemm(g, 2);
+        for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) H[(size_t)i * n + j] = C(0, 0);
     }
     stats[0] = st.sweeps; stats[1] = st.passes; stats[2] = st.done; stats[3] = st.small_solves;
     stats[4] = st.aeds; stats[5] = st.aed_deflated;
@@ -1007,7 +1028,8 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
     const long long ms = (long long)n * n;
     const cplx one = C(1, 0), zero = C(0, 0);
 
-    // ---------------- phase 1: Hessenberg, Z accumulated alongside
+    // ---------------- phase 1: keep a copy A0 of the input for the final T = Z^H A0 Z; Hessenberg, Z accumulated
+    EK(cudaMemcpyAsync(ws.X, A, sizeof(cplx) * (size_t)n * n * nb, cudaMemcpyDeviceToDevice, st));
     EK(hessenberg_phase(A, n, nb, ws, st));
 
     // ---------------- phase 2: QR passes (host enqueues, polls the pinned flag every `poll` passes)
@@ -1082,21 +1104,26 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
     cudaStreamDestroy(sb);
     qr_finish_kernel<<<(nb + 127) / 128, 128, 0, st>>>(ws.states, nb, info);
 
-    // ---------------- phase 3: eigenvalues, eigenvectors of T, back-transformation, normalisation
-    diag_extract_kernel<<<dim3((n + 255) / 256, nb), 256, 0, st>>>(A, ms, n, n, wout);
+    // ---------------- phase 3: Schur form T = Z^H A0 Z (upper triangle; the strictly lower part is round-off
+    // and is never read), eigenvalues, eigenvectors of T, back-transformation, normalisation
+    cplx* Tm = ws.X;            // A0 -> T
+    cplx* Xv = A;               // scratch for A0*Z, then the eigenvector matrix of T
+    EK(zgemm_strided(OP_N, OP_N, n, n, n, one, ws.X, n, ms, ws.Z, n, ms, zero, A, n, ms, nb, ws.gs, st));        // A  = A0 Z
+    EK(zgemm_strided(OP_H, OP_N, n, n, n, one, ws.Z, n, ms, A, n, ms, zero, Tm, n, ms, nb, ws.gs, st));          // T  = Z^H (A0 Z)
+    diag_extract_kernel<<<dim3((n + 255) / 256, nb), 256, 0, st>>>(Tm, ms, n, n, wout);
     tnorm_kernel<<<nb, 256, 0, st>>>(wout, n, ws.tnorm);
-    EK(cudaMemsetAsync(ws.X, 0, sizeof(cplx) * (size_t)ms * nb, st));
+    EK(cudaMemsetAsync(Xv, 0, sizeof(cplx) * (size_t)ms * nb, st));
     const int nblk = (n + TV_NB - 1) / TV_NB;
     for (int kb = nblk - 1; kb >= 0; --kb) {
         const int r0 = kb * TV_NB, nbk = (n - r0 < TV_NB) ? n - r0 : TV_NB, r1 = r0 + nbk;
         if (r1 < n) {
             // X[I, r1:n] = -T[I, r1:n] * X[r1:n, r1:n]
-            EK(zgemm_strided(OP_N, OP_N, nbk, n - r1, n - r1, C(-1, 0), A + (size_t)r0 * n + r1, n, ms,
-                             ws.X + (size_t)r1 * n + r1, n, ms, zero, ws.X + (size_t)r0 * n + r1, n, ms, nb, ws.gs, st));
+            EK(zgemm_strided(OP_N, OP_N, nbk, n - r1, n - r1, C(-1, 0), Tm + (size_t)r0 * n + r1, n, ms,
+                             Xv + (size_t)r1 * n + r1, n, ms, zero, Xv + (size_t)r0 * n + r1, n, ms, nb, ws.gs, st));
         }
-        trevc_block_kernel<<<dim3((n - r0 + 127) / 128, nb), 128, 0, st>>>(A, ms, n, n, r0, nbk, wout, ws.tnorm, ws.X, ms, n);
+        trevc_block_kernel<<<dim3((n - r0 + 127) / 128, nb), 128, 0, st>>>(Tm, ms, n, n, r0, nbk, wout, ws.tnorm, Xv, ms, n);
     }
-    EK(zgemm_strided(OP_N, OP_N, n, n, n, one, ws.Z, n, ms, ws.X, n, ms, zero, V, n, ms, nb, ws.gs, st));
+    EK(zgemm_strided(OP_N, OP_N, n, n, n, one, ws.Z, n, ms, Xv, n, ms, zero, V, n, ms, nb, ws.gs, st));
     colnorm_kernel<<<dim3((n + 31) / 32, nb), dim3(32, 8), 0, st>>>(V, ms, n, n, ws.nrm);
     colscale_kernel<<<dim3((n + 255) / 256, n, nb), 256, 0, st>>>(V, ms, n, n, ws.nrm);
     return cudaGetLastError();
