@@ -59,6 +59,23 @@ int rcwa_zgemm_batched(int opa, int opb, int M, int N, int K, double alpha_re, d
                        double beta_re, double beta_im, void* C, int ldc, long long stride_c,
                        int nb, void* gemm_scratch, void* stream);
 
+/* Tuning / profiling entry points (not needed by a binding; used by bench.py and tools/).
+ * rcwa_zgemm_batched_cfg: the same product on an explicit kernel configuration:
+ *   cfg = tile | 8*m3;  tile 0: 64x128, 1: 128x64 (256 threads, one CTA/SM, long K), 2: 64x64, 3: 128x32,
+ *   4: 32x128 (128 threads, two CTAs/SM: short K or one skinny dimension); m3 = 3-multiplication complex
+ *   product (25 % fewer fp64 tensor instructions, norm-wise accuracy); cfg = -1: automatic choice.
+ *   Tiles 2-4 and m3 exist for the op pairs (N,N), (N,H), (H,N) only.
+ * rcwa_set_tuning(key, value): process-wide knobs of the automatic choice -- key 0: use m3 (default 1);
+ *   1 / 2: tile of the QR row / column updates; 3: use the 128-thread tiles (default 1); 4: the QR pass
+ *   kernel claims a whole SM per matrix so that no GEMM CTA shares its fp64 pipe (default 1).  Call before
+ *   enqueuing work; the numerical contract does not depend on them. */
+int rcwa_zgemm_batched_cfg(int cfg, int opa, int opb, int M, int N, int K, double alpha_re, double alpha_im,
+                           const void* A, int lda, long long stride_a, const void* B, int ldb, long long stride_b,
+                           double beta_re, double beta_im, void* C, int ldc, long long stride_c,
+                           int nb, void* gemm_scratch, void* stream);
+int rcwa_set_tuning(int key, int value);
+int rcwa_get_tuning(int key);
+
 /* In-place LU with column pivoting for right-solves X*A = B (A*Pi = L*U, L lower, U unit upper).
  * ipiv, perm: int32 [nb,n]; info int32 [nb]; tinv: rcwa_lu_tinv_bytes(n, nb) bytes receiving the
  * inverses of the 128 x 128 diagonal blocks of L and U (they turn the triangular solves into GEMMs).
@@ -93,6 +110,10 @@ int rcwa_eig(void* A, int n, int nb, void* w, void* V, void* ws, size_t ws_bytes
 /* Diagnostics of the last rcwa_eig that used workspace `ws`: out[4*b..] = {QR sweeps, window passes,
  * AED windows, info} of matrix b (device int32 [nb,4]). */
 int rcwa_eig_stats(const void* ws, int n, int nb, int* out, void* stream);
+/* Profile of the QR phase of the last rcwa_eig on `ws`: out = device int64 [nb,6,2] = {launch count, SM cycles}
+ * per pass segment (0 sweep start: deflation scan + shifts, 1 bulge-chain window, 2 small-block slice,
+ * 3 AED Schur slice, 4 AED deflation-scan slice, 5 AED finish). */
+int rcwa_eig_profile(const void* ws, int n, int nb, long long* out, void* stream);
 /* First phase of rcwa_eig on its own (profiling / building block): A[b] -> H[b] upper Hessenberg in
  * place, Z[b] unitary with A_in = Z H Z^H.  Workspace as for rcwa_eig.  This is the HBM-bound
  * streaming kernel of the eigen stage (one fused pass over [A; Z] per column). */

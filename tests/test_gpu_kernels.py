@@ -43,6 +43,44 @@ def test_zgemm(opa, opb, mnk):
     assert rel(out0, f[opa](A) @ f[opb](B)) < 1e-14
 
 
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 8, 9, 10, 11, 12])
+@pytest.mark.parametrize("ops", [("N", "N"), ("N", "H"), ("H", "N")])
+@pytest.mark.parametrize("mnk", [(97, 130, 37), (200, 33, 64), (33, 300, 5), (130, 70, 129), (64, 64, 64)])
+def test_zgemm_explicit_configs(cfg, ops, mnk):
+    """Every tile / 3-multiplication configuration of the DMMA GEMM (rcwa_zgemm_batched_cfg), ragged edges included.
+    The 3M product is accurate norm-wise (|err| <= c eps |A||B|), not component-wise: the bound is on the Frobenius norm."""
+    from torcwa_b200 import _lib
+    opa, opb = ops
+    M, N, K = mnk
+    nb = 3
+    A = rnd(nb, *((M, K) if opa == "N" else (K, M)), seed=11)
+    B = rnd(nb, *((K, N) if opb == "N" else (N, K)), seed=12)
+    Cin = rnd(nb, M, N, seed=13)
+    f = {"N": lambda x: x, "H": lambda x: x.transpose(1, 2).conj()}
+    ref = (0.5 - 0.25j) * (f[opa](A) @ f[opb](B)) + (2.0 + 1.0j) * Cin
+    out = Cin.clone()
+    _lib.zgemm(A, B, opa, opb, alpha=0.5 - 0.25j, beta=2.0 + 1.0j, out=out, cfg=cfg)
+    assert rel(out, ref) < 2e-14
+
+
+def test_zgemm_inplace_window_updates():
+    """The QR phase applies window unitaries in place: C aliases B (rows, M <= 64) or A (columns, N <= 64)."""
+    from torcwa_b200 import _lib
+    U = torch.linalg.qr(rnd(2, 64, 64, seed=21))[0].contiguous()
+    Hrow = rnd(2, 64, 700, seed=22)
+    ref = U.transpose(1, 2).conj() @ Hrow
+    for cfg in (0, 2, 8, 10):
+        X = Hrow.clone()
+        _lib.zgemm(U, X, "H", "N", out=X, cfg=cfg)
+        assert rel(X, ref) < 2e-14
+    Z = rnd(2, 900, 64, seed=23)
+    ref = Z @ U
+    for cfg in (1, 2, 9, 10):
+        X = Z.clone()
+        _lib.zgemm(X, U, "N", "N", out=X, cfg=cfg)
+        assert rel(X, ref) < 2e-14
+
+
 def test_zgemm_large():
     from torcwa_b200 import _lib
     A, B = rnd(2, 500, 700, seed=4), rnd(2, 700, 450, seed=5)

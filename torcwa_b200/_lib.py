@@ -9,12 +9,12 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librcwa_b200.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("RCWA_B200_LIB", "librcwa_b200.so"))   # env: experimental build variants
 
 EXPORTS = [
     "rcwa_b200_abi_version", "rcwa_gemm_scratch_bytes", "rcwa_convmat_workspace_bytes", "rcwa_convmat",
-    "rcwa_zgemm_batched", "rcwa_lu_tinv_bytes", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
-    "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_eig_stats", "rcwa_hessenberg", "rcwa_kz_branch", "rcwa_layer_smatrix_workspace_bytes",
+    "rcwa_zgemm_batched", "rcwa_zgemm_batched_cfg", "rcwa_set_tuning", "rcwa_get_tuning", "rcwa_lu_tinv_bytes", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
+    "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_eig_stats", "rcwa_eig_profile", "rcwa_hessenberg", "rcwa_kz_branch", "rcwa_layer_smatrix_workspace_bytes",
     "rcwa_layer_smatrix", "rcwa_redheffer_workspace_bytes", "rcwa_redheffer", "rcwa_redheffer_bdleft", "rcwa_blockdiag_dense",
 ]
 
@@ -25,6 +25,9 @@ _SIGS = {
     "rcwa_convmat_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "rcwa_convmat": (_i, [_vp, _i, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rcwa_zgemm_batched": (_i, [_i, _i, _i, _i, _i, _d, _d, _vp, _i, _ll, _vp, _i, _ll, _d, _d, _vp, _i, _ll, _i, _vp, _vp]),
+    "rcwa_zgemm_batched_cfg": (_i, [_i, _i, _i, _i, _i, _i, _d, _d, _vp, _i, _ll, _vp, _i, _ll, _d, _d, _vp, _i, _ll, _i, _vp, _vp]),
+    "rcwa_set_tuning": (_i, [_i, _i]),
+    "rcwa_get_tuning": (_i, [_i]),
     "rcwa_lu_tinv_bytes": (_sz, [_i, _i]),
     "rcwa_lu_factor": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rcwa_lu_solve_right": (_i, [_vp, _ll, _i, _i, _vp, _vp, _vp, _ll, _i, _i, _vp, _ll, _i, _vp, _i, _vp, _vp]),
@@ -32,6 +35,7 @@ _SIGS = {
     "rcwa_eig_workspace_bytes": (_sz, [_i, _i]),
     "rcwa_eig": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "rcwa_eig_stats": (_i, [_vp, _i, _i, _vp, _vp]),
+    "rcwa_eig_profile": (_i, [_vp, _i, _i, _vp, _vp]),
     "rcwa_hessenberg": (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),
     "rcwa_kz_branch": (_i, [_vp, _vp, _ll, _vp]),
     "rcwa_layer_smatrix_workspace_bytes": (_sz, [_i, _i]),
@@ -64,6 +68,10 @@ def load():
         if lib.rcwa_b200_abi_version() != 1:
             raise ImportError("torcwa_b200: ABI version mismatch")
         _lib = lib
+        # development knob: RCWA_B200_TUNE="0=1,1=2" -> rcwa_set_tuning(key, value) (see include/rcwa_b200.h)
+        for kv in filter(None, os.environ.get("RCWA_B200_TUNE", "").split(",")):
+            k, v = kv.split("=")
+            lib.rcwa_set_tuning(int(k), int(v))
     return _lib
 
 
@@ -118,8 +126,8 @@ def convmat(grid, ox, oy, nb=None):
 _OPS = {"N": 0, "T": 1, "H": 2}
 
 
-def zgemm(A, B, opa="N", opb="N", alpha=1.0, beta=0.0, out=None):
-    """Batched C = alpha op(A) op(B) + beta C on [nb,*,*] complex128 tensors."""
+def zgemm(A, B, opa="N", opb="N", alpha=1.0, beta=0.0, out=None, cfg=None):
+    """Batched C = alpha op(A) op(B) + beta C on [nb,*,*] complex128 tensors (cfg: explicit kernel configuration)."""
     lib = load()
     _c128(A, "A"); _c128(B, "B")
     nb = A.shape[0]
@@ -132,6 +140,11 @@ def zgemm(A, B, opa="N", opb="N", alpha=1.0, beta=0.0, out=None):
     _c128(out, "out")
     gs = _ws(lib.rcwa_gemm_scratch_bytes(nb), A.device)
     al, be = complex(alpha), complex(beta)
+    if cfg is not None:
+        _check(lib.rcwa_zgemm_batched_cfg(int(cfg), _OPS[opa], _OPS[opb], M, N, K, al.real, al.imag,
+                                          _ptr(A), A.shape[2], A.shape[1] * A.shape[2], _ptr(B), B.shape[2], B.shape[1] * B.shape[2],
+                                          be.real, be.imag, _ptr(out), N, M * N, nb, _ptr(gs), _stream()), "rcwa_zgemm_batched_cfg")
+        return out
     _check(lib.rcwa_zgemm_batched(_OPS[opa], _OPS[opb], M, N, K, al.real, al.imag,
                                   _ptr(A), A.shape[2], A.shape[1] * A.shape[2], _ptr(B), B.shape[2], B.shape[1] * B.shape[2],
                                   be.real, be.imag, _ptr(out), N, M * N, nb, _ptr(gs), _stream()), "rcwa_zgemm_batched")
@@ -206,10 +219,15 @@ def eig(A):
     stats = torch.empty((nb, 4), dtype=torch.int32, device=A.device)
     _check(lib.rcwa_eig_stats(_ptr(ws), n, nb, _ptr(stats), _stream()), "rcwa_eig_stats")
     last_eig_stats = stats
+    prof = torch.empty((nb, 6, 2), dtype=torch.int64, device=A.device)
+    _check(lib.rcwa_eig_profile(_ptr(ws), n, nb, _ptr(prof), _stream()), "rcwa_eig_profile")
+    global last_eig_profile
+    last_eig_profile = prof
     return w, V, info
 
 
 last_eig_stats = None
+last_eig_profile = None      # [nb,6,2] int64: {launches, SM cycles} per QR pass segment (rcwa_eig_profile)
 
 
 def hessenberg_(A):

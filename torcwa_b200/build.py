@@ -42,20 +42,23 @@ def _sources():
     return hdrs
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA translation unit for sm_100a and link librcwa_b200.so in-tree."""
+def build(force=False, verbose=False, defines=(), suffix=""):
+    """Compile every CUDA translation unit for sm_100a and link librcwa_b200.so in-tree.
+    `defines` / `suffix` build an experimental variant (e.g. defines=("HB_NB=64",), suffix="_hb64") next to it;
+    torcwa_b200._lib loads it when RCWA_B200_LIB names it."""
     srcs = [os.path.join(CSRC, f) for f in CU_FILES]
+    LIB = os.path.join(HERE, "librcwa_b200%s.so" % suffix)
     stamp = LIB + ".stamp"
-    dig = _digest(srcs + _sources())
+    dig = _digest(srcs + _sources()) + "".join(defines)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
-    bdir = os.path.join(HERE, "build")
+    bdir = os.path.join(HERE, "build" + suffix)
     os.makedirs(bdir, exist_ok=True)
     nvcc = _nvcc()
 
     def one(src):
         obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

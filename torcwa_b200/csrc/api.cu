@@ -53,6 +53,26 @@ int rcwa_zgemm_batched(int opa, int opb, int M, int N, int K, double alpha_re, d
                             C(beta_re, beta_im), (cplx*)Cm, ldc, sc, nb, (ZGemmProblem*)gs, S(stream)));
 }
 
+int rcwa_zgemm_batched_cfg(int cfg, int opa, int opb, int M, int N, int K, double alpha_re, double alpha_im,
+                           const void* A, int lda, long long sa, const void* B, int ldb, long long sb,
+                           double beta_re, double beta_im, void* Cm, int ldc, long long sc, int nb, void* gs, void* stream) {
+    if (cfg < -1 || cfg > 15 || (cfg >= 0 && (cfg & 7) > 4)) return -1;
+    if (opa < 0 || opa > 2) return -2;
+    if (opb < 0 || opb > 2) return -3;
+    if (M < 0 || N < 0 || K < 0) return -4;
+    if (!A || !B || !Cm || !gs) return -9;
+    if (nb <= 0) return -20;
+    return cu(zgemm_strided_cfg(cfg, opa, opb, M, N, K, C(alpha_re, alpha_im), (const cplx*)A, lda, sa, (const cplx*)B, ldb, sb,
+                                C(beta_re, beta_im), (cplx*)Cm, ldc, sc, nb, (ZGemmProblem*)gs, S(stream)));
+}
+
+int rcwa_set_tuning(int key, int value) {
+    if (key < 0 || key > 7) return -1;
+    gemm_set_tuning(key, value);
+    return 0;
+}
+int rcwa_get_tuning(int key) { return gemm_get_tuning(key); }
+
 size_t rcwa_lu_tinv_bytes(int n, int nb) { return align256(lu_tinv_elems(n, nb > 0 ? nb : 1) * sizeof(cplx)); }
 
 int rcwa_lu_factor(void* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info, void* tinv, void* gs, void* stream) {
@@ -119,6 +139,14 @@ int rcwa_eig_stats(const void* ws, int n, int nb, int* out, void* stream) {
     if (nb <= 0) return -3;
     if (!out) return -4;
     return cu(eig_stats((const char*)ws, n, nb, out, S(stream)));
+}
+
+int rcwa_eig_profile(const void* ws, int n, int nb, long long* out, void* stream) {
+    if (!ws) return -1;
+    if (n <= 0) return -2;
+    if (nb <= 0) return -3;
+    if (!out) return -4;
+    return cu(eig_profile((const char*)ws, n, nb, out, S(stream)));
 }
 
 int rcwa_hessenberg(void* A, int n, int nb, void* Z, void* ws, size_t ws_bytes, void* stream) {

@@ -34,9 +34,18 @@
 #define QR_NS 16           // max simultaneous shifts / bulges
 #define QR_SMALL 48         // active blocks up to this size are Schur-factored directly in shared memory
 #define QR_AED_W 48         // aggressive-early-deflation window
-#define QR_AED_SLICE 300    // rotations per launch while Schur-factoring the AED window
-#define QR_AED_SWAPS 160    // eigenvalue swaps per launch during the AED deflation scan
-#define QR_SLICE_ROT 400    // rotations per launch of a small-block solve (time slice: keeps the batch in lockstep)
+// Time-slice budgets of the serial pieces of a pass.  A launch lasts as long as its slowest matrix, and with
+// ~100 matrices in a batch some matrix is in its most expensive segment in EVERY launch (measured: mean
+// own work 117 us per pass, launch duration 400 us), so every segment type is cut to about the duration of a
+// bulge-chain window (60-80 us).
+struct QrBudget {
+    int schur;      // rotations per launch while Schur-factoring an AED window or a small block
+    int swaps;      // eigenvalue swaps per launch during the AED deflation scan
+    int restore;    // Householder steps per launch while folding the AED spike back to Hessenberg form
+};
+#define QR_BUDGET_SCHUR 160
+#define QR_BUDGET_SWAPS 100
+#define QR_BUDGET_RESTORE 12
 #define QR_MAXSTALL 40     // sweeps without deflation before giving up on a matrix
 #define TV_NB 32           // eigenvector back-substitution block
 
@@ -58,11 +67,13 @@ struct QrState {
     int aed_kw, aed_nw;  // AED window [aed_kw, aed_kw + aed_nw) (phase 3)
     int p_last;          // window start of the previous chase pass (its column update may still be in flight)
     int aed_off;         // AED disabled for this matrix (its window failed to converge)
-    int aed_stage;       // 0: Schur slices, 1: deflation scan slices (then restore + finish)
+    int aed_stage;       // 0: Schur slices, 1: deflation scan slices, 2: Hessenberg-restore slices (then finish)
     int aed_prog[4];     // scan progress: ns, ilst, knt, kcur
     int shifts_ready;    // phase 1 may start with st.shifts as they are (supplied by AED)
     int aeds, aed_deflated;   // statistics
     int pad0, pad1;
+    long long cyc[6];    // profiling: SM cycles spent per pass segment (0 sweep start: scan + shifts, 1 chase, 2 small-block
+    int cnt[6];          //   slice, 3 AED Schur slice, 4 AED scan slice, 5 AED finish: scan + restore + write-back) and counts
     int kpos[QR_NS];     // column of each bulge (leading first): bulge element is H[k+2][k]
     cplx shifts[QR_NS];
 };
@@ -74,13 +85,18 @@ HD void givens(cplx a, cplx b, double& c, cplx& s, cplx& r) {
     if (cis_zero(a)) { c = 0.0; double nb = cabs_(b); s = cscale(cconj(b), 1.0 / nb); r = C(nb, 0); return; }
     const double na2 = cabs2(a), nb2 = cabs2(b), n2 = na2 + nb2;
     if (na2 > 1e-280 && nb2 > 1e-280 && n2 < 1e280) {
-        // common, well-scaled case: two square roots and two divisions (this sits on the serial critical
-        // path of every chase step; hypot-based scaling is several times more expensive in fp64)
-        const double na = sqrt(na2), nrm = sqrt(n2);
-        const double inv = 1.0 / (na * nrm);
-        c = na / nrm;
-        s = cscale(cmul(a, cconj(b)), inv);
-        r = cscale(a, nrm / na);
+        // common, well-scaled case.  This sits on the serial critical path of every chase step and of every
+        // small-Schur rotation: two INDEPENDENT reciprocal square roots (they pipeline) and multiplications
+        // instead of two square roots and three divisions in sequence (several hundred cycles in fp64).
+#ifdef RCWA_EMU
+        const double ina = 1.0 / sqrt(na2), inr = 1.0 / sqrt(n2);
+#else
+        const double ina = rsqrt(na2), inr = rsqrt(n2);
+#endif
+        const double w = ina * inr;                 // 1 / (|a| * norm)
+        c = na2 * w;                                // |a| / norm
+        s = cscale(cmul(a, cconj(b)), w);
+        r = cscale(a, n2 * w);                      // a * norm / |a|
         return;
     }
     const double na = cabs_(a), nb = cabs_(b);
@@ -185,23 +201,61 @@ DEV int tiny_hqr_eigs(int lane, int nlanes, cplx* T, int ldt, int m, cplx* wout)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Resumable single-shift QR (zlahqr with Schur vectors) on an m x m upper-Hessenberg block held in
+// Largest l in (0, i] whose subdiagonal H[l][l-1] is negligible (LAPACK zlahqr test); 0 if none.
+// Warp version: every lane tests one candidate, one ballot per 32 candidates.
+DEV int schur_find_split(const Cta& c, const cplx* Hs, int i) {
+#ifndef RCWA_EMU
+    if (c.warp_only && c.nthreads == 32) {
+        for (int base = i; base > 0; base -= 32) {
+            const int k = base - c.tid;
+            bool z = false;
+            if (k > 0) {
+                const cplx h10 = Hs[k * QR_LD + k - 1];
+                z = cis_zero(h10);
+                if (!z) {
+                    double extra = 0.0;
+                    if (k - 2 >= 0) extra += cabs1(Hs[(k - 1) * QR_LD + k - 2]);
+                    if (k + 1 <= i) extra += cabs1(Hs[(k + 1) * QR_LD + k]);
+                    z = negligible_subdiag(h10, Hs[(k - 1) * QR_LD + k - 1], Hs[k * QR_LD + k], Hs[(k - 1) * QR_LD + k], extra);
+                }
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, z);
+            if (mask) return base - (__ffs(mask) - 1);
+        }
+        return 0;
+    }
+#endif
+    int l;
+    for (l = i; l > 0; --l) {
+        cplx h10 = Hs[l * QR_LD + l - 1];
+        if (cis_zero(h10)) break;
+        double extra = 0.0;
+        if (l - 2 >= 0) extra += cabs1(Hs[(l - 1) * QR_LD + l - 2]);
+        if (l + 1 <= i) extra += cabs1(Hs[(l + 1) * QR_LD + l]);
+        if (negligible_subdiag(h10, Hs[(l - 1) * QR_LD + l - 1], Hs[l * QR_LD + l], Hs[(l - 1) * QR_LD + l], extra)) break;
+    }
+    return l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Resumable single-shift QR (Schur form with Schur vectors) on an m x m upper-Hessenberg block held in
 // shared memory (Hs, Us with leading dimension QR_LD; Us accumulates the unitary).  Runs at most
 // `budget` rotations, then returns; state (i, its) lives in QrState so the next launch continues.
 // Returns 1 when the block is upper triangular, 0 if more slices are needed, -1 on failure.
-DEV int small_schur_slice(const Cta& c, cplx* Hs, cplx* Us, int m, int* pi, int* pits, int budget) {
+//
+// Each QR iteration on the active block [l, i] is an EXPLICIT shifted step, H - sig I = Q R,
+// H' = R Q + sig I, in two phases that need one group barrier per rotation instead of three:
+//   phase 1 (thread j owns COLUMN j): for k = l..i-1 every thread forms the same rotation G_k from
+//           (R[k][k], H[k+1][k]) and applies it to rows (k, k+1) of its own columns; the rotations are
+//           parked in rot_c / rot_s;
+//   phase 2 (thread r owns ROW r of H or of U): applies the whole parked sequence to its row, carrying
+//           the running element in a register -- no barriers at all.
+// sig is subtracted from / added back to the diagonal of the active block only (the rotations are the
+// identity outside it, so this is the same similarity as the implicit step).
+DEV int small_schur_slice(const Cta& c, cplx* Hs, cplx* Us, int m, int* pi, int* pits, int budget, double* rot_c, cplx* rot_s) {
     int i = *pi, its = *pits, used = 0;
     while (i >= 1) {
-        // ---- deflation scan (uniform scalar code; every thread reads the same shared values)
-        int l;
-        for (l = i; l > 0; --l) {
-            cplx h10 = Hs[l * QR_LD + l - 1];
-            if (cis_zero(h10)) break;
-            double extra = 0.0;
-            if (l - 2 >= 0) extra += cabs1(Hs[(l - 1) * QR_LD + l - 2]);
-            if (l + 1 <= i) extra += cabs1(Hs[(l + 1) * QR_LD + l]);
-            if (negligible_subdiag(h10, Hs[(l - 1) * QR_LD + l - 1], Hs[l * QR_LD + l], Hs[(l - 1) * QR_LD + l], extra)) break;
-        }
+        const int l = schur_find_split(c, Hs, i);
         GROUP_SYNC(c);
         if (l > 0 && c.tid == 0) Hs[l * QR_LD + l - 1] = C(0, 0);
         GROUP_SYNC(c);
@@ -220,30 +274,46 @@ DEV int small_schur_slice(const Cta& c, cplx* Hs, cplx* Us, int m, int* pi, int*
             cplx den = (cabs2(den1) >= cabs2(den2)) ? den1 : den2;
             sig = cis_zero(den) ? d : csub(d, cdiv(cmul(b, cc), den));
         }
-        // ---- one QR sweep l..i with Schur-vector accumulation (full rows/columns of the block)
+        GROUP_SYNC(c);                                         // every thread has read the shift operands
+        for (int d = l + c.tid; d <= i; d += c.nthreads) Hs[d * QR_LD + d] = csub(Hs[d * QR_LD + d], sig);
+        GROUP_SYNC(c);
+        // ---- phase 1: R = Q^H (H - sig I)
+        cplx r_prev = C(0, 0);
         for (int k = l; k < i; ++k) {
-            cplx a, b;
-            if (k == l) { a = csub(Hs[k * QR_LD + k], sig); b = Hs[(k + 1) * QR_LD + k]; }
-            else { a = Hs[k * QR_LD + k - 1]; b = Hs[(k + 1) * QR_LD + k - 1]; }
             double cs; cplx sn, r;
-            givens(a, b, cs, sn, r);
-            GROUP_SYNC(c);
-            if (k > l && c.tid == 0) { Hs[k * QR_LD + k - 1] = r; Hs[(k + 1) * QR_LD + k - 1] = C(0, 0); }
-            for (int j = k + c.tid; j < m; j += c.nthreads) {
-                cplx x = Hs[k * QR_LD + j], y = Hs[(k + 1) * QR_LD + j];
+            givens(Hs[k * QR_LD + k], Hs[(k + 1) * QR_LD + k], cs, sn, r);
+            if (c.tid == 0) {
+                rot_c[k] = cs; rot_s[k] = sn;
+                // column k-1 gets its final (r, 0) one step late: every thread has read it by now
+                if (k > l) { Hs[(k - 1) * QR_LD + k - 1] = r_prev; Hs[k * QR_LD + k - 1] = C(0, 0); }
+            }
+            r_prev = r;
+            for (int j = k + 1 + c.tid; j < m; j += c.nthreads) {
+                const cplx x = Hs[k * QR_LD + j], y = Hs[(k + 1) * QR_LD + j];
                 Hs[k * QR_LD + j] = cadd(cscale(x, cs), cmul(sn, y));
                 Hs[(k + 1) * QR_LD + j] = csub(cscale(y, cs), cmul(cconj(sn), x));
             }
             GROUP_SYNC(c);
-            const int rmax = (k + 2 < i) ? k + 2 : i;
-            for (int idx = c.tid; idx < (rmax + 1) + m; idx += c.nthreads) {
-                cplx* base = (idx <= rmax) ? (Hs + idx * QR_LD) : (Us + (idx - rmax - 1) * QR_LD);
-                cplx x = base[k], y = base[k + 1];
-                base[k] = cadd(cscale(x, cs), cmul(y, cconj(sn)));
-                base[k + 1] = csub(cscale(y, cs), cmul(x, sn));
-            }
-            GROUP_SYNC(c);      // the next rotation reads the bulge this right-update just created
         }
+        if (c.tid == 0) { Hs[(i - 1) * QR_LD + i - 1] = r_prev; Hs[i * QR_LD + i - 1] = C(0, 0); }
+        GROUP_SYNC(c);
+        // ---- phase 2: H' = R Q (rows 0..i; row r only holds columns >= r) and U <- U Q (all m rows)
+        for (int idx = c.tid; idx < (i + 1) + m; idx += c.nthreads) {
+            cplx* row; int ks;
+            if (idx <= i) { row = Hs + idx * QR_LD; ks = (idx - 1 > l) ? idx - 1 : l; }
+            else { row = Us + (idx - i - 1) * QR_LD; ks = l; }
+            cplx x = row[ks];
+            for (int k = ks; k < i; ++k) {
+                const cplx y = row[k + 1];
+                const double cs = rot_c[k]; const cplx sn = rot_s[k];
+                row[k] = cadd(cscale(x, cs), cmul(y, cconj(sn)));
+                x = csub(cscale(y, cs), cmul(x, sn));
+            }
+            row[i] = x;
+        }
+        GROUP_SYNC(c);
+        for (int d = l + c.tid; d <= i; d += c.nthreads) Hs[d * QR_LD + d] = cadd(Hs[d * QR_LD + d], sig);
+        GROUP_SYNC(c);
         used += i - l;
         ++its;
     }
@@ -270,6 +340,8 @@ struct QrScratch {
     int ss_rc, ss_i, ss_its;    // results of a small-Schur slice run by warp 0
     cplx hv[QR_W];              // Householder vector (AED restore)
     double red[40];
+    double rot_c[QR_W];         // rotations of one small-Schur iteration (phase 1 -> phase 2)
+    cplx rot_s[QR_W];
 };
 
 HD size_t qr_pass_smem_bytes(int n) {
@@ -331,21 +403,32 @@ DEV int aed_deflation_scan(const Cta& c, cplx* T, cplx* V, int nw, cplx s, int* 
 // r0..r1-1 of column `col`, stride QR_LD), or for an explicit vector when M == nullptr (then `u`
 // holds x on entry).  Thread 0 builds u (indexed by absolute row) into `u`; returns beta via *beta.
 DEV void small_reflector(const Cta& c, cplx* u, int r0, int r1, cplx* beta_out) {
-    if (c.tid == 0) {
-        double ss = 0.0;
-        for (int r = r0; r < r1; ++r) ss += cabs2(u[r]);
-        const double sigma = sqrt(ss);
-        const cplx x1 = u[r0];
-        const double ax = cabs_(x1);
-        if (sigma == 0.0) { for (int r = r0; r < r1; ++r) u[r] = C(0, 0); *beta_out = x1; }
-        else {
-            const cplx ph = (ax == 0.0) ? C(1, 0) : cscale(x1, 1.0 / ax);
-            const cplx beta = cscale(ph, -sigma);
-            const double scl = 1.0 / sqrt(sigma * (sigma + ax));
-            u[r0] = csub(u[r0], beta);
-            for (int r = r0; r < r1; ++r) u[r] = cscale(u[r], scl);
-            *beta_out = beta;
+    // every thread forms the same scalars (partial sums combined by warp shuffles on the device)
+    double ss = 0.0;
+#ifndef RCWA_EMU
+    if (c.warp_only && c.nthreads == 32) {
+        for (int r = r0 + c.tid; r < r1; r += 32) ss += cabs2(u[r]);
+        ss = warp_sum(ss);
+    } else
+#endif
+    { for (int r = r0; r < r1; ++r) ss += cabs2(u[r]); }
+    const double sigma = sqrt(ss);
+    const cplx x1 = u[r0];
+    const double ax = cabs_(x1);
+    GROUP_SYNC(c);                                   // all reads of u done before anyone rewrites it
+    if (sigma == 0.0) {
+        for (int r = r0 + c.tid; r < r1; r += c.nthreads) u[r] = C(0, 0);
+        *beta_out = x1;
+    } else {
+        const cplx ph = (ax == 0.0) ? C(1, 0) : cscale(x1, 1.0 / ax);
+        const cplx beta = cscale(ph, -sigma);
+        const double scl = 1.0 / sqrt(sigma * (sigma + ax));
+        for (int r = r0 + c.tid; r < r1; r += c.nthreads) {
+            cplx v = u[r];
+            if (r == r0) v = csub(v, beta);
+            u[r] = cscale(v, scl);
         }
+        *beta_out = beta;
     }
     GROUP_SYNC(c);
 }
@@ -353,37 +436,50 @@ DEV void small_reflector(const Cta& c, cplx* u, int r0, int r1, cplx* beta_out) 
 // M <- (I - u u^H) M on rows r0..r1-1, columns c0..c1-1 (one thread per column: dot then update)
 DEV void small_hh_left(const Cta& c, cplx* M, const cplx* u, int r0, int r1, int c0, int c1) {
     for (int j = c0 + c.tid; j < c1; j += c.nthreads) {
-        cplx w = C(0, 0);
-        for (int r = r0; r < r1; ++r) w = cadd(w, cmulc(u[r], M[r * QR_LD + j]));
-        for (int r = r0; r < r1; ++r) M[r * QR_LD + j] = csub(M[r * QR_LD + j], cmul(u[r], w));
+        cplx w = C(0, 0), w2 = C(0, 0);              // two chains: the dot product is latency-bound
+        int r = r0;
+        for (; r + 1 < r1; r += 2) { w = cadd(w, cmulc(u[r], M[r * QR_LD + j])); w2 = cadd(w2, cmulc(u[r + 1], M[(r + 1) * QR_LD + j])); }
+        if (r < r1) w = cadd(w, cmulc(u[r], M[r * QR_LD + j]));
+        w = cadd(w, w2);
+        for (r = r0; r < r1; ++r) M[r * QR_LD + j] = csub(M[r * QR_LD + j], cmul(u[r], w));
     }
 }
 // M <- M (I - u u^H) on rows q0..q1-1, columns r0..r1-1 (one thread per row)
 DEV void small_hh_right(const Cta& c, cplx* M, const cplx* u, int q0, int q1, int r0, int r1) {
     for (int i = q0 + c.tid; i < q1; i += c.nthreads) {
-        cplx y = C(0, 0);
-        for (int r = r0; r < r1; ++r) y = cfma(M[i * QR_LD + r], u[r], y);
-        for (int r = r0; r < r1; ++r) M[i * QR_LD + r] = csub(M[i * QR_LD + r], cmul(y, cconj(u[r])));
+        cplx y = C(0, 0), y2 = C(0, 0);
+        int r = r0;
+        for (; r + 1 < r1; r += 2) { y = cfma(M[i * QR_LD + r], u[r], y); y2 = cfma(M[i * QR_LD + r + 1], u[r + 1], y2); }
+        if (r < r1) y = cfma(M[i * QR_LD + r], u[r], y);
+        y = cadd(y, y2);
+        for (r = r0; r < r1; ++r) M[i * QR_LD + r] = csub(M[i * QR_LD + r], cmul(y, cconj(u[r])));
     }
 }
 
 // After the scan: fold the remaining spike s*conj(V[0,0:ns]) back into Hessenberg form.
 // T[0:ns,0:ns] <- Hessenberg, T[0:ns, ns:nw] and V[:,0:ns] updated accordingly (LAPACK zlaqr2:
 // zlarfg on the spike, zlarf x3, zgehrd, zunmhr -- done here with Hermitian reflectors).
-DEV void aed_restore_hessenberg(const Cta& c, cplx* T, cplx* V, int nw, int ns, cplx* u) {
-    if (ns <= 1) return;
+// Resumable: *pj = -1 on entry of the first slice (the spike reflector), then the column index of the
+// reduction; at most `budget` Householder steps per call.  Returns 1 when finished.
+DEV int aed_restore_hessenberg(const Cta& c, cplx* T, cplx* V, int nw, int ns, cplx* u, int* pj, int budget) {
+    if (ns <= 1) return 1;
     cplx beta;
-    // reflector that maps the spike direction conj(V[0,0:ns]) onto e_0
-    for (int r = c.tid; r < ns; r += c.nthreads) u[r] = cconj(V[r]);
-    GROUP_SYNC(c);
-    small_reflector(c, u, 0, ns, &beta);
-    small_hh_left(c, T, u, 0, ns, 0, nw);
-    GROUP_SYNC(c);
-    small_hh_right(c, T, u, 0, ns, 0, ns);
-    small_hh_right(c, V, u, 0, nw, 0, ns);
-    GROUP_SYNC(c);
+    int j = *pj, used = 0;
+    if (j < 0) {
+        // reflector that maps the spike direction conj(V[0,0:ns]) onto e_0
+        for (int r = c.tid; r < ns; r += c.nthreads) u[r] = cconj(V[r]);
+        GROUP_SYNC(c);
+        small_reflector(c, u, 0, ns, &beta);
+        small_hh_left(c, T, u, 0, ns, 0, nw);
+        GROUP_SYNC(c);
+        small_hh_right(c, T, u, 0, ns, 0, ns);
+        small_hh_right(c, V, u, 0, nw, 0, ns);
+        GROUP_SYNC(c);
+        j = 0; used = 2;
+    }
     // Hessenberg reduction of T[0:ns,0:ns]; reflectors act on indices >= 1, so the spike stays on e_0
-    for (int j = 0; j + 2 < ns; ++j) {
+    for (; j + 2 < ns; ++j) {
+        if (used >= budget) { *pj = j; return 0; }
         for (int r = j + 1 + c.tid; r < ns; r += c.nthreads) u[r] = T[r * QR_LD + j];
         GROUP_SYNC(c);
         small_reflector(c, u, j + 1, ns, &beta);
@@ -396,7 +492,10 @@ DEV void aed_restore_hessenberg(const Cta& c, cplx* T, cplx* V, int nw, int ns, 
         small_hh_right(c, T, u, 0, ns, j + 1, ns);
         small_hh_right(c, V, u, 0, nw, j + 1, ns);
         GROUP_SYNC(c);
+        ++used;
     }
+    *pj = j;
+    return 1;
 }
 
 // emit the three GEMM problems that apply the window unitary U (wl x wl at Ug) for the window [p, p+wl)
@@ -417,9 +516,16 @@ DEV void emit_window_gemms(cplx* H, int ldh, int n, cplx* Zm, int ldz, cplx* Ug,
     g.M = n; g.N = wl; g.K = wl; *prob_z = g;                                            // Z[:, p:wend] <- (.) * U
 }
 
+#ifdef RCWA_EMU
+#define QR_CLOCK() 0LL
+#else
+#define QR_CLOCK() clock64()
+#endif
+#define QR_ACCOUNT(seg) do { if (c.tid == 0) { const long long _t = QR_CLOCK(); st.cyc[seg] += _t - tseg; st.cnt[seg]++; tseg = _t; } } while (0)
+
 DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, QrState* stg,
                       cplx* Ug, cplx* Vg, cplx* Tg, ZGemmProblem* prob_rows, ZGemmProblem* prob_cols_main,
-                      ZGemmProblem* prob_cols, ZGemmProblem* prob_z) {
+                      ZGemmProblem* prob_cols, ZGemmProblem* prob_z, QrBudget bud) {
     // Ug: this pass's window unitary (double-buffered by the host: its GEMMs may still run while the next
     //     pass works); Vg/Tg: persistent copies for the time-sliced AED / small-block solves.
     // prob_rows, prob_cols_main run on the main stream before the next pass; prob_cols, prob_z on the side
@@ -436,6 +542,8 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
     if (c.tid == 0) { prob_rows->M = 0; prob_cols_main->M = 0; prob_cols->M = 0; prob_z->M = 0; st = *stg; }
     CTA_SYNC();
     if (st.done) return;
+    long long tseg = QR_CLOCK();
+    const bool ran0 = (st.phase == 0);
 
     if (st.phase == 0) {
         // ---------------- new sweep: deflation scan over the whole remaining matrix [1..hi]
@@ -504,6 +612,8 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         }
     }
 
+    if (ran0) QR_ACCOUNT(0);
+
     if (st.phase == 3) {
         // ---------------- AED: time slices of the window's Schur factorisation on a COPY (Tg, Ug), then
         // the deflation analysis; H itself is only touched if something deflates
@@ -520,12 +630,13 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         if (st.aed_stage == 0) {
             if (c.tid < w1.nthreads) {
                 int si = st.ss_i, sits = st.ss_its;
-                const int rc1 = small_schur_slice(w1, Hs, Us, nw, &si, &sits, QR_AED_SLICE);
+                const int rc1 = small_schur_slice(w1, Hs, Us, nw, &si, &sits, bud.schur, sc->rot_c, sc->rot_s);
                 if (c.tid == 0) { sc->ss_rc = rc1; sc->ss_i = si; sc->ss_its = sits; }
             }
             CTA_SYNC();
             const int rc = sc->ss_rc;
             if (rc < 0) {               // the window did not converge: fall back to plain sweeps for this matrix
+                QR_ACCOUNT(3);
                 if (c.tid == 0) { st.aed_off = 1; st.phase = 0; st.passes++; *stg = st; }
                 return;
             }
@@ -535,6 +646,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
                 Tg[r * QR_W + q] = Hs[r * QR_LD + q];
                 Vg[r * QR_W + q] = Us[r * QR_LD + q];
             }
+            QR_ACCOUNT(3);
             if (c.tid == 0) {
                 st.ss_i = sc->ss_i; st.ss_its = sc->ss_its; st.ss_fresh = 0; st.passes++;
                 if (rc == 1) { st.aed_stage = 1; st.aed_prog[0] = nw; st.aed_prog[1] = 0; st.aed_prog[2] = 0; st.aed_prog[3] = -1; }
@@ -542,36 +654,58 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
             }
             return;
         }
-        // ---- stage 1: deflation scan in time slices, then restore + finish in the launch that completes it
+        // ---- stage 1: deflation scan in time slices; stage 2: Hessenberg restore in time slices; then finish
         const cplx spike = H[(size_t)kw * ldh + kw - 1];
-        if (c.tid < w1.nthreads) {
-            int prog[4] = {st.aed_prog[0], st.aed_prog[1], st.aed_prog[2], st.aed_prog[3]};
-            const int done1 = aed_deflation_scan(w1, Hs, Us, nw, spike, prog, QR_AED_SWAPS);
-            if (c.tid == 0) { sc->ss_rc = done1; sc->aed_ns = prog[0]; sc->ss_i = prog[1]; sc->ss_its = prog[2]; sc->nslots = prog[3]; }
-        }
-        CTA_SYNC();
-        if (!sc->ss_rc) {
-            for (int idx = c.tid; idx < nw * nw; idx += c.nthreads) {
-                int r = idx / nw, q = idx % nw;
-                Tg[r * QR_W + q] = Hs[r * QR_LD + q];
-                Vg[r * QR_W + q] = Us[r * QR_LD + q];
+        if (st.aed_stage == 1) {
+            if (c.tid < w1.nthreads) {
+                int prog[4] = {st.aed_prog[0], st.aed_prog[1], st.aed_prog[2], st.aed_prog[3]};
+                const int done1 = aed_deflation_scan(w1, Hs, Us, nw, spike, prog, bud.swaps);
+                if (c.tid == 0) { sc->ss_rc = done1; sc->aed_ns = prog[0]; sc->ss_i = prog[1]; sc->ss_its = prog[2]; sc->nslots = prog[3]; }
             }
-            if (c.tid == 0) {
-                st.aed_prog[0] = sc->aed_ns; st.aed_prog[1] = sc->ss_i; st.aed_prog[2] = sc->ss_its; st.aed_prog[3] = sc->nslots;
-                st.passes++; *stg = st;
+            CTA_SYNC();
+            const int scan_done = sc->ss_rc, ns1 = sc->aed_ns;
+            const bool need_restore = scan_done && (nw - ns1 > 0) && (ns1 > 1);
+            if (scan_done && c.tid == 0) {                       // shifts offered to the next sweep: trailing
+                const int nsh1 = (ns1 < QR_NS) ? ns1 : QR_NS;    // undeflated eigenvalues of the window
+                for (int j = 0; j < nsh1; ++j) st.shifts[j] = Hs[(ns1 - nsh1 + j) * QR_LD + (ns1 - nsh1 + j)];
             }
-            return;
+            if (!scan_done || need_restore) {
+                for (int idx = c.tid; idx < nw * nw; idx += c.nthreads) {
+                    int r = idx / nw, q = idx % nw;
+                    Tg[r * QR_W + q] = Hs[r * QR_LD + q];
+                    Vg[r * QR_W + q] = Us[r * QR_LD + q];
+                }
+                QR_ACCOUNT(4);
+                if (c.tid == 0) {
+                    st.aed_prog[0] = ns1; st.aed_prog[1] = sc->ss_i; st.aed_prog[2] = sc->ss_its; st.aed_prog[3] = sc->nslots;
+                    if (need_restore) { st.aed_stage = 2; st.aed_prog[1] = -1; }
+                    st.passes++; *stg = st;
+                }
+                return;
+            }
+            CTA_SYNC();
+        } else {
+            if (c.tid < w1.nthreads) {
+                int rj = st.aed_prog[1];
+                const int done2 = aed_restore_hessenberg(w1, Hs, Us, nw, st.aed_prog[0], sc->hv, &rj, bud.restore);
+                if (c.tid == 0) { sc->ss_rc = done2; sc->ss_i = rj; sc->aed_ns = st.aed_prog[0]; }
+            }
+            CTA_SYNC();
+            if (!sc->ss_rc) {
+                for (int idx = c.tid; idx < nw * nw; idx += c.nthreads) {
+                    int r = idx / nw, q = idx % nw;
+                    Tg[r * QR_W + q] = Hs[r * QR_LD + q];
+                    Vg[r * QR_W + q] = Us[r * QR_LD + q];
+                }
+                QR_ACCOUNT(5);
+                if (c.tid == 0) { st.aed_prog[1] = sc->ss_i; st.passes++; *stg = st; }
+                return;
+            }
         }
         const int ns = sc->aed_ns;
         const int nd = nw - ns;
-        const int nsh = (ns < QR_NS) ? ns : QR_NS;              // shifts offered to the next sweep:
-        if (c.tid == 0) {                                        // trailing undeflated eigenvalues of the window
-            for (int j = 0; j < nsh; ++j) st.shifts[j] = Hs[(ns - nsh + j) * QR_LD + (ns - nsh + j)];
-        }
-        CTA_SYNC();
+        const int nsh = (ns < QR_NS) ? ns : QR_NS;
         if (nd > 0) {
-            if (c.tid < w1.nthreads) aed_restore_hessenberg(w1, Hs, Us, nw, ns, sc->hv);
-            CTA_SYNC();
             for (int idx = c.tid; idx < nw * nw; idx += c.nthreads) {
                 int r = idx / nw, q = idx % nw;
                 const bool below = (q < ns) ? (r > q + 1) : (r > q);        // exact zeros below the (quasi-)triangle
@@ -579,6 +713,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
                 Ug[r * QR_W + q] = Us[r * QR_LD + q];
             }
         }
+        QR_ACCOUNT(5);
         if (c.tid == 0) {
             st.passes++;
             if (nd > 0) {
@@ -612,7 +747,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         Cta w1 = c; w1.warp_only = 1; w1.nthreads = (c.nthreads < 32) ? c.nthreads : 32;
         if (c.tid < w1.nthreads) {
             int si1 = st.ss_i, sits1 = st.ss_its;
-            const int rc1 = small_schur_slice(w1, Hs, Us, m2, &si1, &sits1, QR_SLICE_ROT);
+            const int rc1 = small_schur_slice(w1, Hs, Us, m2, &si1, &sits1, bud.schur, sc->rot_c, sc->rot_s);
             if (c.tid == 0) { sc->ss_rc = rc1; sc->ss_i = si1; sc->ss_its = sits1; }
         }
         CTA_SYNC();
@@ -623,6 +758,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
             Vg[r * QR_W + q] = Us[r * QR_LD + q];
             if (rc != 0) Ug[r * QR_W + q] = Us[r * QR_LD + q];
         }
+        QR_ACCOUNT(2);
         if (c.tid == 0) {
             st.ss_i = si; st.ss_its = sits; st.ss_fresh = 0;
             st.passes++;
@@ -749,6 +885,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         st.nintro += introduced;
         if (p == st.lo && st.nintro < st.ns) st.ns = st.nintro;      // window could not take more: cap this sweep
         st.nbulge = nb_after;
+        { const long long _t = QR_CLOCK(); st.cyc[1] += _t - tseg; st.cnt[1]++; }
         st.passes++;
         if (nb_after == 0) { st.phase = 0; st.shifts_ready = 0; }   // chain gone: next pass starts a new sweep
         else st.p = st.kpos[nb_after - 1];                    // next window starts at the trailing bulge
@@ -816,7 +953,8 @@ extern "C" int emu_qr(cplx* H, cplx* Z, int n, int max_passes, int* stats) {
     ZGemmProblem pr, pcm, pc, pz;
     int it = 0;
     for (; it < max_passes && !st.done; ++it) {
-        qr_pass_body(c, H, n, n, Z, n, &st, U.data(), Vgbuf.data(), Tgbuf.data(), &pr, &pcm, &pc, &pz);
+        QrBudget bud; bud.schur = QR_BUDGET_SCHUR; bud.swaps = QR_BUDGET_SWAPS; bud.restore = QR_BUDGET_RESTORE;
+        qr_pass_body(c, H, n, n, Z, n, &st, U.data(), Vgbuf.data(), Tgbuf.data(), &pr, &pcm, &pc, &pz, bud);
         emu_gemm(pr, 2); emu_gemm(pcm, 0); emu_gemm(pc, 0); emu_gemm(pz, 0);
     }
     {   // T = Z^H A0 Z (as the device path does); strictly lower part set to exact zero
@@ -869,13 +1007,13 @@ namespace {
 // ---------------------------------------------------------------- phase 2: QR passes
 __global__ void __launch_bounds__(512, 1)
 qr_pass_kernel(cplx* H, long long hstride, int ldh, int n, cplx* Z, long long zstride, int ldz, QrState* states,
-               cplx* U, cplx* Vg, cplx* Tg, ZGemmProblem* prows, ZGemmProblem* pcols_main, ZGemmProblem* pcolsz) {
+               cplx* U, cplx* Vg, cplx* Tg, ZGemmProblem* prows, ZGemmProblem* pcols_main, ZGemmProblem* pcolsz, QrBudget bud) {
     extern __shared__ __align__(16) char smem_raw[];
     const int b = blockIdx.x;
     Cta c = make_cta(b, smem_raw);
     qr_pass_body(c, H + (size_t)b * hstride, ldh, n, Z + (size_t)b * zstride, ldz, states + b,
                  U + (size_t)b * QR_W * QR_W, Vg + (size_t)b * QR_W * QR_W, Tg + (size_t)b * QR_W * QR_W,
-                 prows + b, pcols_main + b, pcolsz + 2 * b, pcolsz + 2 * b + 1);
+                 prows + b, pcols_main + b, pcolsz + 2 * b, pcolsz + 2 * b + 1, bud);
 }
 
 __global__ void qr_init_kernel(QrState* states, int n, int nb) {
@@ -905,6 +1043,12 @@ __global__ void qr_stats_kernel(const QrState* states, int nb, int* out) {
     if (b >= nb) return;
     out[4 * b + 0] = states[b].sweeps; out[4 * b + 1] = states[b].passes;
     out[4 * b + 2] = states[b].aeds; out[4 * b + 3] = states[b].done ? states[b].info : -1;
+}
+
+__global__ void qr_profile_kernel(const QrState* states, int nb, long long* out) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    for (int k = 0; k < 6; ++k) { out[12 * b + 2 * k] = states[b].cnt[k]; out[12 * b + 2 * k + 1] = states[b].cyc[k]; }
 }
 
 __global__ void qr_finish_kernel(const QrState* states, int nb, int* info) {
@@ -1014,6 +1158,13 @@ cudaError_t eig_stats(const char* wsb, int n, int nb, int* out, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// per matrix 6 x {count, SM cycles} of the QR pass segments (see QrState::cyc)
+cudaError_t eig_profile(const char* wsb, int n, int nb, long long* out, cudaStream_t st) {
+    EigWs ws = carve(const_cast<char*>(wsb), n, nb);
+    qr_profile_kernel<<<(nb + 127) / 128, 128, 0, st>>>(ws.states, nb, out);
+    return cudaGetLastError();
+}
+
 // A -> H (upper Hessenberg, in place), Zout = accumulated reflectors (A_in = Z H Z^H)
 cudaError_t hessenberg(cplx* A, int n, int nb, cplx* Zout, char* wsb, size_t ws_bytes, cudaStream_t st) {
     EigWs ws = carve(wsb, n, nb);
@@ -1034,12 +1185,26 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
 
     // ---------------- phase 2: QR passes (host enqueues, polls the pinned flag every `poll` passes)
     qr_init_kernel<<<(nb + 127) / 128, 128, 0, st>>>(ws.states, n, nb);
-    const size_t smem = qr_pass_smem_bytes(n);
+    // The pass kernel is a latency-bound chain of dependent fp64 operations.  Sharing an SM with a DMMA GEMM
+    // CTA of the side stream puts every one of them behind queued tensor instructions in the same fp64 pipe
+    // (measured: 77 us per chase pass alone, 380 us next to the GEMMs).  Asking for the whole shared memory
+    // of the SM keeps GEMM CTAs off the SMs that run a pass; they use the remaining SMs meanwhile.
+    size_t smem = qr_pass_smem_bytes(n);
+    if (gemm_get_tuning(4) && smem < 227 * 1024) smem = 227 * 1024;
     EK(cudaFuncSetAttribute(qr_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long max_passes = 40LL * n + 2000;       // generous: ~(n/NS) sweeps x (n/(W-2NS)) windows x iterations
+    QrBudget bud;
+    bud.schur = gemm_get_tuning(5) > 0 ? gemm_get_tuning(5) : QR_BUDGET_SCHUR;
+    bud.swaps = gemm_get_tuning(6) > 0 ? gemm_get_tuning(6) : QR_BUDGET_SWAPS;
+    bud.restore = gemm_get_tuning(7) > 0 ? gemm_get_tuning(7) : QR_BUDGET_RESTORE;
+    const long long max_passes = 80LL * n + 4000;       // generous: ~(n/NS) sweeps x (n/(W-2NS)) windows x iterations
     const int poll = 64;
-    const int max_tiles_rows = gemm_tiles(GEMM_TILE_64x128, QR_W, n);
-    const int max_tiles_cz = gemm_tiles(GEMM_TILE_128x64, n, QR_W);
+    // in-place window updates need one tile across the K-side dimension (zgemm.cu): rows 64x128 or 64x64,
+    // columns/Z 128x64 or 64x64; the 128-thread 64x64 tile (two CTAs per SM) is the measured best at K = 64
+    const int m3 = gemm_get_tuning(0) ? GEMM_M3 : 0;
+    const int cfg_rows = ((gemm_get_tuning(1) == GEMM_TILE_64x128) ? GEMM_TILE_64x128 : GEMM_TILE_64x64) | m3;
+    const int cfg_cz = ((gemm_get_tuning(2) == GEMM_TILE_128x64) ? GEMM_TILE_128x64 : GEMM_TILE_64x64) | m3;
+    const int max_tiles_rows = gemm_tiles(cfg_rows, QR_W, n);
+    const int max_tiles_cz = gemm_tiles(cfg_cz, n, QR_W);
     // Two streams: the main stream carries the serial chain  pass -> row-panel GEMM -> next pass ; the
     // column-panel and Z updates of a chase pass (2/3 of the flops) run on a side stream, overlapping the
     // next pass.  Window unitaries and side-stream descriptors are double-buffered; pass k+2 waits for the
@@ -1071,12 +1236,12 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
         const int buf = (int)(it & 1);
         if (it >= 2) EK(cudaStreamWaitEvent(st, ev_side[buf], 0));          // U[buf] / descriptors[buf] are free again
         qr_pass_kernel<<<nb, 512, smem, st>>>(A, ms, n, n, ws.Z, ms, n, ws.states, ws.U + buf * ustride, ws.Vg, ws.Tg,
-                                               ws.prows, ws.pcols_main, ws.pcolsz + (size_t)buf * 2 * nb);
+                                               ws.prows, ws.pcols_main, ws.pcolsz + (size_t)buf * 2 * nb, bud);
         EK(cudaEventRecord(ev_pass[buf], st));
-        EK(zgemm_grouped(GEMM_TILE_64x128, OP_H, OP_N, ws.prows, nb, max_tiles_rows, one, zero, st));
-        EK(zgemm_grouped(GEMM_TILE_128x64, OP_N, OP_N, ws.pcols_main, nb, max_tiles_cz, one, zero, st));
+        EK(zgemm_grouped(cfg_rows, OP_H, OP_N, ws.prows, nb, max_tiles_rows, one, zero, st));
+        EK(zgemm_grouped(cfg_cz, OP_N, OP_N, ws.pcols_main, nb, max_tiles_cz, one, zero, st));
         EK(cudaStreamWaitEvent(sb, ev_pass[buf], 0));
-        EK(zgemm_grouped(GEMM_TILE_128x64, OP_N, OP_N, ws.pcolsz + (size_t)buf * 2 * nb, 2 * nb, max_tiles_cz, one, zero, sb));
+        EK(zgemm_grouped(cfg_cz, OP_N, OP_N, ws.pcolsz + (size_t)buf * 2 * nb, 2 * nb, max_tiles_cz, one, zero, sb));
         EK(cudaEventRecord(ev_side[buf], sb));
         if (hf && (it % poll) == poll - 1) {
             const int slot = (int)(group & 1);

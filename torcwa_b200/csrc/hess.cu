@@ -18,7 +18,9 @@
 #include "common.cuh"
 #include "kernels.h"
 
-#define HB_NB 32
+#ifndef HB_NB
+#define HB_NB 32          // panel width (compile-time; -DHB_NB=64 builds the wide-panel variant)
+#endif
 #define HB_ROWS 32          // rows per CTA in the matvec (8 warps x 4 rows)
 
 namespace {

@@ -2,8 +2,13 @@
 #pragma once
 #include "common.cuh"
 
-#define GEMM_TILE_64x128 0
+#define GEMM_TILE_64x128 0     // 8 warps, 1 CTA/SM  (long K)
 #define GEMM_TILE_128x64 1
+#define GEMM_TILE_64x64 2      // 4 warps, 2 CTAs/SM (short K)
+#define GEMM_TILE_128x32 3     // 4 warps, 2 CTAs/SM (N <= 32)
+#define GEMM_TILE_32x128 4     // 4 warps, 2 CTAs/SM (M <= 32)
+#define GEMM_M3 8              // flag: 3-multiplication complex product
+#define GEMM_SHORT_K 128
 #define OP_N 0
 #define OP_T 1
 #define OP_H 2
@@ -14,6 +19,13 @@ namespace rcwa {
 int gemm_tiles(int tile_cfg, int M, int N);
 cudaError_t zgemm_grouped(int tile_cfg, int opa, int opb, const ZGemmProblem* probs, int nprob, int max_tiles,
                           cplx alpha, cplx beta, cudaStream_t st);
+bool gemm_cfg_supports(int tile_cfg, int opa, int opb);
+int gemm_pick_cfg(int opa, int opb, int M, int N, int K);
+void gemm_set_tuning(int key, int value);
+int gemm_get_tuning(int key);
+cudaError_t zgemm_strided_cfg(int cfg, int opa, int opb, int M, int N, int K, cplx alpha, const cplx* A, int lda, long long sa,
+                              const cplx* B, int ldb, long long sb, cplx beta, cplx* C, int ldc, long long sc,
+                              int batch, ZGemmProblem* scratch, cudaStream_t st);
 // `scratch`: device array of >= batch ZGemmProblem
 cudaError_t zgemm_strided(int opa, int opb, int M, int N, int K, cplx alpha, const cplx* A, int lda, long long sa,
                           const cplx* B, int ldb, long long sb, cplx beta, cplx* C, int ldc, long long sc,
@@ -55,6 +67,7 @@ cudaError_t hessenberg_blocked(cplx* A, int n, int nb, cplx* Z, char* ws, cudaSt
 // ---- eig.cu
 size_t eig_workspace_bytes(int n, int nb);
 cudaError_t eig_stats(const char* ws, int n, int nb, int* out, cudaStream_t st);
+cudaError_t eig_profile(const char* ws, int n, int nb, long long* out, cudaStream_t st);
 cudaError_t hessenberg(cplx* A, int n, int nb, cplx* Zout, char* ws, size_t ws_bytes, cudaStream_t st);
 cudaError_t eig(cplx* A, int n, int nb, cplx* w, cplx* V, char* ws, size_t ws_bytes, int* info, volatile int* host_flag, cudaStream_t st);
 
