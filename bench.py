@@ -26,6 +26,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# a step allocates and frees ~10 buffers of 7.6 GB each: growable segments keep the caching allocator from fragmenting
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -201,9 +203,15 @@ def bench_b200(args):
         # ---- stage split and roofline of the eigen stage (untimed extra step on rank 0)
         from torcwa_b200 import _lib
         launches, per_kernel = count_my_launches(lambda: step_resident(0))
+        torch.cuda.empty_cache()
         sl0 = chunk(0).to(device)
-        sim_stage = stage_times(case, grids_res[sl0][:min(P, 32)].contiguous(), freq_res[sl0][:min(P, 32)].contiguous(), device)
-        Ps = min(P, 32)
+        Ps = P
+        sim_stage, A_eig = stage_times(case, grids_res[sl0][:Ps].contiguous(), freq_res[sl0][:Ps].contiguous(), device)
+        torch.cuda.empty_cache()
+        mv = matvec_roofline(A_eig)
+        tz = tensor_roofline(A_eig)
+        del A_eig
+        torch.cuda.empty_cache()
         b_eig = 16.0 * (n ** 3 / 3.0 + 2.0 * n * n)                      # SURVEY.md 8d, s = 16 (fp64 internals)
         peaks = {}
         try:
@@ -216,10 +224,25 @@ def bench_b200(args):
         t_h = sim_stage["hessenberg_alone_ms"]
         achieved_h = Ps * b_eig / (t_h * 1e-3) / 1e9
         achieved_eig = Ps * b_eig / (sim_stage["eig_ms"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "hb_matvec_kernel (streaming mat-vec of the blocked Hessenberg phase of rcwa_eig; phase timed alone with CUDA events)",
-                "achieved": achieved_h, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_h / hbm_peak,
-                "traffic": None, "peak_source": peak_src,
+        traffic = None
+        try:        # dram__bytes_read + dram__bytes_write of one captured launch (ncu --set full), as a ratio to its algorithmic bytes
+            tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["hb_matvec_kernel"]
+            traffic = tr["dram_bytes_per_algorithmic_byte"] * mv["bytes_per_launch"]
+        except Exception:
+            pass
+        cupti_mv = per_kernel.get("hb_matvec")
+        roof = {"bound": "hbm", "kernel": "hb_matvec_kernel: streaming mat-vec y = A[k0+1:n, j+1:n] u_j of the blocked Hessenberg phase of rcwa_eig "
+                                          "(one launch per column; launches of %d sampled columns timed ALONE with CUDA events on the launching stream, batch %d)"
+                                          % (mv["launches"], Ps),
+                "achieved": mv["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": mv["gbs"] / hbm_peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": mv["bytes_per_launch"], "us_per_launch": mv["us_per_launch"],
+                "in_step_cupti": None if not cupti_mv else {
+                    "launches": cupti_mv[0], "us_per_launch": cupti_mv[1] / max(cupti_mv[0], 1),
+                    "achieved": P * (b_eig - 32.0 * n * n) / max(cupti_mv[1], 1e-9) / 1e3,
+                    "note": "all %d launches of one step (CUPTI durations): P * 16 n^3/3 bytes / total kernel time" % cupti_mv[0]},
                 "algorithmic_bytes_per_matrix": b_eig,
+                "hessenberg_phase_whole": {"achieved": achieved_h, "frac": achieved_h / hbm_peak, "ms_per_batch": t_h},
                 "eig_stage_whole": {"achieved": achieved_eig, "frac": achieved_eig / hbm_peak, "ms_per_batch": sim_stage["eig_ms"]}}
         cpu = cpu_baseline(args.order, args.ref_dtype) if args.cpu_baseline else None
         out = {
@@ -236,6 +259,7 @@ def bench_b200(args):
             "gpu_launches_per_step": launches,
             "clocks": clk,
             "roofline": roof,
+            "roofline_tensor": tz,
             "stage_ms_per_batch": dict(sim_stage, batch=Ps),
             "dominant_kernel_by_time": dom,
             "kernel_time_share": {k: round(v[1] / max(sum(x[1] for x in per_kernel.values()), 1e-9), 4) for k, v in
@@ -266,12 +290,14 @@ def stage_times(case, grids, freq, device):
         e.record()
         return e
     res = {}
-    for _ in range(2):
+    A = None
+    for rep in range(2):
         e = [ev()]
         E = _lib.convmat(grids, o, o, nb=P); e.append(ev())
         eta, _i = _lib.inverse(E); e.append(ev())
         Pm, Q = _lib.pq_assemble(eta, E, sim._kx, sim._ky, mu_scalar=torch.ones(P, dtype=torch.complex128, device=device))
         A = _lib.zgemm(Pm, Q); e.append(ev())
+        del E, eta, Pm
         H = A.clone(); e.append(ev())
         _lib.hessenberg_(H); e.append(ev())
         del H
@@ -280,7 +306,8 @@ def stage_times(case, grids, freq, device):
         om = sim._omega64.expand(P).contiguous()
         th = torch.full((P,), 300.0, dtype=torch.float64, device=device)
         S11, S21, _i = _lib.layer_smatrix(Wv, kz, Q, sim._Vf_inv, om, th); e.append(ev())
-        _lib.redheffer_bdleft(sim._Sin, [S11, S21, S21, S11]); e.append(ev())
+        del Wv, Q
+        S, _i = _lib.redheffer_bdleft(sim._Sin, [S11, S21, S21, S11]); e.append(ev())
         torch.cuda.synchronize()
         names = ["convmat_ms", "inv_eps_ms", "pq_and_product_ms", "_clone", "hessenberg_alone_ms", "eig_ms", "layer_smatrix_ms", "redheffer_ms"]
         res = {names[i]: e[i].elapsed_time(e[i + 1]) for i in range(len(names)) if not names[i].startswith("_")}
@@ -288,7 +315,63 @@ def stage_times(case, grids, freq, device):
         res["qr_sweeps_per_matrix"] = float(st[:, 0].mean())
         res["qr_passes_max"] = int(st[:, 1].max())
         res["eig_info_max"] = int(info.abs().max())
-    return res
+        del S, S11, S21, lam, kz
+        if rep == 0:
+            del A
+    pr = _lib.last_eig_profile.cpu().numpy().astype(float)
+    seg = ["sweep_start", "chase_window", "small_block_slice", "aed_schur_slice", "aed_scan_slice", "aed_finish"]
+    res["qr_pass_segments_mean_per_matrix"] = {seg[k]: {"launches": float(pr[:, k, 0].mean()), "sm_cycles": float(pr[:, k, 1].mean())} for k in range(6)}
+    return res, A      # A: scratch contents after rcwa_eig (only its size matters to the roofline probes)
+
+
+def matvec_roofline(A):
+    """Kernel-only timing of the HBM-bound kernel: launches of hb_matvec_kernel for sampled columns, alone on the stream,
+    CUDA events around them.  Algorithmic bytes of a launch = 16 (n-k0-1)(n-j-1) nb (what the kernel reads once)."""
+    from torcwa_b200 import _lib
+    nb, n = A.shape[0], A.shape[1]
+    ws = _lib.eig_workspace(n, nb, A.device)
+    ws.zero_()
+    hb = _lib.load().rcwa_hessenberg_panel_width()
+    cols = list(range(0, n - 2, 61))
+    for j in cols[:2]:
+        _lib.matvec_probe(A, ws, j)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for j in cols:
+        _lib.matvec_probe(A, ws, j)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    byts = sum(16.0 * (n - (j // hb) * hb - 1) * (n - j - 1) * nb for j in cols)
+    return {"gbs": byts / (ms * 1e-3) / 1e9, "launches": len(cols), "bytes_per_launch": byts / len(cols), "us_per_launch": 1e3 * ms / len(cols)}
+
+
+def tensor_roofline(A):
+    """fp64 tensor pipe: one batched n x n x n complex product on our DMMA kernel and on cuBLAS (torch.matmul), CUDA events.
+    MEASURED_PEAKS.json has no fp64 figure; the denominator is the nominal dense fp64 tensor peak of B200 (40 TFLOP/s),
+    with cuBLAS zgemm measured beside it."""
+    from torcwa_b200 import _lib
+    nb = min(A.shape[0], 8)
+    n = A.shape[1]
+    X, Y = A[:nb].contiguous(), A[nb:2 * nb].contiguous() if A.shape[0] >= 2 * nb else A[:nb].clone()
+    out = torch.empty_like(X)
+
+    def t(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    ms = t(lambda: _lib.zgemm(X, Y, out=out))
+    ms_c = t(lambda: torch.matmul(X, Y))
+    fl = 8.0 * n ** 3 * nb
+    return {"bound": "tensor", "kernel": "zgemm_grouped_kernel<32,128,+3M> (batched %d x n^3 complex product, n=%d; fp64 DMMA mma.sync, tcgen05 has no f64 kind)" % (nb, n),
+            "achieved": fl / ms / 1e9, "peak": 40.0, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / 40.0,
+            "peak_source": "nominal B200 dense fp64 tensor (no fp64 entry in MEASURED_PEAKS.json)", "cublas_zgemm_same_shape": fl / ms_c / 1e9,
+            "note": "flops counted as 8 n^3 per complex product; the 3-multiplication kernel issues 6 n^3"}
 
 
 # ------------------------------------------------------------------------------------------- CPU legs
@@ -367,7 +450,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--points", type=int, default=96, help="wavelengths per step per GPU (peak footprint ~0.7 GB each)")
+    ap.add_argument("--points", type=int, default=128, help="wavelengths per step per GPU (peak footprint ~0.7 GB each)")
     ap.add_argument("--order", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)

@@ -67,7 +67,9 @@ int rcwa_zgemm_batched(int opa, int opb, int M, int N, int K, double alpha_re, d
  *   Tiles 2-4 and m3 exist for the op pairs (N,N), (N,H), (H,N) only.
  * rcwa_set_tuning(key, value): process-wide knobs of the automatic choice -- key 0: use m3 (default 1);
  *   1 / 2: tile of the QR row / column updates; 3: use the 128-thread tiles (default 1); 4: the QR pass
- *   kernel claims a whole SM per matrix so that no GEMM CTA shares its fp64 pipe (default 1).  Call before
+ *   kernel claims a whole SM per matrix (default 0); 5-7: count limits of the serial QR slices (Schur
+ *   rotations, AED swaps, AED restore steps); 8: time budget of a serial QR slice in us (default 90);
+ *   9: number of independently pipelined matrix groups of the QR phase (default 2).  Call before
  *   enqueuing work; the numerical contract does not depend on them. */
 int rcwa_zgemm_batched_cfg(int cfg, int opa, int opb, int M, int N, int K, double alpha_re, double alpha_im,
                            const void* A, int lda, long long stride_a, const void* B, int ldb, long long stride_b,
@@ -110,14 +112,20 @@ int rcwa_eig(void* A, int n, int nb, void* w, void* V, void* ws, size_t ws_bytes
 /* Diagnostics of the last rcwa_eig that used workspace `ws`: out[4*b..] = {QR sweeps, window passes,
  * AED windows, info} of matrix b (device int32 [nb,4]). */
 int rcwa_eig_stats(const void* ws, int n, int nb, int* out, void* stream);
-/* Profile of the QR phase of the last rcwa_eig on `ws`: out = device int64 [nb,6,2] = {launch count, SM cycles}
- * per pass segment (0 sweep start: deflation scan + shifts, 1 bulge-chain window, 2 small-block slice,
+/* Profile of the QR phase of the last rcwa_eig on `ws`: out = device int64 [nb,6,3] = {launch count, SM cycles,
+ * longest single segment in cycles} per pass segment (0 sweep start: deflation scan + shifts, 1 bulge-chain window, 2 small-block slice,
  * 3 AED Schur slice, 4 AED deflation-scan slice, 5 AED finish). */
 int rcwa_eig_profile(const void* ws, int n, int nb, long long* out, void* stream);
 /* First phase of rcwa_eig on its own (profiling / building block): A[b] -> H[b] upper Hessenberg in
  * place, Z[b] unitary with A_in = Z H Z^H.  Workspace as for rcwa_eig.  This is the HBM-bound
  * streaming kernel of the eigen stage (one fused pass over [A; Z] per column). */
 int rcwa_hessenberg(void* A, int n, int nb, void* Z, void* ws, size_t ws_bytes, void* stream);
+/* Profiling entry: ONE launch of the streaming mat-vec kernel of rcwa_hessenberg for column j (0 <= j <= n-3)
+ * on A[nb,n,n] (read only; the vector it multiplies with is whatever the workspace holds).  It reads the
+ * (n - k0 - 1) x (n - j - 1) trailing block of every matrix once, k0 = j rounded down to the panel width
+ * (rcwa_hessenberg_panel_width()): the algorithmic bytes of that launch are 16 (n-k0-1)(n-j-1) nb. */
+int rcwa_hessenberg_matvec_probe(const void* A, int n, int nb, int j, void* ws, size_t ws_bytes, void* stream);
+int rcwa_hessenberg_panel_width(void);
 /* kz = sqrt(lambda), negated where Im < 0 (rcwa.py:1240-1241). total = nb*n elements. */
 int rcwa_kz_branch(const void* lam, void* kz, long long total, void* stream);
 

@@ -77,3 +77,19 @@ def test_warnings_match_reference_messages(cpu_double):
     o = torch.tensor([[9, 0]])
     sim.S_parameters(o)
     assert o.tolist() == [[1, 0]]           # out-of-range orders are clamped in place (rcwa.py:1115-1122)
+
+
+def test_finished_simulation_is_freed_by_refcount(cpu_double):
+    """A batched sweep allocates tens of GB per simulation object; it must die with its last reference, not
+    whenever the cyclic garbage collector runs (a sim <-> sim.Sin cycle once kept two steps' S-matrices alive)."""
+    import gc
+    import weakref
+    gc.disable()
+    try:
+        sim = C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, **kw), C.CASES["stack_o3"], torch.complex128)
+        _ = sim.Sin[0], sim.Sout[0]
+        ref = weakref.ref(sim)
+        del sim
+        assert ref() is None
+    finally:
+        gc.enable()

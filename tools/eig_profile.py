@@ -57,11 +57,11 @@ for k, (c, t) in rows[:24]:
 q = np.array(qr)
 if len(q):
     print("  qr_pass durations us: " + ", ".join(f"p{p}={np.percentile(q, p):.0f}" for p in (5, 25, 50, 75, 95, 99)) + f", sum {q.sum()/1e3:.0f} ms, n={len(q)}")
-pr = _lib.last_eig_profile.cpu().numpy().astype(float)      # [nb,6,2]
+pr = _lib.last_eig_profile.cpu().numpy().astype(float)      # [nb,6,3]
 names = ["sweep start (scan+shifts)", "chase window", "small-block slice", "AED Schur slice", "AED scan slice", "AED finish"]
 print("  QR pass segments (mean over matrices): count, total ms @1.9GHz, mean us")
 for k in range(6):
     cnt, cyc = pr[:, k, 0].mean(), pr[:, k, 1].mean()
-    print(f"    {names[k]:28s} n={cnt:8.1f}  total {cyc/1.9e6:8.1f} ms  mean {cyc/max(cnt,1)/1.9e3:8.1f} us   (max-matrix total {pr[:, k, 1].max()/1.9e6:.1f} ms)")
+    print(f"    {names[k]:28s} n={cnt:8.1f}  total {cyc/1.9e6:8.1f} ms  mean {cyc/max(cnt,1)/1.9e3:8.1f} us   (max-matrix total {pr[:, k, 1].max()/1.9e6:.1f} ms; longest segment {pr[:, k, 2].max()/1.9e3:.0f} us, mean of per-matrix longest {pr[:, k, 2].mean()/1.9e3:.0f} us)")
 if a.out:
     json.dump({"wall_ms": tot, "kernels": {k: v for k, v in rows}, "qr_pass_us_percentiles": {str(p): float(np.percentile(q, p)) for p in (5, 25, 50, 75, 95, 99)} if len(q) else None}, open(a.out, "w"), indent=1)

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("RCWA_B200_LIB", "librcwa_b200.so"
 EXPORTS = [
     "rcwa_b200_abi_version", "rcwa_gemm_scratch_bytes", "rcwa_convmat_workspace_bytes", "rcwa_convmat",
     "rcwa_zgemm_batched", "rcwa_zgemm_batched_cfg", "rcwa_set_tuning", "rcwa_get_tuning", "rcwa_lu_tinv_bytes", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
-    "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_eig_stats", "rcwa_eig_profile", "rcwa_hessenberg", "rcwa_kz_branch", "rcwa_layer_smatrix_workspace_bytes",
+    "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_eig_stats", "rcwa_eig_profile", "rcwa_hessenberg", "rcwa_hessenberg_matvec_probe", "rcwa_hessenberg_panel_width", "rcwa_kz_branch", "rcwa_layer_smatrix_workspace_bytes",
     "rcwa_layer_smatrix", "rcwa_redheffer_workspace_bytes", "rcwa_redheffer", "rcwa_redheffer_bdleft", "rcwa_blockdiag_dense",
 ]
 
@@ -37,6 +37,8 @@ _SIGS = {
     "rcwa_eig_stats": (_i, [_vp, _i, _i, _vp, _vp]),
     "rcwa_eig_profile": (_i, [_vp, _i, _i, _vp, _vp]),
     "rcwa_hessenberg": (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "rcwa_hessenberg_matvec_probe": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp]),
+    "rcwa_hessenberg_panel_width": (_i, []),
     "rcwa_kz_branch": (_i, [_vp, _vp, _ll, _vp]),
     "rcwa_layer_smatrix_workspace_bytes": (_sz, [_i, _i]),
     "rcwa_layer_smatrix": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
@@ -219,7 +221,7 @@ def eig(A):
     stats = torch.empty((nb, 4), dtype=torch.int32, device=A.device)
     _check(lib.rcwa_eig_stats(_ptr(ws), n, nb, _ptr(stats), _stream()), "rcwa_eig_stats")
     last_eig_stats = stats
-    prof = torch.empty((nb, 6, 2), dtype=torch.int64, device=A.device)
+    prof = torch.empty((nb, 6, 3), dtype=torch.int64, device=A.device)
     _check(lib.rcwa_eig_profile(_ptr(ws), n, nb, _ptr(prof), _stream()), "rcwa_eig_profile")
     global last_eig_profile
     last_eig_profile = prof
@@ -227,7 +229,7 @@ def eig(A):
 
 
 last_eig_stats = None
-last_eig_profile = None      # [nb,6,2] int64: {launches, SM cycles} per QR pass segment (rcwa_eig_profile)
+last_eig_profile = None      # [nb,6,3] int64: {launches, SM cycles, longest segment} per QR pass segment (rcwa_eig_profile)
 
 
 def hessenberg_(A):
@@ -240,6 +242,18 @@ def hessenberg_(A):
     ws = _ws(nbytes, A.device)
     _check(lib.rcwa_hessenberg(_ptr(A), n, nb, _ptr(Z), _ptr(ws), nbytes, _stream()), "rcwa_hessenberg")
     return Z
+
+
+def matvec_probe(A, ws, j):
+    """One launch of the Hessenberg streaming mat-vec for column j (profiling; A is only read)."""
+    lib = load()
+    nb, n = A.shape[0], A.shape[1]
+    _check(lib.rcwa_hessenberg_matvec_probe(_ptr(_c128(A, "A")), n, nb, int(j), _ptr(ws), ws.numel(), _stream()), "rcwa_hessenberg_matvec_probe")
+
+
+def eig_workspace(n, nb, device):
+    lib = load()
+    return _ws(lib.rcwa_eig_workspace_bytes(n, nb), device)
 
 
 def kz_branch(lam):

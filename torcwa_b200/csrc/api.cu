@@ -67,7 +67,7 @@ int rcwa_zgemm_batched_cfg(int cfg, int opa, int opb, int M, int N, int K, doubl
 }
 
 int rcwa_set_tuning(int key, int value) {
-    if (key < 0 || key > 7) return -1;
+    if (key < 0 || key > 15) return -1;
     gemm_set_tuning(key, value);
     return 0;
 }
@@ -157,6 +157,16 @@ int rcwa_hessenberg(void* A, int n, int nb, void* Z, void* ws, size_t ws_bytes, 
     if (!ws || ws_bytes < eig_workspace_bytes(n, nb)) return -5;
     return cu(hessenberg((cplx*)A, n, nb, (cplx*)Z, (char*)ws, ws_bytes, S(stream)));
 }
+
+int rcwa_hessenberg_matvec_probe(const void* A, int n, int nb, int j, void* ws, size_t ws_bytes, void* stream) {
+    if (!A) return -1;
+    if (n < 3) return -2;
+    if (nb <= 0) return -3;
+    if (j < 0 || j > n - 3) return -4;
+    if (!ws || ws_bytes < eig_workspace_bytes(n, nb)) return -5;
+    return cu(eig_matvec_probe((const cplx*)A, n, nb, j, (char*)ws, ws_bytes, S(stream)));
+}
+int rcwa_hessenberg_panel_width(void) { return hessenberg_panel_width(); }
 
 int rcwa_kz_branch(const void* lam, void* kz, long long total, void* stream) {
     if (!lam) return -1;

@@ -42,10 +42,24 @@ struct QrBudget {
     int schur;      // rotations per launch while Schur-factoring an AED window or a small block
     int swaps;      // eigenvalue swaps per launch during the AED deflation scan
     int restore;    // Householder steps per launch while folding the AED spike back to Hessenberg form
+    long long cycles;   // SM-clock budget of a serial slice (0: count budgets only); the counts above are upper bounds
 };
-#define QR_BUDGET_SCHUR 160
-#define QR_BUDGET_SWAPS 100
-#define QR_BUDGET_RESTORE 12
+#define QR_BUDGET_SCHUR 400
+#define QR_BUDGET_SWAPS 300
+#define QR_BUDGET_RESTORE 32
+#define QR_BUDGET_US 90
+
+// Deadline test of a time slice, uniform over the cooperating warp (lane 0 reads the clock).
+DEV bool slice_expired(const Cta& c, long long deadline) {
+#ifdef RCWA_EMU
+    (void)c; (void)deadline; return false;
+#else
+    if (deadline == 0 || !c.warp_only) return false;
+    int e = (clock64() > deadline) ? 1 : 0;
+    e = __shfl_sync(0xffffffffu, e, 0);
+    return e != 0;
+#endif
+}
 #define QR_MAXSTALL 40     // sweeps without deflation before giving up on a matrix
 #define TV_NB 32           // eigenvector back-substitution block
 
@@ -72,6 +86,7 @@ struct QrState {
     int shifts_ready;    // phase 1 may start with st.shifts as they are (supplied by AED)
     int aeds, aed_deflated;   // statistics
     int pad0, pad1;
+    long long cyc_max[6]; // profiling: longest single segment
     long long cyc[6];    // profiling: SM cycles spent per pass segment (0 sweep start: scan + shifts, 1 chase, 2 small-block
     int cnt[6];          //   slice, 3 AED Schur slice, 4 AED scan slice, 5 AED finish: scan + restore + write-back) and counts
     int kpos[QR_NS];     // column of each bulge (leading first): bulge element is H[k+2][k]
@@ -252,7 +267,7 @@ DEV int schur_find_split(const Cta& c, const cplx* Hs, int i) {
 //           the running element in a register -- no barriers at all.
 // sig is subtracted from / added back to the diagonal of the active block only (the rotations are the
 // identity outside it, so this is the same similarity as the implicit step).
-DEV int small_schur_slice(const Cta& c, cplx* Hs, cplx* Us, int m, int* pi, int* pits, int budget, double* rot_c, cplx* rot_s) {
+DEV int small_schur_slice(const Cta& c, cplx* Hs, cplx* Us, int m, int* pi, int* pits, int budget, long long deadline, double* rot_c, cplx* rot_s) {
     int i = *pi, its = *pits, used = 0;
     while (i >= 1) {
         const int l = schur_find_split(c, Hs, i);
@@ -261,7 +276,7 @@ DEV int small_schur_slice(const Cta& c, cplx* Hs, cplx* Us, int m, int* pi, int*
         GROUP_SYNC(c);
         if (l >= i) { --i; its = 0; continue; }
         if (its > 60) { *pi = i; *pits = its; return -1; }
-        if (used + (i - l) > budget && used > 0) break;       // out of time: resume at the next launch
+        if (used > 0 && (used + (i - l) > budget || slice_expired(c, deadline))) break;       // out of time: resume at the next launch
         // ---- shift
         cplx sig;
         if (its == 10 || its == 30) sig = cadd(Hs[l * QR_LD + l], C(0.75 * cabs1(Hs[(l + 1) * QR_LD + l]), 0.0));
@@ -357,7 +372,7 @@ HD size_t qr_pass_smem_bytes(int n) {
 // then occupy T[0:ns, 0:ns].
 // Resumable: at most `budget` swaps per call; progress (ns, ilst, knt, kcur) lives in `prog[4]`.
 // Returns 1 when the scan is complete (prog[0] = ns), 0 if it must be continued.
-DEV int aed_deflation_scan(const Cta& c, cplx* T, cplx* V, int nw, cplx s, int* prog, int budget) {
+DEV int aed_deflation_scan(const Cta& c, cplx* T, cplx* V, int nw, cplx s, int* prog, int budget, long long deadline) {
     const double smlnum = RCWA_SAFMIN * (1.0 / RCWA_EPS);
     int ns = prog[0], ilst = prog[1], knt = prog[2], kcur = prog[3], used = 0;
     while (knt < nw) {
@@ -368,7 +383,7 @@ DEV int aed_deflation_scan(const Cta& c, cplx* T, cplx* V, int nw, cplx s, int* 
             kcur = ns - 2;            // undeflatable: move position ns-1 up to ilst by adjacent swaps
         }
         while (kcur >= ilst) {
-            if (used >= budget) { GROUP_SYNC(c); prog[0] = ns; prog[1] = ilst; prog[2] = knt; prog[3] = kcur; return 0; }
+            if (used >= budget || (used > 0 && (used & 7) == 0 && slice_expired(c, deadline))) { GROUP_SYNC(c); prog[0] = ns; prog[1] = ilst; prog[2] = knt; prog[3] = kcur; return 0; }
             const int k = kcur;
             const cplx t11 = T[k * QR_LD + k], t22 = T[(k + 1) * QR_LD + k + 1];
             double cs; cplx sn, r;
@@ -461,7 +476,7 @@ DEV void small_hh_right(const Cta& c, cplx* M, const cplx* u, int q0, int q1, in
 // zlarfg on the spike, zlarf x3, zgehrd, zunmhr -- done here with Hermitian reflectors).
 // Resumable: *pj = -1 on entry of the first slice (the spike reflector), then the column index of the
 // reduction; at most `budget` Householder steps per call.  Returns 1 when finished.
-DEV int aed_restore_hessenberg(const Cta& c, cplx* T, cplx* V, int nw, int ns, cplx* u, int* pj, int budget) {
+DEV int aed_restore_hessenberg(const Cta& c, cplx* T, cplx* V, int nw, int ns, cplx* u, int* pj, int budget, long long deadline) {
     if (ns <= 1) return 1;
     cplx beta;
     int j = *pj, used = 0;
@@ -479,7 +494,7 @@ DEV int aed_restore_hessenberg(const Cta& c, cplx* T, cplx* V, int nw, int ns, c
     }
     // Hessenberg reduction of T[0:ns,0:ns]; reflectors act on indices >= 1, so the spike stays on e_0
     for (; j + 2 < ns; ++j) {
-        if (used >= budget) { *pj = j; return 0; }
+        if (used >= budget || (used > 0 && slice_expired(c, deadline))) { *pj = j; return 0; }
         for (int r = j + 1 + c.tid; r < ns; r += c.nthreads) u[r] = T[r * QR_LD + j];
         GROUP_SYNC(c);
         small_reflector(c, u, j + 1, ns, &beta);
@@ -521,7 +536,7 @@ DEV void emit_window_gemms(cplx* H, int ldh, int n, cplx* Zm, int ldz, cplx* Ug,
 #else
 #define QR_CLOCK() clock64()
 #endif
-#define QR_ACCOUNT(seg) do { if (c.tid == 0) { const long long _t = QR_CLOCK(); st.cyc[seg] += _t - tseg; st.cnt[seg]++; tseg = _t; } } while (0)
+#define QR_ACCOUNT(seg) do { if (c.tid == 0) { const long long _t = QR_CLOCK(); st.cyc[seg] += _t - tseg; st.cnt[seg]++; if (_t - tseg > st.cyc_max[seg]) st.cyc_max[seg] = _t - tseg; tseg = _t; } } while (0)
 
 DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, QrState* stg,
                       cplx* Ug, cplx* Vg, cplx* Tg, ZGemmProblem* prob_rows, ZGemmProblem* prob_cols_main,
@@ -543,6 +558,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
     CTA_SYNC();
     if (st.done) return;
     long long tseg = QR_CLOCK();
+    const long long deadline = (bud.cycles > 0) ? tseg + bud.cycles : 0;
     const bool ran0 = (st.phase == 0);
 
     if (st.phase == 0) {
@@ -630,7 +646,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         if (st.aed_stage == 0) {
             if (c.tid < w1.nthreads) {
                 int si = st.ss_i, sits = st.ss_its;
-                const int rc1 = small_schur_slice(w1, Hs, Us, nw, &si, &sits, bud.schur, sc->rot_c, sc->rot_s);
+                const int rc1 = small_schur_slice(w1, Hs, Us, nw, &si, &sits, bud.schur, deadline, sc->rot_c, sc->rot_s);
                 if (c.tid == 0) { sc->ss_rc = rc1; sc->ss_i = si; sc->ss_its = sits; }
             }
             CTA_SYNC();
@@ -659,7 +675,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         if (st.aed_stage == 1) {
             if (c.tid < w1.nthreads) {
                 int prog[4] = {st.aed_prog[0], st.aed_prog[1], st.aed_prog[2], st.aed_prog[3]};
-                const int done1 = aed_deflation_scan(w1, Hs, Us, nw, spike, prog, bud.swaps);
+                const int done1 = aed_deflation_scan(w1, Hs, Us, nw, spike, prog, bud.swaps, deadline);
                 if (c.tid == 0) { sc->ss_rc = done1; sc->aed_ns = prog[0]; sc->ss_i = prog[1]; sc->ss_its = prog[2]; sc->nslots = prog[3]; }
             }
             CTA_SYNC();
@@ -687,7 +703,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         } else {
             if (c.tid < w1.nthreads) {
                 int rj = st.aed_prog[1];
-                const int done2 = aed_restore_hessenberg(w1, Hs, Us, nw, st.aed_prog[0], sc->hv, &rj, bud.restore);
+                const int done2 = aed_restore_hessenberg(w1, Hs, Us, nw, st.aed_prog[0], sc->hv, &rj, bud.restore, deadline);
                 if (c.tid == 0) { sc->ss_rc = done2; sc->ss_i = rj; sc->aed_ns = st.aed_prog[0]; }
             }
             CTA_SYNC();
@@ -747,7 +763,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         Cta w1 = c; w1.warp_only = 1; w1.nthreads = (c.nthreads < 32) ? c.nthreads : 32;
         if (c.tid < w1.nthreads) {
             int si1 = st.ss_i, sits1 = st.ss_its;
-            const int rc1 = small_schur_slice(w1, Hs, Us, m2, &si1, &sits1, bud.schur, sc->rot_c, sc->rot_s);
+            const int rc1 = small_schur_slice(w1, Hs, Us, m2, &si1, &sits1, bud.schur, deadline, sc->rot_c, sc->rot_s);
             if (c.tid == 0) { sc->ss_rc = rc1; sc->ss_i = si1; sc->ss_its = sits1; }
         }
         CTA_SYNC();
@@ -885,7 +901,7 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         st.nintro += introduced;
         if (p == st.lo && st.nintro < st.ns) st.ns = st.nintro;      // window could not take more: cap this sweep
         st.nbulge = nb_after;
-        { const long long _t = QR_CLOCK(); st.cyc[1] += _t - tseg; st.cnt[1]++; }
+        { const long long _t = QR_CLOCK(); st.cyc[1] += _t - tseg; st.cnt[1]++; if (_t - tseg > st.cyc_max[1]) st.cyc_max[1] = _t - tseg; }
         st.passes++;
         if (nb_after == 0) { st.phase = 0; st.shifts_ready = 0; }   // chain gone: next pass starts a new sweep
         else st.p = st.kpos[nb_after - 1];                    // next window starts at the trailing bulge
@@ -953,7 +969,7 @@ extern "C" int emu_qr(cplx* H, cplx* Z, int n, int max_passes, int* stats) {
     ZGemmProblem pr, pcm, pc, pz;
     int it = 0;
     for (; it < max_passes && !st.done; ++it) {
-        QrBudget bud; bud.schur = QR_BUDGET_SCHUR; bud.swaps = QR_BUDGET_SWAPS; bud.restore = QR_BUDGET_RESTORE;
+        QrBudget bud; bud.schur = 160; bud.swaps = 100; bud.restore = 12; bud.cycles = 0;     // count budgets exercise the slicing on the CPU
         qr_pass_body(c, H, n, n, Z, n, &st, U.data(), Vgbuf.data(), Tgbuf.data(), &pr, &pcm, &pc, &pz, bud);
         emu_gemm(pr, 2); emu_gemm(pcm, 0); emu_gemm(pc, 0); emu_gemm(pz, 0);
     }
@@ -1048,7 +1064,7 @@ __global__ void qr_stats_kernel(const QrState* states, int nb, int* out) {
 __global__ void qr_profile_kernel(const QrState* states, int nb, long long* out) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
-    for (int k = 0; k < 6; ++k) { out[12 * b + 2 * k] = states[b].cnt[k]; out[12 * b + 2 * k + 1] = states[b].cyc[k]; }
+    for (int k = 0; k < 6; ++k) { out[18 * b + 3 * k] = states[b].cnt[k]; out[18 * b + 3 * k + 1] = states[b].cyc[k]; out[18 * b + 3 * k + 2] = states[b].cyc_max[k]; }
 }
 
 __global__ void qr_finish_kernel(const QrState* states, int nb, int* info) {
@@ -1165,6 +1181,12 @@ cudaError_t eig_profile(const char* wsb, int n, int nb, long long* out, cudaStre
     return cudaGetLastError();
 }
 
+cudaError_t eig_matvec_probe(const cplx* A, int n, int nb, int j, char* wsb, size_t ws_bytes, cudaStream_t st) {
+    EigWs ws = carve(wsb, n, nb);
+    if (ws_bytes < ws.total) return cudaErrorInvalidValue;
+    return rcwa::hessenberg_matvec_probe(A, n, nb, j, ws.hess, st);
+}
+
 // A -> H (upper Hessenberg, in place), Zout = accumulated reflectors (A_in = Z H Z^H)
 cudaError_t hessenberg(cplx* A, int n, int nb, cplx* Zout, char* wsb, size_t ws_bytes, cudaStream_t st) {
     EigWs ws = carve(wsb, n, nb);
@@ -1185,10 +1207,9 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
 
     // ---------------- phase 2: QR passes (host enqueues, polls the pinned flag every `poll` passes)
     qr_init_kernel<<<(nb + 127) / 128, 128, 0, st>>>(ws.states, n, nb);
-    // The pass kernel is a latency-bound chain of dependent fp64 operations.  Sharing an SM with a DMMA GEMM
-    // CTA of the side stream puts every one of them behind queued tensor instructions in the same fp64 pipe
-    // (measured: 77 us per chase pass alone, 380 us next to the GEMMs).  Asking for the whole shared memory
-    // of the SM keeps GEMM CTAs off the SMs that run a pass; they use the remaining SMs meanwhile.
+    // Optional (tuning key 4): let every pass CTA claim the whole shared memory of its SM so that no GEMM CTA
+    // becomes co-resident.  Measured on B200 (profiles/): no difference -- the pass is bound by its own
+    // dependent fp64 chain, not by sharing the fp64 pipe with DMMA warps -- so it is off by default.
     size_t smem = qr_pass_smem_bytes(n);
     if (gemm_get_tuning(4) && smem < 227 * 1024) smem = 227 * 1024;
     EK(cudaFuncSetAttribute(qr_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1196,6 +1217,13 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
     bud.schur = gemm_get_tuning(5) > 0 ? gemm_get_tuning(5) : QR_BUDGET_SCHUR;
     bud.swaps = gemm_get_tuning(6) > 0 ? gemm_get_tuning(6) : QR_BUDGET_SWAPS;
     bud.restore = gemm_get_tuning(7) > 0 ? gemm_get_tuning(7) : QR_BUDGET_RESTORE;
+    {
+        int dev = 0, khz = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+        const int us = gemm_get_tuning(8) != 0 ? gemm_get_tuning(8) : QR_BUDGET_US;
+        bud.cycles = (us > 0) ? (long long)us * (khz > 0 ? khz : 1900000) / 1000 : 0;         // us < 0: count budgets only
+    }
     const long long max_passes = 80LL * n + 4000;       // generous: ~(n/NS) sweeps x (n/(W-2NS)) windows x iterations
     const int poll = 64;
     // in-place window updates need one tile across the K-side dimension (zgemm.cu): rows 64x128 or 64x64,
@@ -1214,59 +1242,86 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
     // HIGH-priority stream forked from the caller's stream; the bulk column/Z GEMMs run on a low-priority side
     // stream, so that a pass kernel's CTAs are dispatched as soon as SMs free up instead of queueing behind
     // thousands of GEMM tiles.  Both are joined back into the caller's stream before the eigenvector phase.
+    // The batch is split into G groups with their own stream pairs: the chain of one group (pass -> row GEMM ->
+    // next pass) leaves the tensor pipes idle while its pass kernel runs and most SMs idle while its row GEMM
+    // runs; the other groups' chains fill those gaps.
+    int G = gemm_get_tuning(9) > 0 ? gemm_get_tuning(9) : 2;
+    if (G > 4) G = 4;
+    while (G > 1 && nb < 8 * G) --G;
     int prio_lo = 0, prio_hi = 0;
     EK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    cudaStream_t user_st = st, sa = nullptr, sb = nullptr;
-    EK(cudaStreamCreateWithPriority(&sa, cudaStreamNonBlocking, prio_hi));
-    EK(cudaStreamCreateWithPriority(&sb, cudaStreamNonBlocking, prio_lo));
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t user_st = st, sa[4] = {nullptr, nullptr, nullptr, nullptr}, sb[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[4], ev_pass[4][2], ev_side[4][2], ev[4][2];
+    int gb0[5];
+    for (int g = 0; g <= G; ++g) gb0[g] = (int)((long long)nb * g / G);
     EK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    EK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     EK(cudaEventRecord(ev_fork, user_st));
-    EK(cudaStreamWaitEvent(sa, ev_fork, 0));
-    st = sa;
-    cudaEvent_t ev_pass[2], ev_side[2], ev[2] = {nullptr, nullptr};
-    for (int q = 0; q < 2; ++q) { EK(cudaEventCreateWithFlags(&ev_pass[q], cudaEventDisableTiming)); EK(cudaEventCreateWithFlags(&ev_side[q], cudaEventDisableTiming)); }
     int* hf = const_cast<int*>(host_flag);
-    if (hf) { EK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming)); EK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming)); hf[0] = hf[1] = nb; }
+    for (int g = 0; g < G; ++g) {
+        EK(cudaStreamCreateWithPriority(&sa[g], cudaStreamNonBlocking, prio_hi));
+        EK(cudaStreamCreateWithPriority(&sb[g], cudaStreamNonBlocking, prio_lo));
+        EK(cudaStreamWaitEvent(sa[g], ev_fork, 0));
+        EK(cudaEventCreateWithFlags(&ev_join[g], cudaEventDisableTiming));
+        for (int q = 0; q < 2; ++q) {
+            EK(cudaEventCreateWithFlags(&ev_pass[g][q], cudaEventDisableTiming));
+            EK(cudaEventCreateWithFlags(&ev_side[g][q], cudaEventDisableTiming));
+            EK(cudaEventCreateWithFlags(&ev[g][q], cudaEventDisableTiming));
+            if (hf) hf[g * 2 + q] = gb0[g + 1] - gb0[g];
+        }
+    }
     long long group = 0;
-    bool finished = false;
+    bool fin[4] = {false, false, false, false};
+    int nfin = 0;
     const size_t ustride = (size_t)QR_W * QR_W * nb;
-    for (long long it = 0; it < max_passes && !finished; ++it) {
+    const size_t w2 = (size_t)QR_W * QR_W;
+    for (long long it = 0; it < max_passes && nfin < G; ++it) {
         const int buf = (int)(it & 1);
-        if (it >= 2) EK(cudaStreamWaitEvent(st, ev_side[buf], 0));          // U[buf] / descriptors[buf] are free again
-        qr_pass_kernel<<<nb, 512, smem, st>>>(A, ms, n, n, ws.Z, ms, n, ws.states, ws.U + buf * ustride, ws.Vg, ws.Tg,
-                                               ws.prows, ws.pcols_main, ws.pcolsz + (size_t)buf * 2 * nb, bud);
-        EK(cudaEventRecord(ev_pass[buf], st));
-        EK(zgemm_grouped(cfg_rows, OP_H, OP_N, ws.prows, nb, max_tiles_rows, one, zero, st));
-        EK(zgemm_grouped(cfg_cz, OP_N, OP_N, ws.pcols_main, nb, max_tiles_cz, one, zero, st));
-        EK(cudaStreamWaitEvent(sb, ev_pass[buf], 0));
-        EK(zgemm_grouped(cfg_cz, OP_N, OP_N, ws.pcolsz + (size_t)buf * 2 * nb, 2 * nb, max_tiles_cz, one, zero, sb));
-        EK(cudaEventRecord(ev_side[buf], sb));
+        for (int g = 0; g < G; ++g) {
+            if (fin[g]) continue;
+            const int b0 = gb0[g], nbg = gb0[g + 1] - gb0[g];
+            cudaStream_t sm = sa[g], ss = sb[g];
+            ZGemmProblem* pcz = ws.pcolsz + (size_t)buf * 2 * nb + 2 * (size_t)b0;
+            if (it >= 2) EK(cudaStreamWaitEvent(sm, ev_side[g][buf], 0));          // U[buf] / descriptors[buf] are free again
+            qr_pass_kernel<<<nbg, 512, smem, sm>>>(A + (size_t)b0 * ms, ms, n, n, ws.Z + (size_t)b0 * ms, ms, n, ws.states + b0,
+                                                   ws.U + buf * ustride + b0 * w2, ws.Vg + b0 * w2, ws.Tg + b0 * w2,
+                                                   ws.prows + b0, ws.pcols_main + b0, pcz, bud);
+            EK(cudaEventRecord(ev_pass[g][buf], sm));
+            EK(zgemm_grouped(cfg_rows, OP_H, OP_N, ws.prows + b0, nbg, max_tiles_rows, one, zero, sm));
+            EK(zgemm_grouped(cfg_cz, OP_N, OP_N, ws.pcols_main + b0, nbg, max_tiles_cz, one, zero, sm));
+            EK(cudaStreamWaitEvent(ss, ev_pass[g][buf], 0));
+            EK(zgemm_grouped(cfg_cz, OP_N, OP_N, pcz, 2 * nbg, max_tiles_cz, one, zero, ss));
+            EK(cudaEventRecord(ev_side[g][buf], ss));
+        }
         if (hf && (it % poll) == poll - 1) {
             const int slot = (int)(group & 1);
-            if (group >= 1) {       // examine the previous group's count (its copy was enqueued one group ago)
-                EK(cudaEventSynchronize(ev[slot ^ 1]));
-                if (hf[slot ^ 1] == 0) finished = true;
+            for (int g = 0; g < G; ++g) {
+                if (fin[g]) continue;
+                if (group >= 1) {       // examine the previous group's count (its copy was enqueued one poll period ago)
+                    EK(cudaEventSynchronize(ev[g][slot ^ 1]));
+                    if (hf[g * 2 + (slot ^ 1)] == 0) { fin[g] = true; ++nfin; continue; }
+                }
+                qr_count_kernel<<<1, 128, 0, sa[g]>>>(ws.states + gb0[g], gb0[g + 1] - gb0[g], ws.flag + g * 2 + slot);
+                EK(cudaMemcpyAsync(hf + g * 2 + slot, ws.flag + g * 2 + slot, sizeof(int), cudaMemcpyDeviceToHost, sa[g]));
+                EK(cudaEventRecord(ev[g][slot], sa[g]));
             }
-            qr_count_kernel<<<1, 128, 0, st>>>(ws.states, nb, ws.flag + slot);
-            EK(cudaMemcpyAsync(hf + slot, ws.flag + slot, sizeof(int), cudaMemcpyDeviceToHost, st));
-            EK(cudaEventRecord(ev[slot], st));
             ++group;
         }
     }
-    // join both internal streams back into the caller's stream before anything reads H or Z
-    EK(cudaStreamWaitEvent(st, ev_side[0], 0));
-    EK(cudaStreamWaitEvent(st, ev_side[1], 0));
-    EK(cudaEventRecord(ev_join, st));
+    // join all internal streams back into the caller's stream before anything reads H or Z
     st = user_st;
-    EK(cudaStreamWaitEvent(st, ev_join, 0));
-    cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join);
-    cudaStreamDestroy(sa);
-    for (int q = 0; q < 2; ++q) { cudaEventDestroy(ev_pass[q]); cudaEventDestroy(ev_side[q]); }
-    if (ev[0]) cudaEventDestroy(ev[0]);
-    if (ev[1]) cudaEventDestroy(ev[1]);
-    cudaStreamDestroy(sb);
+    for (int g = 0; g < G; ++g) {
+        EK(cudaStreamWaitEvent(sa[g], ev_side[g][0], 0));
+        EK(cudaStreamWaitEvent(sa[g], ev_side[g][1], 0));
+        EK(cudaEventRecord(ev_join[g], sa[g]));
+        EK(cudaStreamWaitEvent(st, ev_join[g], 0));
+    }
+    cudaEventDestroy(ev_fork);
+    for (int g = 0; g < G; ++g) {
+        cudaEventDestroy(ev_join[g]);
+        for (int q = 0; q < 2; ++q) { cudaEventDestroy(ev_pass[g][q]); cudaEventDestroy(ev_side[g][q]); cudaEventDestroy(ev[g][q]); }
+        cudaStreamDestroy(sa[g]);
+        cudaStreamDestroy(sb[g]);
+    }
     qr_finish_kernel<<<(nb + 127) / 128, 128, 0, st>>>(ws.states, nb, info);
 
     // ---------------- phase 3: Schur form T = Z^H A0 Z (upper triangle; the strictly lower part is round-off

@@ -205,6 +205,18 @@ size_t hessenberg_workspace_bytes(int n, int nb) {
 
 #define HK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
 
+// One launch of the streaming mat-vec of column j = k0 + i exactly as hessenberg_blocked issues it (profiling
+// entry: bench.py times these launches alone with CUDA events for the roofline figure).  Reads the
+// (n - k0 - 1) x (n - j - 1) trailing block of every matrix once: 16 (n-k0-1)(n-j-1) nb bytes.
+cudaError_t hessenberg_matvec_probe(const cplx* A, int n, int nb, int j, char* wsb, cudaStream_t st) {
+    if (j < 0 || j > n - 3) return cudaErrorInvalidValue;
+    const int k0 = (j / HB_NB) * HB_NB, i = j - k0;
+    cplx* pan = (cplx*)wsb;
+    hb_matvec_kernel<<<dim3((n - k0 - 1 + HB_ROWS - 1) / HB_ROWS, nb), 256, 0, st>>>(A, (long long)n * n, n, n, k0, i, pan, (long long)hb_elems(n));
+    return cudaGetLastError();
+}
+int hessenberg_panel_width() { return HB_NB; }
+
 // A [nb] (n x n) -> upper Hessenberg in place; Z [nb] (n x n) <- accumulated reflectors (A_in = Z H Z^H)
 cudaError_t hessenberg_blocked(cplx* A, int n, int nb, cplx* Z, char* wsb, cudaStream_t st) {
     const long long ms = (long long)n * n;

@@ -63,12 +63,15 @@ cudaError_t lu_solve_right(const cplx* LU, long long lustride, int n, int lda, c
 // ---- hess.cu
 size_t hessenberg_workspace_bytes(int n, int nb);
 cudaError_t hessenberg_blocked(cplx* A, int n, int nb, cplx* Z, char* ws, cudaStream_t st);
+cudaError_t hessenberg_matvec_probe(const cplx* A, int n, int nb, int j, char* ws, cudaStream_t st);
+int hessenberg_panel_width();
 
 // ---- eig.cu
 size_t eig_workspace_bytes(int n, int nb);
 cudaError_t eig_stats(const char* ws, int n, int nb, int* out, cudaStream_t st);
 cudaError_t eig_profile(const char* ws, int n, int nb, long long* out, cudaStream_t st);
 cudaError_t hessenberg(cplx* A, int n, int nb, cplx* Zout, char* ws, size_t ws_bytes, cudaStream_t st);
+cudaError_t eig_matvec_probe(const cplx* A, int n, int nb, int j, char* ws, size_t ws_bytes, cudaStream_t st);
 cudaError_t eig(cplx* A, int n, int nb, cplx* w, cplx* V, char* ws, size_t ws_bytes, int* info, volatile int* host_flag, cudaStream_t st);
 
 }  // namespace rcwa

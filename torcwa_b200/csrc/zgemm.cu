@@ -306,15 +306,17 @@ cudaError_t zgemm_grouped(int tile_cfg, int opa, int opb, const ZGemmProblem* pr
 // 256-thread CTA per SM, so they use the 128-thread tiles (two CTAs per SM overlap each other's load and
 // store phases); products with one dimension <= 32 use the matching skinny tile instead of computing a
 // half-empty 64-wide one.
-static int g_tune[8] = {1, GEMM_TILE_64x64, GEMM_TILE_64x64, 1, 1, 0, 0, 0};
+static int g_tune[16] = {1, GEMM_TILE_64x64, GEMM_TILE_64x64, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 // tuning knobs (process-wide, set before use; not part of the numerical contract):
 //   0: use the 3-multiplication complex product where a kernel exists      (default 1)
 //   1: tile of the QR row-panel updates   2: tile of the QR column/Z updates
 //   3: use the short-K / skinny tiles in the automatic choice               (default 1)
-//   4: the QR pass kernel claims a whole SM per matrix (no GEMM CTA co-resident)  (default 1)
-//   5 / 6 / 7: per-launch budgets of the QR pass: small-Schur rotations, AED swaps, AED restore steps (0 = default)
-void gemm_set_tuning(int key, int value) { if (key >= 0 && key < 8) g_tune[key] = value; }
-int gemm_get_tuning(int key) { return (key >= 0 && key < 8) ? g_tune[key] : 0; }
+//   4: the QR pass kernel claims a whole SM per matrix (no GEMM CTA co-resident)  (default 0)
+//   5 / 6 / 7: per-launch count limits of the QR pass: small-Schur rotations, AED swaps, AED restore steps (0 = default)
+//   8: time budget of a serial QR slice in microseconds (0 = default 90, < 0 = count limits only)
+//   9: number of independently pipelined matrix groups in the QR phase (0 = default 2)
+void gemm_set_tuning(int key, int value) { if (key >= 0 && key < 16) g_tune[key] = value; }
+int gemm_get_tuning(int key) { return (key >= 0 && key < 16) ? g_tune[key] : 0; }
 
 int gemm_pick_cfg(int opa, int opb, int M, int N, int K) {
     const int big = (gemm_tiles(GEMM_TILE_64x128, M, N) * 64 * 128 <= gemm_tiles(GEMM_TILE_128x64, M, N) * 128 * 64) ? GEMM_TILE_64x128 : GEMM_TILE_128x64;

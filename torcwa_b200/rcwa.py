@@ -17,6 +17,7 @@ torch is used for device memory, streams and O(N) per-order bookkeeping only; th
 fallback for the dense stages -- if the CUDA library is missing the constructor raises.
 """
 import warnings
+import weakref
 
 import torch
 
@@ -426,10 +427,12 @@ class _LazyDense:
     access (the reference's ``Sin`` / ``Sout`` are lists of four dense matrices)."""
 
     def __init__(self, sim, blocks):
-        self._sim, self._blocks = sim, blocks
+        # weak back-reference: a strong one makes sim <-> sim.Sin a reference cycle, and a cycle keeps a finished
+        # simulation's multi-GB S-matrices alive until the cyclic garbage collector happens to run
+        self._sim, self._blocks = weakref.ref(sim), blocks
 
     def __len__(self):
         return len(self._blocks)
 
     def __getitem__(self, k):
-        return self._sim._pub(_lib.blockdiag_dense(self._blocks[k].contiguous()))
+        return self._sim()._pub(_lib.blockdiag_dense(self._blocks[k].contiguous()))
