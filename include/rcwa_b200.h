@@ -129,6 +129,16 @@ int rcwa_hessenberg_panel_width(void);
 /* kz = sqrt(lambda), negated where Im < 0 (rcwa.py:1240-1241). total = nb*n elements. */
 int rcwa_kz_branch(const void* lam, void* kz, long long total, void* stream);
 
+/* ---- stage 2, reverse mode: gradient of the eigendecomposition ------------------------------
+ * grad[b] (n x n) = X^-H (diag(g_lambda) + conj(F) o (X^H g_X)) X^H with F_ij = conj(s_ij) / (|s_ij|^2 + delta),
+ * s_ij = lambda_j - lambda_i, F_ii = 0 (Lorentzian broadening, delta = torcwa.Eig.broadening_parameter).
+ * lam [nb,n], X [nb,n,n] = the outputs of rcwa_eig; glam [nb,n] and gX [nb,n,n] the incoming gradients (either
+ * may be NULL = zero).  Two GEMMs, one LU of X, one right-solve; info[nb] reports a singular X.
+ * Replaces Eig.backward, torcwa/torch_eig.py:19-44 (3 matmul + 1 inverse). */
+size_t rcwa_eig_backward_workspace_bytes(int n, int nb);
+int rcwa_eig_backward(const void* lam, const void* X, const void* glam, const void* gX, double delta, int nb, int n,
+                      void* grad, void* ws, int* info, void* stream);
+
 /* ---- stage 3a: layer S-matrix -------------------------------------------------------------
  * Inputs: eigenvectors W [nb,n,n], kz [nb,n], Q [nb,n,n], vfinv [nb,4,N] = the four diagonals of
  * Vf^-1 (free-space E->H matrix, rcwa.py:1143-1147), omega[nb], thickness[nb] (fp64).

@@ -364,3 +364,21 @@ def solve_point(freq, order, L, layers, *, dtype=torch.complex128, eps_in=None, 
         sim.add_layer(d, e)
     sim.solve_global_smatrix()
     return sim
+
+
+def eig_backward(eigval, eigvec, grad_eigval, grad_eigvec, broadening_parameter=1e-10):
+    """Restatement of Eig.backward (torcwa/torch_eig.py:19-44) for one matrix, complex input:
+    s_ij = lambda_j - lambda_i (:25); F = conj(s) / (|s|^2 + delta), delta = broadening parameter or the
+    smallest denormal of the precision (:28-33); diag(F) = 0 (:35-36);
+    grad = X^-H (diag(g_lambda) + conj(F) o (X^H g_X)) X^H (:37-40).  TEST INFRASTRUCTURE (see module header)."""
+    s = eigval.unsqueeze(-2) - eigval.unsqueeze(-1)
+    if broadening_parameter is not None:
+        delta = broadening_parameter
+    else:
+        delta = 1.4e-45 if s.dtype == torch.complex64 else 4.9e-324
+    F = torch.conj(s) / (torch.abs(s) ** 2 + delta)
+    idx = torch.arange(F.shape[-1])
+    F[idx, idx] = 0.0
+    XH = torch.transpose(torch.conj(eigvec), -2, -1)
+    tmp = torch.conj(F) * torch.matmul(XH, grad_eigvec)
+    return torch.matmul(torch.matmul(torch.inverse(XH), torch.diag(grad_eigval) + tmp), XH)

@@ -18,6 +18,10 @@ def rnd(*shape, seed=0):
                          torch.randn(*shape, generator=g, dtype=torch.float64)).to(dev())
 
 
+def rel(a, b):
+    return float(torch.linalg.norm((a - b).reshape(-1)) / torch.linalg.norm(b.reshape(-1)))
+
+
 def match_sorted(a, b):
     """max distance between two multisets of complex numbers after greedy nearest matching."""
     a, b = list(a), list(b)
@@ -95,3 +99,65 @@ def test_eig_rcwa_matrix(name, golden_dir):
     mine = np.sort_complex(w[0].cpu().numpy())
     assert np.abs(mine - g["kz2_sorted"][0]).max() < 1e-9 * np.abs(mine).max()
     assert float(torch.linalg.cond(V[0].cpu())) < 1e8
+
+
+# ------------------------------------------------------------------ Eig.backward
+@pytest.mark.parametrize("name", ["rand6", "rand24", "rand57", "rcwa_o3"])
+@pytest.mark.parametrize("broadening", [1e-10, None])
+def test_eig_backward_kernel_vs_reference_golden(name, broadening, golden_dir):
+    """rcwa_eig_backward on the reference's own (eigval, eigvec, incoming gradients) == the reference's Eig.backward."""
+    import os
+    from torcwa_b200 import _lib
+    g = np.load(os.path.join(golden_dir, "eig_backward.npz"))
+    t = lambda k: torch.from_numpy(g[name + "_" + k]).to(dev())[None].contiguous()
+    ref = g[name + "_grad_b" + ("1e-10" if broadening is not None else "None")]
+    delta = 1e-10 if broadening is not None else 4.9e-324
+    grad, info = _lib.eig_backward(t("w"), t("V"), t("gw"), t("gV"), delta)
+    assert int(info.abs().max()) == 0
+    got = grad[0].cpu().numpy()
+    assert np.linalg.norm(got - ref) <= 1e-10 * np.linalg.norm(ref)
+    # either incoming gradient may be absent
+    from oracle.rcwa_oracle import eig_backward
+    w, V, gw, gV = (torch.from_numpy(g[name + "_" + k]) for k in ("w", "V", "gw", "gV"))
+    only_w, _ = _lib.eig_backward(t("w"), t("V"), t("gw"), None, 1e-10)
+    only_V, _ = _lib.eig_backward(t("w"), t("V"), None, t("gV"), 1e-10)
+    rw = eig_backward(w, V, gw, torch.zeros_like(gV), 1e-10).numpy()
+    rV = eig_backward(w, V, torch.zeros_like(gw), gV, 1e-10).numpy()
+    assert np.linalg.norm(only_w[0].cpu().numpy() - rw) <= 1e-10 * np.linalg.norm(rw)
+    assert np.linalg.norm(only_V[0].cpu().numpy() - rV) <= 1e-10 * np.linalg.norm(rV)
+
+
+def test_eig_autograd_gauge_invariant_loss_matches_native():
+    """End to end through torcwa_b200.Eig (CUDA forward + CUDA backward) against PyTorch's native eig autograd on the
+    CPU, on a gauge-invariant loss |sum M o (V exp(0.1 i L) V^-1)|^2; batched and unbatched, c128 and c64."""
+    import torcwa_b200
+    n = 40
+    A0 = rnd(2, n, n, seed=77).cpu()
+    Mw = rnd(n, n, seed=78).cpu()
+
+    def loss(w, V, Mw):
+        f = V @ torch.diag_embed(torch.exp(0.1j * w)) @ torch.linalg.inv(V)
+        return ((Mw * f).sum(dim=(-2, -1)).abs() ** 2).sum()
+
+    old = torcwa_b200.Eig.broadening_parameter
+    try:
+        torcwa_b200.Eig.broadening_parameter = None
+        Ac = A0.clone().requires_grad_(True)
+        loss(*torch.linalg.eig(Ac), Mw).backward()
+        Ag = A0.clone().to(dev()).requires_grad_(True)
+        loss(*torcwa_b200.Eig.apply(Ag), Mw.to(dev())).backward()
+        assert rel(Ag.grad.cpu(), Ac.grad) < 1e-9
+        A1 = A0[0].clone().to(dev()).requires_grad_(True)            # unbatched
+        loss(*torcwa_b200.Eig.apply(A1), Mw.to(dev())).backward()
+        A1c = A0[0].clone().requires_grad_(True)
+        loss(*torch.linalg.eig(A1c), Mw).backward()
+        assert rel(A1.grad.cpu(), A1c.grad) < 1e-9
+        A64 = A0.to(torch.complex64).to(dev()).requires_grad_(True)   # complex64 API, complex128 arithmetic
+        loss(*torcwa_b200.Eig.apply(A64), Mw.to(torch.complex64).to(dev())).backward()
+        assert A64.grad.dtype == torch.complex64
+        assert rel(A64.grad.cpu().to(torch.complex128), Ac.grad) < 1e-4
+        Ar = A0[0].real.clone().to(dev()).requires_grad_(True)        # real input -> real gradient (torch_eig.py:41-42)
+        loss(*torcwa_b200.Eig.apply(Ar), Mw.to(dev())).backward()
+        assert Ar.grad.dtype == torch.float64 and not torch.is_complex(Ar.grad)
+    finally:
+        torcwa_b200.Eig.broadening_parameter = old

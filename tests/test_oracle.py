@@ -102,3 +102,15 @@ def test_energy_conservation_lossless():
             v = sim.S_parameters(allo, direction="forward", port=port, polarization=pol)
             tot += float((v.abs() ** 2).sum())
     assert abs(tot - 1.0) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["rand6", "rand24", "rand57", "rcwa_o3"])
+@pytest.mark.parametrize("broadening", [1e-10, None])
+def test_oracle_eig_backward_matches_reference(name, broadening, golden_dir):
+    """oracle.eig_backward == the unmodified reference's Eig.backward (tools/make_golden_eig_backward.py)."""
+    from oracle.rcwa_oracle import eig_backward
+    g = np.load(os.path.join(golden_dir, "eig_backward.npz"))
+    t = lambda k: torch.from_numpy(g[name + "_" + k])
+    ref = g[name + "_grad_b" + ("1e-10" if broadening is not None else "None")]
+    got = eig_backward(t("w"), t("V"), t("gw"), t("gV"), broadening).numpy()
+    assert np.linalg.norm(got - ref) <= 1e-12 * np.linalg.norm(ref)

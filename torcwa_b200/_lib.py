@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("RCWA_B200_LIB", "librcwa_b200.so"
 EXPORTS = [
     "rcwa_b200_abi_version", "rcwa_gemm_scratch_bytes", "rcwa_convmat_workspace_bytes", "rcwa_convmat",
     "rcwa_zgemm_batched", "rcwa_zgemm_batched_cfg", "rcwa_set_tuning", "rcwa_get_tuning", "rcwa_lu_tinv_bytes", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
-    "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_eig_stats", "rcwa_eig_profile", "rcwa_hessenberg", "rcwa_hessenberg_matvec_probe", "rcwa_hessenberg_panel_width", "rcwa_kz_branch", "rcwa_layer_smatrix_workspace_bytes",
+    "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_eig_stats", "rcwa_eig_profile", "rcwa_hessenberg", "rcwa_hessenberg_matvec_probe", "rcwa_hessenberg_panel_width", "rcwa_kz_branch", "rcwa_eig_backward_workspace_bytes", "rcwa_eig_backward", "rcwa_layer_smatrix_workspace_bytes",
     "rcwa_layer_smatrix", "rcwa_redheffer_workspace_bytes", "rcwa_redheffer", "rcwa_redheffer_bdleft", "rcwa_blockdiag_dense",
 ]
 
@@ -40,6 +40,8 @@ _SIGS = {
     "rcwa_hessenberg_matvec_probe": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp]),
     "rcwa_hessenberg_panel_width": (_i, []),
     "rcwa_kz_branch": (_i, [_vp, _vp, _ll, _vp]),
+    "rcwa_eig_backward_workspace_bytes": (_sz, [_i, _i]),
+    "rcwa_eig_backward": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _vp, _vp, _vp, _vp]),
     "rcwa_layer_smatrix_workspace_bytes": (_sz, [_i, _i]),
     "rcwa_layer_smatrix": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "rcwa_redheffer_workspace_bytes": (_sz, [_i, _i]),
@@ -254,6 +256,19 @@ def matvec_probe(A, ws, j):
 def eig_workspace(n, nb, device):
     lib = load()
     return _ws(lib.rcwa_eig_workspace_bytes(n, nb), device)
+
+
+def eig_backward(lam, X, glam, gX, delta):
+    """Gradient of the eigendecomposition (Eig.backward): lam [nb,n], X [nb,n,n], glam / gX or None -> (grad [nb,n,n], info)."""
+    lib = load()
+    nb, n = X.shape[0], X.shape[1]
+    grad = torch.empty_like(X)
+    info = torch.zeros((nb,), dtype=torch.int32, device=X.device)
+    ws = _ws(lib.rcwa_eig_backward_workspace_bytes(n, nb), X.device)
+    _check(lib.rcwa_eig_backward(_ptr(_c128(lam, "lam")), _ptr(_c128(X, "X")), _ptr(None if glam is None else _c128(glam, "glam")),
+                                 _ptr(None if gX is None else _c128(gX, "gX")), float(delta), nb, n, _ptr(grad), _ptr(ws), _ptr(info), _stream()),
+           "rcwa_eig_backward")
+    return grad, info
 
 
 def kz_branch(lam):

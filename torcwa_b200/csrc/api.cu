@@ -175,6 +175,48 @@ int rcwa_kz_branch(const void* lam, void* kz, long long total, void* stream) {
     return cu(kz_branch((const cplx*)lam, (cplx*)kz, (size_t)total, S(stream)));
 }
 
+// ---- Eig.backward (torcwa/torch_eig.py:19-44):  grad = X^-H (diag(g_lambda) + conj(F) o (X^H g_X)) X^H
+size_t rcwa_eig_backward_workspace_bytes(int n, int nb) {
+    const size_t mat = align256((size_t)n * n * nb * sizeof(cplx));
+    return 4 * mat + 2 * align256((size_t)n * nb * sizeof(int)) + rcwa_lu_tinv_bytes(n, nb) + rcwa_gemm_scratch_bytes(nb);
+}
+
+int rcwa_eig_backward(const void* lam, const void* X, const void* glam, const void* gX, double delta, int nb, int n,
+                      void* grad, void* ws, int* info, void* stream) {
+    if (!lam) return -1;
+    if (!X) return -2;
+    if (delta < 0.0) return -5;
+    if (nb <= 0) return -6;
+    if (n <= 0) return -7;
+    if (!grad) return -8;
+    if (!ws) return -9;
+    if (!info) return -10;
+    cudaStream_t st = S(stream);
+    const long long ms = (long long)n * n;
+    const size_t mat = align256((size_t)ms * nb * sizeof(cplx));
+    char* p = (char*)ws;
+    cplx* b0 = (cplx*)p; p += mat;
+    cplx* b1 = (cplx*)p; p += mat;
+    cplx* b2 = (cplx*)p; p += mat;
+    cplx* b3 = (cplx*)p; p += mat;
+    int* ipiv = (int*)p; p += align256((size_t)n * nb * sizeof(int));
+    int* perm = (int*)p; p += align256((size_t)n * nb * sizeof(int));
+    cplx* tinv = (cplx*)p; p += rcwa_lu_tinv_bytes(n, nb);
+    ZGemmProblem* gs = (ZGemmProblem*)p;
+    const cplx one = C(1, 0), zero = C(0, 0);
+    const cplx* Xc = (const cplx*)X;
+    // T = X^H gX -> b0 ;  M = diag(glam) + conj(F) o T -> b1
+    if (gX) CK(zgemm_strided(OP_H, OP_N, n, n, n, one, Xc, n, ms, (const cplx*)gX, n, ms, zero, b0, n, ms, nb, gs, st));
+    CK(eig_backward_combine((const cplx*)lam, (const cplx*)glam, gX ? b0 : nullptr, delta, nb, n, b1, st));
+    // grad = X^-H M X^H  =  (X M^H X^-1)^H :   Y = X M^H -> b0 ;  R = Y X^-1 (right-solve on the LU of X) -> b2 ;  grad = R^H
+    CK(zgemm_strided(OP_N, OP_H, n, n, n, one, Xc, n, ms, b1, n, ms, zero, b0, n, ms, nb, gs, st));
+    CK(cudaMemcpyAsync(b1, Xc, (size_t)ms * nb * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+    CK(lu_factor(b1, ms, n, n, nb, ipiv, perm, info, tinv, gs, st));
+    CK(lu_solve_right(b1, ms, n, n, perm, tinv, b0, ms, n, n, b2, ms, n, b3, nb, gs, st));
+    CK(conj_transpose(b2, nb, n, (cplx*)grad, st));
+    return 0;
+}
+
 // workspace layout helpers ---------------------------------------------------------------------
 size_t rcwa_layer_smatrix_workspace_bytes(int N, int nb) {
     const size_t n = 2 * (size_t)N, mat = align256(n * n * nb * sizeof(cplx));

@@ -46,6 +46,42 @@ __global__ void pq_assemble_kernel(const cplx* __restrict__ eta, const cplx* __r
     q[r1 + N] = cmul(yv, kxj);                // Ky nu Kx
 }
 
+// Eig.backward, elementwise part (torcwa/torch_eig.py:24-38):  M = diag(g_lambda) + conj(F) o T,
+//   s_ij = lambda_j - lambda_i,  F_ij = conj(s_ij) / (|s_ij|^2 + delta),  F_ii = 0   =>   conj(F_ij) = s_ij / (|s_ij|^2 + delta).
+// grid (ceil(n/256), n, B).  glam may be nullptr (zero eigenvalue gradient); T may be nullptr (zero eigenvector gradient).
+__global__ void eig_backward_combine_kernel(const cplx* __restrict__ lam, const cplx* __restrict__ glam, const cplx* __restrict__ T,
+                                            double delta, int n, cplx* __restrict__ M) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+    if (j >= n) return;
+    const size_t e = ((size_t)b * n + i) * n + j;
+    cplx out;
+    if (i == j) out = glam ? glam[(size_t)b * n + i] : C(0, 0);
+    else if (!T) out = C(0, 0);
+    else {
+        const cplx sij = csub(lam[(size_t)b * n + j], lam[(size_t)b * n + i]);
+        const double den = cabs_(sij) * cabs_(sij) + delta;        // torch.abs(s)**2 + delta, as the reference rounds it
+        out = cmul(C(sij.x / den, sij.y / den), T[e]);
+    }
+    M[e] = out;
+}
+
+// B[b][j][i] = conj(A[b][i][j])   (tile transpose through shared memory), grid (ceil(n/32), ceil(n/32), B), block (32, 8)
+__global__ void conj_transpose_kernel(const cplx* __restrict__ A, int n, cplx* __restrict__ Bm) {
+    __shared__ cplx tile[32][33];
+    const int b = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const cplx* a = A + (size_t)b * n * n;
+    cplx* o = Bm + (size_t)b * n * n;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = y0 + r, j = x0 + threadIdx.x;
+        if (i < n && j < n) tile[r][threadIdx.x] = a[(size_t)i * n + j];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = x0 + r, j = y0 + threadIdx.x;          // output row = input column
+        if (i < n && j < n) o[(size_t)i * n + j] = cconj(tile[threadIdx.x][r]);
+    }
+}
+
 __global__ void kz_branch_kernel(const cplx* __restrict__ lam, cplx* __restrict__ kz, size_t total) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
@@ -172,6 +208,14 @@ namespace rcwa {
 cudaError_t pq_assemble(const cplx* eta, const cplx* E, const cplx* Mc, const cplx* nu, const cplx* mu_s,
                         const cplx* kx, const cplx* ky, int nb, int N, cplx* P, cplx* Q, cudaStream_t st) {
     pq_assemble_kernel<<<dim3((N + 255) / 256, N, nb), 256, 0, st>>>(eta, E, Mc, nu, mu_s, kx, ky, N, P, Q);
+    return cudaGetLastError();
+}
+cudaError_t eig_backward_combine(const cplx* lam, const cplx* glam, const cplx* T, double delta, int nb, int n, cplx* M, cudaStream_t st) {
+    eig_backward_combine_kernel<<<dim3((n + 255) / 256, n, nb), 256, 0, st>>>(lam, glam, T, delta, n, M);
+    return cudaGetLastError();
+}
+cudaError_t conj_transpose(const cplx* A, int nb, int n, cplx* Bm, cudaStream_t st) {
+    conj_transpose_kernel<<<dim3((n + 31) / 32, (n + 31) / 32, nb), dim3(32, 8), 0, st>>>(A, n, Bm);
     return cudaGetLastError();
 }
 cudaError_t kz_branch(const cplx* lam, cplx* kz, size_t total, cudaStream_t st) {

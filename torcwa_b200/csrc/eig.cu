@@ -4,7 +4,7 @@
 //
 //  (1) Blocked Householder Hessenberg reduction  A = Z H Z^H  (hess.cu): per column one read-only
 //      streaming mat-vec over the trailing matrix (the HBM-bound kernel of the stage, exactly the
-//      algorithmic 16 n^3/3 bytes), per 32-column panel compact-WY block updates of A and Z on the
+//      algorithmic 16 n^3/3 bytes), per 64-column panel compact-WY block updates of A and Z on the
 //      DMMA GEMM.
 //  (2) Windowed multishift QR  H -> T (upper triangular), Z <- Z U:  chains of up to QR_NS
 //      single-shift Givens bulges (spacing 2) are chased through a QR_W x QR_W diagonal window held
@@ -1287,6 +1287,11 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
                                                    ws.prows + b0, ws.pcols_main + b0, pcz, bud);
             EK(cudaEventRecord(ev_pass[g][buf], sm));
             EK(zgemm_grouped(cfg_rows, OP_H, OP_N, ws.prows + b0, nbg, max_tiles_rows, one, zero, sm));
+            // A main-stream column update (last window of a sweep, AED, small block) overlaps the columns of the
+            // previous window's side-stream column update and must be applied AFTER it: wait for the previous
+            // iteration's side GEMMs.  (Without this the order was only a matter of timing -- the low-priority side
+            // GEMM normally finishes long before -- and a second group's kernels delaying it corrupted results.)
+            if (it >= 1) EK(cudaStreamWaitEvent(sm, ev_side[g][buf ^ 1], 0));
             EK(zgemm_grouped(cfg_cz, OP_N, OP_N, ws.pcols_main + b0, nbg, max_tiles_cz, one, zero, sm));
             EK(cudaStreamWaitEvent(ss, ev_pass[g][buf], 0));
             EK(zgemm_grouped(cfg_cz, OP_N, OP_N, pcz, 2 * nbg, max_tiles_cz, one, zero, ss));

@@ -1,6 +1,6 @@
 // Phase 1 of rcwa_eig: batched BLOCKED Householder Hessenberg reduction  A = Z H Z^H  (complex128).
 //
-// Panel of HB_NB columns (compact WY, LAPACK zgehrd/zlahr2 structure, Hermitian reflectors
+// Panel of HB_NB = 64 columns (compact WY, LAPACK zgehrd/zlahr2 structure, Hermitian reflectors
 // H_j = I - u_j u_j^H with |u_j|^2 = 2, i.e. tau = 1):
 //
 //   per column j of the panel
@@ -19,7 +19,8 @@
 #include "kernels.h"
 
 #ifndef HB_NB
-#define HB_NB 32          // panel width (compile-time; -DHB_NB=64 builds the wide-panel variant)
+#define HB_NB 64          // panel width (compile-time).  64: the panel GEMMs are K = 64 / N = 64 products, which run at
+                          // 21-31 TFLOP/s instead of 14-27 at 32 (profiles/r1b_gemm_probe.json); measured -7 % on the phase
 #endif
 #define HB_ROWS 32          // rows per CTA in the matvec (8 warps x 4 rows)
 

@@ -41,6 +41,8 @@ cudaError_t convmat(const void* grid, int grid_type, long long grid_stride, int 
 cudaError_t pq_assemble(const cplx* eta, const cplx* E, const cplx* Mc, const cplx* nu, const cplx* mu_s,
                         const cplx* kx, const cplx* ky, int nb, int N, cplx* P, cplx* Q, cudaStream_t st);
 cudaError_t kz_branch(const cplx* lam, cplx* kz, size_t total, cudaStream_t st);
+cudaError_t eig_backward_combine(const cplx* lam, const cplx* glam, const cplx* T, double delta, int nb, int n, cplx* M, cudaStream_t st);
+cudaError_t conj_transpose(const cplx* A, int nb, int n, cplx* Bm, cudaStream_t st);
 cudaError_t layer_form(const cplx* W, const cplx* QW, const cplx* kz, const cplx* vfinv, const double* omega,
                        const double* thick, int nb, int N, cplx* Mp, cplx* Mm, cplx* Rp, cplx* Rm, cudaStream_t st);
 cudaError_t layer_finish(const cplx* Tp, const cplx* Tm, int nb, int n, cplx* S11, cplx* S21, cudaStream_t st);
