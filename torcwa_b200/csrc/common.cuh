@@ -133,10 +133,13 @@ DEV double cta_max(const Cta& c, double v, double* scratch) {
 // ------------------------------------------------------------------ grouped GEMM problem descriptor
 // C(M x N) = alpha * op(A) * op(B) + beta * C, row-major, interleaved complex128.
 // M == 0 marks an inactive entry.
+#define ZGEMM_B_UPPER 1      // op(B) is upper triangular (K == N frame): output column tile [n0, n0+BN) only needs k < n0 + BN
+#define ZGEMM_C_UPPER 2      // only the upper triangle of C is wanted: tiles entirely below the diagonal are skipped (left untouched)
 struct ZGemmProblem {
     const cplx* A; const cplx* B; cplx* C;
     int M, N, K;
     int lda, ldb, ldc;
+    int flags;               // ZGEMM_* structure hints (0 = dense)
 };
 
 // status / error codes of the C ABI (LAPACK style: <0 = bad argument #k)

@@ -44,7 +44,7 @@ struct QrBudget {
     int restore;    // Householder steps per launch while folding the AED spike back to Hessenberg form
     long long cycles;   // SM-clock budget of a serial slice (0: count budgets only); the counts above are upper bounds
 };
-#define QR_BUDGET_SCHUR 400
+#define QR_BUDGET_SCHUR 4000
 #define QR_BUDGET_SWAPS 300
 #define QR_BUDGET_RESTORE 32
 #define QR_BUDGET_US 90
@@ -293,6 +293,46 @@ DEV int small_schur_slice(const Cta& c, cplx* Hs, cplx* Us, int m, int* pi, int*
         for (int d = l + c.tid; d <= i; d += c.nthreads) Hs[d * QR_LD + d] = csub(Hs[d * QR_LD + d], sig);
         GROUP_SYNC(c);
         // ---- phase 1: R = Q^H (H - sig I)
+#ifndef RCWA_EMU
+        if (c.warp_only && c.nthreads == 32 && m <= 64) {
+            // Warp version without any barrier inside the rotation loop: lane t owns columns t and t + 32 and keeps
+            // the running row (row k after G_{k-1}) of its columns in registers; the pivot element travels by
+            // shuffle; row k + 1 is still the untouched original in shared memory when step k reads it; final rows
+            // are stored as they complete, and the zeroed subdiagonal is written after the loop (nobody may clear
+            // H[k+1][k] while another lane can still be reading it as the rotation's second operand).
+            const int lane = c.tid;
+            cplx top[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) { const int j = lane + 32 * q; top[q] = (j >= l && j < m) ? Hs[l * QR_LD + j] : C(0, 0); }
+            for (int k = l; k < i; ++k) {
+                const int ko = k & 31, so = k >> 5;
+                cplx bot[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) { const int j = lane + 32 * q; bot[q] = (j > k && j < m) ? Hs[(k + 1) * QR_LD + j] : C(0, 0); }
+                const cplx y = Hs[(k + 1) * QR_LD + k];
+                cplx x;
+                x.x = __shfl_sync(0xffffffffu, so ? top[1].x : top[0].x, ko);
+                x.y = __shfl_sync(0xffffffffu, so ? top[1].y : top[0].y, ko);
+                double cs; cplx sn, r;
+                givens(x, y, cs, sn, r);
+                if (lane == ko) { rot_c[k] = cs; rot_s[k] = sn; Hs[k * QR_LD + k] = r; }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int j = lane + 32 * q;
+                    if (j > k && j < m) {
+                        Hs[k * QR_LD + j] = cadd(cscale(top[q], cs), cmul(sn, bot[q]));
+                        top[q] = csub(cscale(bot[q], cs), cmul(cconj(sn), top[q]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) { const int j = lane + 32 * q; if (j >= i && j < m) Hs[i * QR_LD + j] = top[q]; }
+            GROUP_SYNC(c);
+            for (int k = l + lane; k < i; k += 32) Hs[(k + 1) * QR_LD + k] = C(0, 0);
+            GROUP_SYNC(c);
+        } else
+#endif
+        {
         cplx r_prev = C(0, 0);
         for (int k = l; k < i; ++k) {
             double cs; cplx sn, r;
@@ -312,6 +352,7 @@ DEV int small_schur_slice(const Cta& c, cplx* Hs, cplx* Us, int m, int* pi, int*
         }
         if (c.tid == 0) { Hs[(i - 1) * QR_LD + i - 1] = r_prev; Hs[i * QR_LD + i - 1] = C(0, 0); }
         GROUP_SYNC(c);
+        }
         // ---- phase 2: H' = R Q (rows 0..i; row r only holds columns >= r) and U <- U Q (all m rows)
         for (int idx = c.tid; idx < (i + 1) + m; idx += c.nthreads) {
             cplx* row; int ks;
@@ -523,6 +564,7 @@ DEV void emit_window_gemms(cplx* H, int ldh, int n, cplx* Zm, int ldz, cplx* Ug,
     const int wend = p + wl;
     const int ncol = hi + 1 - wend, nrow = p - lo;
     ZGemmProblem g;
+    g.flags = 0;
     g.A = Ug; g.lda = QR_W; g.B = H + (size_t)p * ldh + wend; g.ldb = ldh; g.C = H + (size_t)p * ldh + wend; g.ldc = ldh;
     g.M = (ncol > 0) ? wl : 0; g.N = ncol; g.K = wl; *prob_rows = g;                    // H[p:wend, wend:hi+1] <- U^H * (.)
     g.A = H + (size_t)lo * ldh + p; g.lda = ldh; g.B = Ug; g.ldb = QR_W; g.C = H + (size_t)lo * ldh + p; g.ldc = ldh;
@@ -959,7 +1001,7 @@ extern "C" int emu_qr(cplx* H, cplx* Z, int n, int max_passes, int* stats) {
     {
         std::vector<cplx> t0((size_t)n * n), Z0h((size_t)n * n);
         for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) Z0h[(size_t)i * n + j] = cconj(Z0[(size_t)j * n + i]);
-        ZGemmProblem g; g.M = n; g.N = n; g.K = n; g.lda = n; g.ldb = n; g.ldc = n;
+        ZGemmProblem g; g.flags = 0; g.M = n; g.N = n; g.K = n; g.lda = n; g.ldb = n; g.ldc = n;
         g.A = Z0.data(); g.B = H0.data(); g.C = t0.data(); emu_gemm(g, 0);
         g.A = t0.data(); g.B = Z0h.data(); g.C = A0.data(); emu_gemm(g, 0);
     }
@@ -975,7 +1017,7 @@ extern "C" int emu_qr(cplx* H, cplx* Z, int n, int max_passes, int* stats) {
     }
     {   // T = Z^H A0 Z (as the device path does); strictly lower part set to exact zero
         std::vector<cplx> tmp((size_t)n * n);
-        ZGemmProblem g; g.M = n; g.N = n; g.K = n; g.lda = n; g.ldb = n; g.ldc = n;
+        ZGemmProblem g; g.flags = 0; g.M = n; g.N = n; g.K = n; g.lda = n; g.ldb = n; g.ldc = n;
         g.A = A0.data(); g.B = Z; g.C = tmp.data(); emu_gemm(g, 0);
         g.A = Z; g.B = tmp.data(); g.C = H; emu_gemm(g, 2);
         for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) H[(size_t)i * n + j] = C(0, 0);
@@ -1000,7 +1042,7 @@ extern "C" int emu_trevc(const cplx* T, int n, cplx* X) {
     for (int kb = nblk - 1; kb >= 0; --kb) {
         const int r0 = kb * TV_NB, nbk = (n - r0 < TV_NB) ? n - r0 : TV_NB, r1 = r0 + nbk;
         if (r1 < n) {
-            ZGemmProblem g; g.A = T + (size_t)r0 * n + r1; g.lda = n; g.B = X + (size_t)r1 * n + r1; g.ldb = n;
+            ZGemmProblem g; g.flags = 0; g.A = T + (size_t)r0 * n + r1; g.lda = n; g.B = X + (size_t)r1 * n + r1; g.ldb = n;
             g.C = X + (size_t)r0 * n + r1; g.ldc = n; g.M = nbk; g.N = n - r1; g.K = n - r1;
             emu_gemm(g, 0);
             for (int i = 0; i < nbk; ++i) for (int j = r1; j < n; ++j) X[(size_t)(r0 + i) * n + j] = cneg(X[(size_t)(r0 + i) * n + j]);
@@ -1334,7 +1376,7 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
     cplx* Tm = ws.X;            // A0 -> T
     cplx* Xv = A;               // scratch for A0*Z, then the eigenvector matrix of T
     EK(zgemm_strided(OP_N, OP_N, n, n, n, one, ws.X, n, ms, ws.Z, n, ms, zero, A, n, ms, nb, ws.gs, st));        // A  = A0 Z
-    EK(zgemm_strided(OP_H, OP_N, n, n, n, one, ws.Z, n, ms, A, n, ms, zero, Tm, n, ms, nb, ws.gs, st));          // T  = Z^H (A0 Z)
+    EK(zgemm_strided(OP_H, OP_N, n, n, n, one, ws.Z, n, ms, A, n, ms, zero, Tm, n, ms, nb, ws.gs, st, ZGEMM_C_UPPER));   // T  = Z^H (A0 Z), upper tiles only
     diag_extract_kernel<<<dim3((n + 255) / 256, nb), 256, 0, st>>>(Tm, ms, n, n, wout);
     tnorm_kernel<<<nb, 256, 0, st>>>(wout, n, ws.tnorm);
     EK(cudaMemsetAsync(Xv, 0, sizeof(cplx) * (size_t)ms * nb, st));
@@ -1344,11 +1386,11 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
         if (r1 < n) {
             // X[I, r1:n] = -T[I, r1:n] * X[r1:n, r1:n]
             EK(zgemm_strided(OP_N, OP_N, nbk, n - r1, n - r1, C(-1, 0), Tm + (size_t)r0 * n + r1, n, ms,
-                             Xv + (size_t)r1 * n + r1, n, ms, zero, Xv + (size_t)r0 * n + r1, n, ms, nb, ws.gs, st));
+                             Xv + (size_t)r1 * n + r1, n, ms, zero, Xv + (size_t)r0 * n + r1, n, ms, nb, ws.gs, st, ZGEMM_B_UPPER));
         }
         trevc_block_kernel<<<dim3((n - r0 + 127) / 128, nb), 128, 0, st>>>(Tm, ms, n, n, r0, nbk, wout, ws.tnorm, Xv, ms, n);
     }
-    EK(zgemm_strided(OP_N, OP_N, n, n, n, one, ws.Z, n, ms, Xv, n, ms, zero, V, n, ms, nb, ws.gs, st));
+    EK(zgemm_strided(OP_N, OP_N, n, n, n, one, ws.Z, n, ms, Xv, n, ms, zero, V, n, ms, nb, ws.gs, st, ZGEMM_B_UPPER));   // X is upper triangular
     colnorm_kernel<<<dim3((n + 31) / 32, nb), dim3(32, 8), 0, st>>>(V, ms, n, n, ws.nrm);
     colscale_kernel<<<dim3((n + 255) / 256, n, nb), 256, 0, st>>>(V, ms, n, n, ws.nrm);
     return cudaGetLastError();

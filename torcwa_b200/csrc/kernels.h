@@ -25,11 +25,11 @@ void gemm_set_tuning(int key, int value);
 int gemm_get_tuning(int key);
 cudaError_t zgemm_strided_cfg(int cfg, int opa, int opb, int M, int N, int K, cplx alpha, const cplx* A, int lda, long long sa,
                               const cplx* B, int ldb, long long sb, cplx beta, cplx* C, int ldc, long long sc,
-                              int batch, ZGemmProblem* scratch, cudaStream_t st);
+                              int batch, ZGemmProblem* scratch, cudaStream_t st, int flags = 0);
 // `scratch`: device array of >= batch ZGemmProblem
 cudaError_t zgemm_strided(int opa, int opb, int M, int N, int K, cplx alpha, const cplx* A, int lda, long long sa,
                           const cplx* B, int ldb, long long sb, cplx beta, cplx* C, int ldc, long long sc,
-                          int batch, ZGemmProblem* scratch, cudaStream_t st);
+                          int batch, ZGemmProblem* scratch, cudaStream_t st, int flags = 0);   // flags: ZGEMM_* structure hints
 
 
 // ---- convmat.cu

@@ -84,14 +84,17 @@ zgemm_grouped_kernel(const ZGemmProblem* __restrict__ probs, cplx alpha, cplx be
     const int tiles_n = (p.N + BN - 1) / BN, tiles_m = (p.M + BM - 1) / BM;
     if ((int)blockIdx.x >= tiles_m * tiles_n) return;
     const int m0 = ((int)blockIdx.x / tiles_n) * BM, n0 = ((int)blockIdx.x % tiles_n) * BN;
+    if ((p.flags & ZGEMM_C_UPPER) && m0 >= n0 + BN) return;             // tile entirely below the diagonal
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / WNC, wn = warp % WNC;
-    const int nk = (p.K + BK - 1) / BK;
+    // triangular op(B): rows k >= n0 + BN of this column tile are zero -- shorten the k loop (exact: skips zeros)
+    const int kmax = ((p.flags & ZGEMM_B_UPPER) && n0 + BN < p.K) ? n0 + BN : p.K;
+    const int nk = (kmax + BK - 1) / BK;
 
     TileLoader<BM, NTHR, OPA == 0> la;
     TileLoader<BN, NTHR, OPB != 0> lb;
-    la.init(p.A, p.lda, m0, p.M, p.K, tid);
-    lb.init(p.B, p.ldb, n0, p.N, p.K, tid);
+    la.init(p.A, p.lda, m0, p.M, kmax, tid);
+    lb.init(p.B, p.ldb, n0, p.N, kmax, tid);
     auto load_stage = [&](int stage, int kt) {
         la.load(As + stage * A_STAGE, kt * BK);
         lb.load(Bs + stage * B_STAGE, kt * BK);
@@ -209,12 +212,12 @@ zgemm_grouped_kernel(const ZGemmProblem* __restrict__ probs, cplx alpha, cplx be
 }
 
 __global__ void fill_strided_kernel(ZGemmProblem* probs, int batch, const cplx* A, const cplx* B, cplx* C,
-                                    long long sa, long long sb, long long sc, int M, int N, int K, int lda, int ldb, int ldc) {
+                                    long long sa, long long sb, long long sc, int M, int N, int K, int lda, int ldb, int ldc, int flags) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     ZGemmProblem p;
     p.A = A + (size_t)b * sa; p.B = B + (size_t)b * sb; p.C = C + (size_t)b * sc;
-    p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.flags = flags;
     probs[b] = p;
 }
 
@@ -342,18 +345,18 @@ int gemm_pick_cfg_base(int opa, int opb, int M, int N, int K) {
 
 cudaError_t zgemm_strided_cfg(int cfg, int opa, int opb, int M, int N, int K, cplx alpha, const cplx* A, int lda, long long sa,
                               const cplx* B, int ldb, long long sb, cplx beta, cplx* Cm, int ldc, long long sc,
-                              int batch, ZGemmProblem* scratch, cudaStream_t st) {
+                              int batch, ZGemmProblem* scratch, cudaStream_t st, int flags) {
     if (batch <= 0 || M <= 0 || N <= 0) return cudaSuccess;
     if (cfg < 0) cfg = gemm_pick_cfg(opa, opb, M, N, K);
     if (!gemm_cfg_supports(cfg & 7, opa, opb) || ((cfg & GEMM_M3) && !gemm_cfg_supports(GEMM_TILE_64x64, opa, opb))) return cudaErrorNotSupported;
-    fill_strided_kernel<<<(batch + 127) / 128, 128, 0, st>>>(scratch, batch, A, B, Cm, sa, sb, sc, M, N, K, lda, ldb, ldc);
+    fill_strided_kernel<<<(batch + 127) / 128, 128, 0, st>>>(scratch, batch, A, B, Cm, sa, sb, sc, M, N, K, lda, ldb, ldc, flags);
     return zgemm_grouped(cfg, opa, opb, scratch, batch, gemm_tiles(cfg, M, N), alpha, beta, st);
 }
 
 cudaError_t zgemm_strided(int opa, int opb, int M, int N, int K, cplx alpha, const cplx* A, int lda, long long sa,
                           const cplx* B, int ldb, long long sb, cplx beta, cplx* Cm, int ldc, long long sc,
-                          int batch, ZGemmProblem* scratch, cudaStream_t st) {
-    return zgemm_strided_cfg(-1, opa, opb, M, N, K, alpha, A, lda, sa, B, ldb, sb, beta, Cm, ldc, sc, batch, scratch, st);
+                          int batch, ZGemmProblem* scratch, cudaStream_t st, int flags) {
+    return zgemm_strided_cfg(-1, opa, opb, M, N, K, alpha, A, lda, sa, B, ldb, sb, beta, Cm, ldc, sc, batch, scratch, st, flags);
 }
 
 }  // namespace rcwa
