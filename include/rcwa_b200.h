@@ -69,7 +69,9 @@ int rcwa_zgemm_batched(int opa, int opb, int M, int N, int K, double alpha_re, d
  *   1 / 2: tile of the QR row / column updates; 3: use the 128-thread tiles (default 1); 4: the QR pass
  *   kernel claims a whole SM per matrix (default 0); 5-7: count limits of the serial QR slices (Schur
  *   rotations, AED swaps, AED restore steps); 8: time budget of a serial QR slice in us (default 90);
- *   9: number of independently pipelined matrix groups of the QR phase (default 2).  Call before
+ *   9: number of independently pipelined matrix groups of the QR phase (default 2); 10: skip the zero
+ *   k groups of the banded window unitaries in the QR update GEMMs (default 0, measured no gain);
+ *   11: Hessenberg phase as two staggered half batches (default 0, measured slower).  Call before
  *   enqueuing work; the numerical contract does not depend on them. */
 int rcwa_zgemm_batched_cfg(int cfg, int opa, int opb, int M, int N, int K, double alpha_re, double alpha_im,
                            const void* A, int lda, long long stride_a, const void* B, int ldb, long long stride_b,

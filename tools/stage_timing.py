@@ -12,6 +12,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--order", type=int, default=15)
 ap.add_argument("--nb", type=int, default=4)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--residual", action="store_true", help="also report max |A W - W diag(lam)| / |A| of the eigendecomposition")
 a = ap.parse_args()
 d = torch.device("cuda:0")
 
@@ -34,6 +35,7 @@ for rep in range(2):
     e2 = ev(); P, Q = _lib.pq_assemble(eta, E, sim._kx, sim._ky, mu_scalar=torch.ones(a.nb, dtype=cd, device=d))
     e3 = ev(); A = _lib.zgemm(P, Q)
     e4 = ev(); H = A.clone(); Z = _lib.hessenberg_(H)
+    A_keep = A.clone() if (a.residual and rep == 1) else None
     e5 = ev(); del H, Z; lam, W, info = _lib.eig(A)
     e6 = ev(); kz = _lib.kz_branch(lam)
     om = sim._omega64.expand(a.nb).contiguous(); th = torch.full((a.nb,), float(thick), dtype=torch.float64, device=d)
@@ -51,6 +53,10 @@ print("  eig info max:", int(info.abs().max()), " stats [sweeps, passes, aeds, i
 n = 2 * sim.order_N
 beig = 16.0 * (n ** 3 / 3 + 2 * n * n)
 print(f"  B_eig = {beig/1e9:.2f} GB/matrix -> eig stage {a.nb*beig/t['eig(total)']/1e6:.0f} GB/s, hessenberg alone {a.nb*beig/t['hessenberg(alone)']/1e6:.0f} GB/s (algorithmic)")
+if a.residual:
+    R = torch.matmul(A_keep, W) - W * lam[:, None, :]
+    print("  eig residual max|A W - W L| / max|A| per matrix:", float((R.abs().amax(dim=(1, 2)) / A_keep.abs().amax(dim=(1, 2))).max()),
+          " cond-free check |W col norms - 1| max:", float((torch.linalg.norm(W, dim=1) - 1).abs().max()))
 if a.check:
     sim._S = S; sim.S = [s[0] if a.nb == 1 else s for s in S]
     g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ex1_o15.npz"))

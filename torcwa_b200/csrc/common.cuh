@@ -140,7 +140,12 @@ struct ZGemmProblem {
     int M, N, K;
     int lda, ldb, ldc;
     int flags;               // ZGEMM_* structure hints (0 = dense)
+    // ZGEMM_A_BAND / ZGEMM_B_BAND: the small operand U (<= 64 x 64, a QR window unitary: banded, see eig.cu) has
+    // nonzeros of its 8-column tile t only in rows [4*klo[t], 4*khi[t]); the kernel skips the other k groups.
+    unsigned char klo[8], khi[8];
 };
+#define ZGEMM_A_BAND 4       // op(A) = U^H (row update): output ROW tile t <-> U's column tile t
+#define ZGEMM_B_BAND 8       // B = U (column / Z update): output COLUMN tile t <-> U's column tile t
 
 // status / error codes of the C ABI (LAPACK style: <0 = bad argument #k)
 #define RCWA_OK 0

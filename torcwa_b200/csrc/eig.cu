@@ -86,6 +86,7 @@ struct QrState {
     int shifts_ready;    // phase 1 may start with st.shifts as they are (supplied by AED)
     int aeds, aed_deflated;   // statistics
     int pad0, pad1;
+    long long band_active, band_total;   // profiling: k groups the banded update GEMMs keep / would run dense
     long long cyc_max[6]; // profiling: longest single segment
     long long cyc[6];    // profiling: SM cycles spent per pass segment (0 sweep start: scan + shifts, 1 chase, 2 small-block
     int cnt[6];          //   slice, 3 AED Schur slice, 4 AED scan slice, 5 AED finish: scan + restore + write-back) and counts
@@ -396,6 +397,8 @@ struct QrScratch {
     int ss_rc, ss_i, ss_its;    // results of a small-Schur slice run by warp 0
     cplx hv[QR_W];              // Householder vector (AED restore)
     double red[40];
+    unsigned char col_lo[QR_W], col_hi[QR_W];   // first / last nonzero row of each column of the window unitary
+    unsigned char band_lo[8], band_hi[8];       // per 8-column tile: range of 4-row groups holding nonzeros
     double rot_c[QR_W];         // rotations of one small-Schur iteration (phase 1 -> phase 2)
     cplx rot_s[QR_W];
 };
@@ -560,13 +563,16 @@ DEV int aed_restore_hessenberg(const Cta& c, cplx* T, cplx* V, int nw, int ns, c
 // The off-diagonal blocks of the final Schur form are recovered afterwards in two large GEMMs,
 // T = Z^H A0 Z (A0 = the input matrix, Z = all accumulated transformations) -- 2 n^3 complex MACs at full tensor rate instead of ~1/3 of all K = 64 panel updates.
 DEV void emit_window_gemms(cplx* H, int ldh, int n, cplx* Zm, int ldz, cplx* Ug, int p, int wl, int lo, int hi,
-                           ZGemmProblem* prob_rows, ZGemmProblem* prob_cols, ZGemmProblem* prob_z) {
+                           ZGemmProblem* prob_rows, ZGemmProblem* prob_cols, ZGemmProblem* prob_z,
+                           const unsigned char* band_lo = nullptr, const unsigned char* band_hi = nullptr) {
     const int wend = p + wl;
     const int ncol = hi + 1 - wend, nrow = p - lo;
     ZGemmProblem g;
     g.flags = 0;
+    for (int t = 0; t < 8; ++t) { g.klo[t] = band_lo ? band_lo[t] : 0; g.khi[t] = band_hi ? band_hi[t] : 0; }
     g.A = Ug; g.lda = QR_W; g.B = H + (size_t)p * ldh + wend; g.ldb = ldh; g.C = H + (size_t)p * ldh + wend; g.ldc = ldh;
-    g.M = (ncol > 0) ? wl : 0; g.N = ncol; g.K = wl; *prob_rows = g;                    // H[p:wend, wend:hi+1] <- U^H * (.)
+    g.M = (ncol > 0) ? wl : 0; g.N = ncol; g.K = wl; g.flags = band_lo ? ZGEMM_A_BAND : 0; *prob_rows = g;   // H[p:wend, wend:hi+1] <- U^H * (.)
+    g.flags = band_lo ? ZGEMM_B_BAND : 0;
     g.A = H + (size_t)lo * ldh + p; g.lda = ldh; g.B = Ug; g.ldb = QR_W; g.C = H + (size_t)lo * ldh + p; g.ldc = ldh;
     g.M = (nrow > 0) ? nrow : 0; g.N = wl; g.K = wl; *prob_cols = g;                      // H[lo:p, p:wend] <- (.) * U
     g.A = Zm + p; g.lda = ldz; g.B = Ug; g.ldb = QR_W; g.C = Zm + p; g.ldc = ldz;
@@ -922,13 +928,36 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         CTA_SYNC();
     }
 
+    // ---------------- band of the window unitary.  A bulge carries content only along its own travel range and the
+    // bulges never overtake each other, so U is banded (lower bandwidth = number of bulges, upper ~ travel + 1):
+    // about 30 % of a 64 x 64 U are EXACT zeros (never touched since the identity).  The update GEMMs skip the
+    // 4-row k groups that are zero for a whole 8-column tile of U; the table is read off the actual zeros.
+    for (int j = c.tid; j < QR_W; j += c.nthreads) {
+        int lo_r = 255, hi_r = 0;
+        if (j < wl)
+            for (int r = 0; r < wl; ++r)
+                if (!cis_zero(Us[r * QR_LD + j])) { if (r < lo_r) lo_r = r; hi_r = r; }
+        sc->col_lo[j] = (unsigned char)lo_r; sc->col_hi[j] = (unsigned char)hi_r;
+    }
+    CTA_SYNC();
+    for (int t = c.tid; t < 8; t += c.nthreads) {
+        int lo_r = 255, hi_r = -1;
+        for (int q = 0; q < 8; ++q) {
+            const int j = 8 * t + q;
+            if (j < wl && sc->col_lo[j] != 255) { if (sc->col_lo[j] < lo_r) lo_r = sc->col_lo[j]; if (sc->col_hi[j] > hi_r) hi_r = sc->col_hi[j]; }
+        }
+        sc->band_lo[t] = (unsigned char)((hi_r < 0) ? 0 : lo_r / 4);
+        sc->band_hi[t] = (unsigned char)((hi_r < 0) ? 0 : hi_r / 4 + 1);
+    }
     // ---------------- write back window and U, emit GEMM problems, advance state
     for (int idx = c.tid; idx < wl * wl; idx += c.nthreads) {
         int r = idx / wl, q = idx % wl;
         H[(size_t)(p + r) * ldh + (p + q)] = Hs[r * QR_LD + q];
         Ug[r * QR_W + q] = Us[r * QR_LD + q];
     }
+    CTA_SYNC();
     if (c.tid == 0) {
+        for (int t = 0; t < 8; ++t) if (8 * t < wl) { st.band_active += sc->band_hi[t] - sc->band_lo[t]; st.band_total += (wl + 3) / 4; }
         int nb_after = 0, introduced = 0;
         for (int b = 0; b < nslots; ++b) {
             if (sc->q0[b] < 0) ++introduced;
@@ -938,7 +967,8 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
         }
         // the pass that ends a sweep is followed by a deflation scan / AED window that may reach above this
         // window: its column update must be complete by then -> main stream; otherwise side stream
-        emit_window_gemms(H, ldh, n, Zm, ldz, Ug, p, wl, st.lo, st.hi, prob_rows, (nb_after == 0) ? prob_cols_main : prob_cols, prob_z);
+        emit_window_gemms(H, ldh, n, Zm, ldz, Ug, p, wl, st.lo, st.hi, prob_rows, (nb_after == 0) ? prob_cols_main : prob_cols, prob_z,
+                          sc->band_lo, sc->band_hi);
         st.p_last = (nb_after == 0) ? -1 : p;
         st.nintro += introduced;
         if (p == st.lo && st.nintro < st.ns) st.ns = st.nintro;      // window could not take more: cap this sweep
@@ -1024,6 +1054,7 @@ extern "C" int emu_qr(cplx* H, cplx* Z, int n, int max_passes, int* stats) {
     }
     stats[0] = st.sweeps; stats[1] = st.passes; stats[2] = st.done; stats[3] = st.small_solves;
     stats[4] = st.aeds; stats[5] = st.aed_deflated;
+    stats[6] = (int)st.band_active; stats[7] = (int)st.band_total;
     return st.done ? st.info : -1;
 }
 
@@ -1184,7 +1215,7 @@ EigWs carve(char* base, int n, int nb) {
     w.U = (cplx*)take(sizeof(cplx) * (size_t)QR_W * QR_W * nb * 2);      // double-buffered window unitaries
     w.Vg = (cplx*)take(sizeof(cplx) * (size_t)QR_W * QR_W * nb);
     w.Tg = (cplx*)take(sizeof(cplx) * (size_t)QR_W * QR_W * nb);
-    w.hess = take(rcwa::hessenberg_workspace_bytes(n, nb));
+    w.hess = take(rcwa::hessenberg_workspace_bytes(n, nb / 2) + rcwa::hessenberg_workspace_bytes(n, nb - nb / 2) + 4096);   // two half batches
     w.states = (QrState*)take(sizeof(QrState) * (size_t)nb);
     w.prows = (ZGemmProblem*)take(sizeof(ZGemmProblem) * (size_t)nb);
     w.pcols_main = (ZGemmProblem*)take(sizeof(ZGemmProblem) * (size_t)nb);
@@ -1205,8 +1236,38 @@ size_t eig_workspace_bytes(int n, int nb) { return carve(nullptr, n, nb).total; 
 
 #define EK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
 
+// The Hessenberg phase alternates an HBM-bound column phase (streaming mat-vec + a latency-bound per-column kernel:
+// tensor pipes idle) with a tensor-bound block-update phase (HBM idle).  Two half batches on two streams, the second
+// started when the first has finished its first column phase, run in anti-phase and use both resources at once.
 static cudaError_t hessenberg_phase(cplx* A, int n, int nb, const EigWs& ws, cudaStream_t st) {
-    return rcwa::hessenberg_blocked(A, n, nb, ws.Z, ws.hess, st);      // hess.cu
+    if (!gemm_get_tuning(11) || nb < 16) return rcwa::hessenberg_blocked(A, n, nb, ws.Z, ws.hess, st);      // hess.cu
+    const int nb0 = nb / 2, nb1 = nb - nb0;
+    const long long ms = (long long)n * n;
+    cudaStream_t s0 = nullptr, s1 = nullptr;
+    cudaEvent_t fork = nullptr, first = nullptr, j0 = nullptr, j1 = nullptr;
+    cudaError_t e;
+#define HP(expr) do { e = (expr); if (e != cudaSuccess) return e; } while (0)
+    HP(cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking));
+    HP(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+    HP(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    HP(cudaEventCreateWithFlags(&first, cudaEventDisableTiming));
+    HP(cudaEventCreateWithFlags(&j0, cudaEventDisableTiming));
+    HP(cudaEventCreateWithFlags(&j1, cudaEventDisableTiming));
+    HP(cudaEventRecord(fork, st));
+    HP(cudaStreamWaitEvent(s0, fork, 0));
+    HP(cudaStreamWaitEvent(s1, fork, 0));
+    char* w1 = ws.hess + al(rcwa::hessenberg_workspace_bytes(n, nb0));
+    HP(rcwa::hessenberg_blocked(A, n, nb0, ws.Z, ws.hess, s0, first));
+    HP(cudaStreamWaitEvent(s1, first, 0));
+    HP(rcwa::hessenberg_blocked(A + (size_t)nb0 * ms, n, nb1, ws.Z + (size_t)nb0 * ms, w1, s1));
+    HP(cudaEventRecord(j0, s0));
+    HP(cudaEventRecord(j1, s1));
+    HP(cudaStreamWaitEvent(st, j0, 0));
+    HP(cudaStreamWaitEvent(st, j1, 0));
+#undef HP
+    cudaEventDestroy(fork); cudaEventDestroy(first); cudaEventDestroy(j0); cudaEventDestroy(j1);
+    cudaStreamDestroy(s0); cudaStreamDestroy(s1);
+    return cudaSuccess;
 }
 
 // diagnostics of the last eig() run that used this workspace: per matrix {sweeps, passes, AED windows, info}
@@ -1273,6 +1334,9 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
     const int m3 = gemm_get_tuning(0) ? GEMM_M3 : 0;
     const int cfg_rows = ((gemm_get_tuning(1) == GEMM_TILE_64x128) ? GEMM_TILE_64x128 : GEMM_TILE_64x64) | m3;
     const int cfg_cz = ((gemm_get_tuning(2) == GEMM_TILE_128x64) ? GEMM_TILE_128x64 : GEMM_TILE_64x64) | m3;
+    const int band = (m3 && gemm_get_tuning(10)) ? GEMM_BAND : 0;
+    const int cfg_rows_b = ((cfg_rows & 7) == GEMM_TILE_64x64) ? (cfg_rows | band) : cfg_rows;
+    const int cfg_cz_b = ((cfg_cz & 7) == GEMM_TILE_64x64) ? (cfg_cz | band) : cfg_cz;
     const int max_tiles_rows = gemm_tiles(cfg_rows, QR_W, n);
     const int max_tiles_cz = gemm_tiles(cfg_cz, n, QR_W);
     // Two streams: the main stream carries the serial chain  pass -> row-panel GEMM -> next pass ; the
@@ -1328,15 +1392,15 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
                                                    ws.U + buf * ustride + b0 * w2, ws.Vg + b0 * w2, ws.Tg + b0 * w2,
                                                    ws.prows + b0, ws.pcols_main + b0, pcz, bud);
             EK(cudaEventRecord(ev_pass[g][buf], sm));
-            EK(zgemm_grouped(cfg_rows, OP_H, OP_N, ws.prows + b0, nbg, max_tiles_rows, one, zero, sm));
+            EK(zgemm_grouped(cfg_rows_b, OP_H, OP_N, ws.prows + b0, nbg, max_tiles_rows, one, zero, sm));
             // A main-stream column update (last window of a sweep, AED, small block) overlaps the columns of the
             // previous window's side-stream column update and must be applied AFTER it: wait for the previous
             // iteration's side GEMMs.  (Without this the order was only a matter of timing -- the low-priority side
             // GEMM normally finishes long before -- and a second group's kernels delaying it corrupted results.)
             if (it >= 1) EK(cudaStreamWaitEvent(sm, ev_side[g][buf ^ 1], 0));
-            EK(zgemm_grouped(cfg_cz, OP_N, OP_N, ws.pcols_main + b0, nbg, max_tiles_cz, one, zero, sm));
+            EK(zgemm_grouped(cfg_cz_b, OP_N, OP_N, ws.pcols_main + b0, nbg, max_tiles_cz, one, zero, sm));
             EK(cudaStreamWaitEvent(ss, ev_pass[g][buf], 0));
-            EK(zgemm_grouped(cfg_cz, OP_N, OP_N, pcz, 2 * nbg, max_tiles_cz, one, zero, ss));
+            EK(zgemm_grouped(cfg_cz_b, OP_N, OP_N, pcz, 2 * nbg, max_tiles_cz, one, zero, ss));
             EK(cudaEventRecord(ev_side[g][buf], ss));
         }
         if (hf && (it % poll) == poll - 1) {

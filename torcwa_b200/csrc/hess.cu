@@ -219,7 +219,7 @@ cudaError_t hessenberg_matvec_probe(const cplx* A, int n, int nb, int j, char* w
 int hessenberg_panel_width() { return HB_NB; }
 
 // A [nb] (n x n) -> upper Hessenberg in place; Z [nb] (n x n) <- accumulated reflectors (A_in = Z H Z^H)
-cudaError_t hessenberg_blocked(cplx* A, int n, int nb, cplx* Z, char* wsb, cudaStream_t st) {
+cudaError_t hessenberg_blocked(cplx* A, int n, int nb, cplx* Z, char* wsb, cudaStream_t st, cudaEvent_t after_first_columns) {
     const long long ms = (long long)n * n;
     HK(set_identity(Z, n, n, ms, nb, st));
     if (n < 3) return cudaSuccess;
@@ -250,6 +250,7 @@ cudaError_t hessenberg_blocked(cplx* A, int n, int nb, cplx* Z, char* wsb, cudaS
         }
         hb_col_kernel<<<nb, 512, smem_col, st>>>(A, ms, n, n, k0, nbe, 1, pan, wstride);
         HK(cudaGetLastError());
+        if (k0 == 0 && after_first_columns) HK(cudaEventRecord(after_first_columns, st));
         const int r0 = k0 + 1, nr = n - r0;                  // rows touched by this panel's reflectors
         const int c1 = k0 + nbe, nc = n - c1;                // trailing columns (right of the panel)
         // ---- Y_top = A[0:r0, r0:n] V[r0:n,:] T

@@ -8,6 +8,7 @@
 #define GEMM_TILE_128x32 3     // 4 warps, 2 CTAs/SM (N <= 32)
 #define GEMM_TILE_32x128 4     // 4 warps, 2 CTAs/SM (M <= 32)
 #define GEMM_M3 8              // flag: 3-multiplication complex product
+#define GEMM_BAND 16           // flag (64x64 + M3 only): honour the ZGEMM_A_BAND / ZGEMM_B_BAND tables of the descriptors
 #define GEMM_SHORT_K 128
 #define OP_N 0
 #define OP_T 1
@@ -64,7 +65,8 @@ cudaError_t lu_solve_right(const cplx* LU, long long lustride, int n, int lda, c
 
 // ---- hess.cu
 size_t hessenberg_workspace_bytes(int n, int nb);
-cudaError_t hessenberg_blocked(cplx* A, int n, int nb, cplx* Z, char* ws, cudaStream_t st);
+// after_first_columns (optional): recorded on `st` once the column phase of the first panel has been enqueued
+cudaError_t hessenberg_blocked(cplx* A, int n, int nb, cplx* Z, char* ws, cudaStream_t st, cudaEvent_t after_first_columns = nullptr);
 cudaError_t hessenberg_matvec_probe(const cplx* A, int n, int nb, int j, char* ws, cudaStream_t st);
 int hessenberg_panel_width();
 

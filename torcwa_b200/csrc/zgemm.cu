@@ -67,7 +67,9 @@ struct TileLoader {
 // MINB = CTAs per SM the register budget is planned for.  M3 = 3-multiplication complex product
 // (three real accumulators  P1 = sum ar*br, P2 = sum ai*bi, P3 = sum (ar+ai)(br+bi);  re = P1 - P2,
 // im = P3 - P1 - P2): 25 % fewer DMMAs at norm-wise (not component-wise) fp64 accuracy.
-template <int BM, int BN, int WM, int WN, int OPA, int OPB, bool M3, int MINB>
+// BAND (3M kernels only): 1 = op(A) is a banded window unitary (ZGEMM_A_BAND), 2 = B is (ZGEMM_B_BAND): the MMAs of
+// the 4-row k groups that are zero for a whole 8-wide tile of U are skipped (exact; table in the descriptor).
+template <int BM, int BN, int WM, int WN, int OPA, int OPB, bool M3, int MINB, int BAND = 0>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
 zgemm_grouped_kernel(const ZGemmProblem* __restrict__ probs, cplx alpha, cplx beta) {
     constexpr int NTHR = (BM / WM) * (BN / WN) * 32;
@@ -105,6 +107,19 @@ zgemm_grouped_kernel(const ZGemmProblem* __restrict__ probs, cplx alpha, cplx be
     const int fr = lane >> 2, fk = lane & 3;
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) { if (s < nk) load_stage(s, s); cp_async_commit(); }
+
+    // band table of this warp's four 8-wide tiles of U, one byte each (all-active when the problem carries no table)
+    unsigned band_lo4 = 0u, band_hi4 = 0xffffffffu;
+    if (BAND != 0 && (p.flags & (BAND == 1 ? ZGEMM_A_BAND : ZGEMM_B_BAND))) {
+        const int t0 = (BAND == 1) ? (m0 + wm * WM) / 8 : (n0 + wn * WN) / 8;
+        band_lo4 = 0u; band_hi4 = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int t = t0 + q;
+            band_lo4 |= (unsigned)(t < 8 ? p.klo[t] : 0) << (8 * q);
+            band_hi4 |= (unsigned)(t < 8 ? p.khi[t] : 0) << (8 * q);
+        }
+    }
 
     // beta != 0 (rank-k updates C -= A B): the old C tile is folded into the INITIAL accumulators as
     // (beta/alpha) C, loaded here -- all loads independent and in flight together with the first operand
@@ -145,22 +160,35 @@ zgemm_grouped_kernel(const ZGemmProblem* __restrict__ probs, cplx alpha, cplx be
             for (int t = 0; t < NT; ++t) { b[t] = bs[(kk + fk) * LDB_S + t * 8]; if (OPB == 2) b[t].y = -b[t].y; }
             if (M3) {
                 // three real MMAs per complex tile; each pass touches MT*NT independent accumulators
+                unsigned act = 0xfu;
+                if (BAND != 0) {
+                    const unsigned k4 = (unsigned)(kt * BK + kk) >> 2;
+                    act = 0u;
 #pragma unroll
-                for (int i = 0; i < MT; ++i)
+                    for (int q = 0; q < 4; ++q)
+                        if (k4 >= ((band_lo4 >> (8 * q)) & 0xffu) && k4 < ((band_hi4 >> (8 * q)) & 0xffu)) act |= 1u << q;
+                }
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) dmma(acc1[i][j][0], acc1[i][j][1], a[i].x, b[j].x);
+                for (int i = 0; i < MT; ++i) {
+                    if (BAND == 1 && !((act >> i) & 1u)) continue;
 #pragma unroll
-                for (int i = 0; i < MT; ++i)
+                    for (int j = 0; j < NT; ++j) { if (BAND == 2 && !((act >> j) & 1u)) continue; dmma(acc1[i][j][0], acc1[i][j][1], a[i].x, b[j].x); }
+                }
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) dmma(acc2[i][j][0], acc2[i][j][1], a[i].y, b[j].y);
+                for (int i = 0; i < MT; ++i) {
+                    if (BAND == 1 && !((act >> i) & 1u)) continue;
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) { if (BAND == 2 && !((act >> j) & 1u)) continue; dmma(acc2[i][j][0], acc2[i][j][1], a[i].y, b[j].y); }
+                }
                 double bsum[NT];
 #pragma unroll
                 for (int j = 0; j < NT; ++j) bsum[j] = b[j].x + b[j].y;
 #pragma unroll
                 for (int i = 0; i < MT; ++i) {
+                    if (BAND == 1 && !((act >> i) & 1u)) continue;
                     const double asum = a[i].x + a[i].y;
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) dmma(acc3[M3 ? i : 0][M3 ? j : 0][0], acc3[M3 ? i : 0][M3 ? j : 0][1], asum, bsum[j]);
+                    for (int j = 0; j < NT; ++j) { if (BAND == 2 && !((act >> j) & 1u)) continue; dmma(acc3[M3 ? i : 0][M3 ? j : 0][0], acc3[M3 ? i : 0][M3 ? j : 0][1], asum, bsum[j]); }
                 }
             } else {
                 // four real MMAs per complex tile, issued pass by pass so that the two MMAs that accumulate into
@@ -221,18 +249,18 @@ __global__ void fill_strided_kernel(ZGemmProblem* probs, int batch, const cplx* 
     probs[b] = p;
 }
 
-template <int BM, int BN, int WM, int WN, int OPA, int OPB, bool M3, int MINB>
+template <int BM, int BN, int WM, int WN, int OPA, int OPB, bool M3, int MINB, int BAND = 0>
 cudaError_t launch_cfg(const ZGemmProblem* probs, int nprob, int max_tiles, cplx alpha, cplx beta, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * BK * ((BM + 2) + (BN + 2)) * sizeof(cplx);
     constexpr int nthr = (BM / WM) * (BN / WN) * 32;
     static bool attr_set = false;   // idempotent attribute; benign if raced
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(zgemm_grouped_kernel<BM, BN, WM, WN, OPA, OPB, M3, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(zgemm_grouped_kernel<BM, BN, WM, WN, OPA, OPB, M3, MINB, BAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     dim3 grid(max_tiles, nprob);
-    zgemm_grouped_kernel<BM, BN, WM, WN, OPA, OPB, M3, MINB><<<grid, nthr, smem, st>>>(probs, alpha, beta);
+    zgemm_grouped_kernel<BM, BN, WM, WN, OPA, OPB, M3, MINB, BAND><<<grid, nthr, smem, st>>>(probs, alpha, beta);
     return cudaGetLastError();
 }
 
@@ -299,6 +327,10 @@ cudaError_t zgemm_grouped(int tile_cfg, int opa, int opb, const ZGemmProblem* pr
         case GEMM_TILE_64x128 | GEMM_M3: return launch_ops3<64, 128, 32, 32, true, 1>(opa, opb, probs, nprob, max_tiles, alpha, beta, st);
         case GEMM_TILE_128x64 | GEMM_M3: return launch_ops3<128, 64, 32, 32, true, 1>(opa, opb, probs, nprob, max_tiles, alpha, beta, st);
         case GEMM_TILE_64x64 | GEMM_M3: return launch_ops3<64, 64, 32, 32, true, 2>(opa, opb, probs, nprob, max_tiles, alpha, beta, st);
+        case GEMM_TILE_64x64 | GEMM_M3 | GEMM_BAND:      // QR window updates: U^H * rows (band on A) or panel * U (band on B)
+            if (opa == 2 && opb == 0) return launch_cfg<64, 64, 32, 32, 2, 0, true, 2, 1>(probs, nprob, max_tiles, alpha, beta, st);
+            if (opa == 0 && opb == 0) return launch_cfg<64, 64, 32, 32, 0, 0, true, 2, 2>(probs, nprob, max_tiles, alpha, beta, st);
+            return cudaErrorNotSupported;
         case GEMM_TILE_128x32 | GEMM_M3: return launch_ops3<128, 32, 32, 32, true, 2>(opa, opb, probs, nprob, max_tiles, alpha, beta, st);
         case GEMM_TILE_32x128 | GEMM_M3: return launch_ops3<32, 128, 32, 32, true, 2>(opa, opb, probs, nprob, max_tiles, alpha, beta, st);
         default: return cudaErrorInvalidValue;
@@ -318,6 +350,10 @@ static int g_tune[16] = {1, GEMM_TILE_64x64, GEMM_TILE_64x64, 1, 0, 0, 0, 0, 0, 
 //   5 / 6 / 7: per-launch count limits of the QR pass: small-Schur rotations, AED swaps, AED restore steps (0 = default)
 //   8: time budget of a serial QR slice in microseconds (0 = default 90, < 0 = count limits only)
 //   9: number of independently pipelined matrix groups in the QR phase (0 = default 2)
+//  10: skip the zero k groups of the banded window unitaries in the QR update GEMMs (default 0: measured no gain --
+//      34 % fewer MMAs, same time: those launches are bound by their load/store phases and by sharing SMs with the pass kernels)
+//  11: run the Hessenberg phase as two staggered half batches on two streams (default 0: measured 9 % SLOWER --
+//      the latency-bound per-column kernel does not shrink with the batch and the halves do not stay in anti-phase)
 void gemm_set_tuning(int key, int value) { if (key >= 0 && key < 16) g_tune[key] = value; }
 int gemm_get_tuning(int key) { return (key >= 0 && key < 16) ? g_tune[key] : 0; }
 
