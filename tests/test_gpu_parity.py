@@ -165,3 +165,29 @@ def test_order15_batched_sweep_parity_and_batch_independence(golden_dir):
     sub = solve(lams[:5].clone())                                  # one group, other slice boundaries
     t_sub = sub.S_parameters(orders=[[0, 0], [1, 0], [0, -1]], polarization="xx")
     assert torch.equal(t_all[:5], t_sub)
+
+
+def test_order15_energy_conservation_lossless_cell():
+    """Size-independent property at the full BASELINE size (order 15x15, n = 1922): for a lossless cell the power
+    carried by all propagating transmitted and reflected orders equals the incident power.  Batch of 3 wavelengths,
+    complex64 API (complex128 arithmetic): |1 - (R + T)| <= 1e-6."""
+    import torcwa_b200
+    dev = torch.device("cuda:0")
+    case = dict(C.CASES["ex1_o15"])
+    rd = torch.float32
+    mask = C.rectangle_grid(300.0, 300.0, 300, 300, 180.0, 100.0, 150.0, 150.0, 0.0, 1000.0, rd).to(dev)
+    lams = torch.tensor([450.0, 532.0, 640.0], dtype=rd)
+    sim = torcwa_b200.rcwa(freq=1 / lams, order=case["order"], L=case["L"], dtype=torch.complex64, device=dev)
+    sim.add_input_layer(eps=1.46 ** 2)
+    sim.set_incident_angle(0.0, 0.0)
+    sim.add_layer(thickness=300.0, eps=mask * 6.25 + (1.0 - mask))          # real permittivity: no absorption
+    sim.solve_global_smatrix()
+    o = case["order"][0]
+    orders = [[i, j] for i in range(-2, 3) for j in range(-2, 3)]           # every order that can propagate at these wavelengths
+    tot = torch.zeros(3, dtype=torch.float64, device=dev)
+    for port in ("transmission", "reflection"):
+        for pol in ("xx", "yx"):
+            s = sim.S_parameters(orders=orders, direction="forward", port=port, polarization=pol, ref_order=[0, 0], power_norm=True, evanscent=1e-3)
+            tot += (s.abs().to(torch.float64) ** 2).sum(dim=1)
+    print("R + T per wavelength:", tot.tolist())
+    assert float((tot - 1.0).abs().max()) <= 1e-6
