@@ -102,7 +102,7 @@ def run_step(grids_dev, freq_dev, case, device):
 def count_my_launches(fn):
     """Kernels of librcwa_b200.so launched by one step (CUPTI through torch.profiler)."""
     mine = ("zgemm_grouped", "fill_strided", "dft_rows", "dft_cols", "toeplitz", "pq_assemble", "kz_branch", "layer_form", "layer_finish",
-            "blockdiag_dense", "identity_kernel", "axpby", "lu_panel", "lu_perm", "lu_colswap", "trsm_rows", "gather_cols", "hess_step",
+            "blockdiag_dense", "identity_kernel", "axpby", "lu_panel", "lu_perm", "lu_colswap", "tri_inv", "gather_cols", "eig_backward", "conj_transpose", "hess_step",
             "hess_fused", "hess_advance", "hb_col", "hb_matvec", "hb_zero", "bd_left_mul", "bd_right_mul", "bd_add", "qr_pass", "qr_init", "qr_count", "qr_finish", "qr_stats", "diag_extract", "tnorm", "trevc_block",
             "colnorm", "colscale")
     try:

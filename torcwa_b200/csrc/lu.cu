@@ -10,7 +10,7 @@
 // i.e. LAPACK getrf applied to A^T, which makes pivot search, scaling and the rank-1 update all
 // contiguous along rows.  Blocked right-looking, panel = NB rows:
 //   panel kernel (one CTA per matrix; phase-structured, also compiled by the CPU emulation build)
-//   -> column swaps outside the panel -> TRSM of the rows below (x * U11 = a, per row)
+//   -> column swaps outside the panel -> rows below: A21 := A21 * U11^-1 (inverted 32 x 32 block, K = 32 GEMM)
 //   -> trailing update A22 -= A21 * A12 on the DMMA grouped GEMM.
 // Solve: X = B*Pi (gather) ; X := X * U^-1 (forward over column blocks) ; X := X * L^-1 (backward),
 // each block step = a per-row small triangular solve + one GEMM.
@@ -216,31 +216,6 @@ __global__ void lu_colswap_kernel(cplx* A, long long stride, int n, int lda, int
     }
 }
 
-// grid (ceil(nrows/32), B): X[r0+r, c0 : c0+nbe] := X[...] * T^-1 ; T = diagonal block of the LU at (k0,k0)
-// mode 0: unit upper, mode 1: lower non-unit.  Tile staged through shared memory for coalescing.
-__global__ void __launch_bounds__(32)
-trsm_rows_kernel(cplx* X, long long xstride, int ldx, int row0, int nrows, int c0,
-                 const cplx* LU, long long lustride, int lda, int k0, int nbe, int mode) {
-    __shared__ cplx T[LU_NB * LU_NB];
-    __shared__ cplx tile[32 * (LU_NB + 1)];
-    const int b = blockIdx.y;
-    const cplx* lu = LU + (size_t)b * lustride + (size_t)k0 * lda + k0;
-    for (int i = threadIdx.x; i < nbe * nbe; i += 32) T[(i / nbe) * LU_NB + (i % nbe)] = lu[(size_t)(i / nbe) * lda + (i % nbe)];
-    const int rbase = row0 + blockIdx.x * 32;
-    cplx* xb = X + (size_t)b * xstride;
-    for (int i = threadIdx.x; i < 32 * nbe; i += 32) {
-        int r = i / nbe, col = i % nbe;
-        if (rbase + r < row0 + nrows) tile[r * (LU_NB + 1) + col] = xb[(size_t)(rbase + r) * ldx + c0 + col];
-    }
-    __syncthreads();
-    if (rbase + (int)threadIdx.x < row0 + nrows) trsm_row(tile + threadIdx.x * (LU_NB + 1), T, LU_NB, nbe, mode);
-    __syncthreads();
-    for (int i = threadIdx.x; i < 32 * nbe; i += 32) {
-        int r = i / nbe, col = i % nbe;
-        if (rbase + r < row0 + nrows) xb[(size_t)(rbase + r) * ldx + c0 + col] = tile[r * (LU_NB + 1) + col];
-    }
-}
-
 // Inverses of the SOLVE_NB x SOLVE_NB diagonal blocks of the factors, so that the triangular solves
 // become large-K GEMMs:  grid (nblk, B, 2): z = 0 -> unit upper U_kk^-1, z = 1 -> lower L_kk^-1.
 // One thread per column of the inverse (back-substitution down its own column; every thread reads the
@@ -273,6 +248,30 @@ tri_inv_kernel(const cplx* __restrict__ LU, long long lustride, int n, int lda, 
     }
 }
 
+// Inverse of the unit-upper nbe x nbe diagonal block U11 of the current panel (identity-extended to LU_NB), so that
+// the rows below get  A21 := A21 * U11^-1  as a K = 32 GEMM instead of a per-row substitution by 32-thread CTAs.
+// grid (B), block (LU_NB): thread j builds column j by back-substitution in shared memory.
+__global__ void __launch_bounds__(LU_NB)
+tri_inv_panel_kernel(const cplx* __restrict__ LU, long long lustride, int lda, int k0, int nbe, cplx* __restrict__ uinv, long long ustride) {
+    __shared__ cplx F[LU_NB][LU_NB + 1];
+    __shared__ cplx X[LU_NB][LU_NB + 1];
+    const int b = blockIdx.x, j = threadIdx.x;
+    const cplx* src = LU + (size_t)b * lustride + (size_t)k0 * lda + k0;
+    for (int i = 0; i < nbe; ++i) F[i][j] = (j < nbe) ? src[(size_t)i * lda + j] : C(0, 0);
+    for (int i = 0; i < LU_NB; ++i) X[i][j] = C(i == j ? 1.0 : 0.0, 0.0);
+    __syncthreads();
+    if (j < nbe) {
+        for (int i = j - 1; i >= 0; --i) {
+            cplx acc = C(0, 0);
+            for (int k = i + 1; k <= j; ++k) acc = cfma(F[i][k], X[k][j], acc);
+            X[i][j] = cneg(acc);
+        }
+    }
+    __syncthreads();
+    cplx* dst = uinv + (size_t)b * ustride;
+    for (int i = 0; i < LU_NB; ++i) dst[i * LU_NB + j] = X[i][j];
+}
+
 // grid (nrows, B): X[r][c] = Bm[r][perm[c]]
 __global__ void gather_cols_kernel(const cplx* __restrict__ Bm, long long bstride, int ldb, const int* __restrict__ perm,
                                    int n, cplx* __restrict__ X, long long xstride, int ldx) {
@@ -300,8 +299,14 @@ cudaError_t lu_factor(cplx* A, long long stride, int n, int lda, int nb, int* ip
         lu_colswap_kernel<<<dim3((n + 127) / 128, nb), 128, 0, st>>>(A, stride, n, lda, k0, nbe, ipiv);
         const int rem = n - k0 - nbe;
         if (rem > 0) {
-            trsm_rows_kernel<<<dim3((rem + 31) / 32, nb), 32, 0, st>>>(A, stride, lda, k0 + nbe, rem, k0, A, stride, lda, k0, nbe, 0);
-            cudaError_t e = zgemm_strided(OP_N, OP_N, rem, rem, nbe, mone,
+            // A21 := A21 * U11^-1 (in place: one tile spans the nbe <= 32 columns).  `tinv` is free until the end of the
+            // factorisation and serves as the scratch of the inverted diagonal block.
+            const long long ustride = (long long)2 * ((n + SOLVE_NB - 1) / SOLVE_NB) * SOLVE_NB * SOLVE_NB;
+            tri_inv_panel_kernel<<<nb, LU_NB, 0, st>>>(A, stride, lda, k0, nbe, tinv, ustride);
+            cudaError_t e = zgemm_strided(OP_N, OP_N, rem, nbe, nbe, one, A + (size_t)(k0 + nbe) * lda + k0, lda, stride,
+                                          tinv, LU_NB, ustride, C(0, 0), A + (size_t)(k0 + nbe) * lda + k0, lda, stride, nb, gscratch, st);
+            if (e != cudaSuccess) return e;
+            e = zgemm_strided(OP_N, OP_N, rem, rem, nbe, mone,
                                           A + (size_t)(k0 + nbe) * lda + k0, lda, stride,
                                           A + (size_t)k0 * lda + (k0 + nbe), lda, stride, one,
                                           A + (size_t)(k0 + nbe) * lda + (k0 + nbe), lda, stride, nb, gscratch, st);
