@@ -28,6 +28,25 @@ def inverse(A):
     return torch.linalg.inv(A), torch.zeros(A.shape[0], dtype=torch.int32)
 
 
+def right_solve(Bm, A):
+    return Bm @ torch.linalg.inv(A), torch.zeros(A.shape[0], dtype=torch.int32)
+
+
+def eig_backward(lam, X, glam, gX, delta):
+    """Batched restatement of torch_eig.py:19-44 (what rcwa_eig_backward computes)."""
+    s = lam.unsqueeze(-2) - lam.unsqueeze(-1)
+    Fc = s / (torch.abs(s) ** 2 + delta)                        # conj(F)
+    n = lam.shape[-1]
+    Fc = Fc * (1 - torch.eye(n, dtype=Fc.dtype))
+    XH = X.transpose(-2, -1).conj()
+    M = torch.zeros_like(X)
+    if gX is not None:
+        M = Fc * (XH @ gX)
+    if glam is not None:
+        M = M + torch.diag_embed(glam)
+    return torch.linalg.inv(XH) @ M @ XH, torch.zeros(X.shape[0], dtype=torch.int32)
+
+
 def zgemm(A, B, opa="N", opb="N", alpha=1.0, beta=0.0, out=None):
     f = {"N": lambda x: x, "T": lambda x: x.transpose(1, 2), "H": lambda x: x.transpose(1, 2).conj()}
     r = alpha * (f[opa](A) @ f[opb](B))
@@ -91,5 +110,7 @@ def cpu_double(monkeypatch):
     import torcwa_b200  # noqa: F401
     host = sys.modules['torcwa_b200.rcwa']      # the module (the package attribute `rcwa` is the class)
     monkeypatch.setattr(host, "_lib", sys.modules[__name__])
+    monkeypatch.setattr(sys.modules['torcwa_b200.autodiff'], "_lib", sys.modules[__name__])
+    monkeypatch.setattr(sys.modules['torcwa_b200.torch_eig'], "_lib", sys.modules[__name__])
     monkeypatch.setattr(host, "_TEST_ALLOW_NON_CUDA", True)
     return host

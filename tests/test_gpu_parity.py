@@ -191,3 +191,33 @@ def test_order15_energy_conservation_lossless_cell():
             tot += (s.abs().to(torch.float64) ** 2).sum(dim=1)
     print("R + T per wavelength:", tot.tolist())
     assert float((tot - 1.0).abs().max()) <= 1e-6
+
+
+def test_differentiable_pipeline_gradients_vs_reference_autograd(golden_dir):
+    """BASELINE config 5's shape of work (forward + autograd backward through the whole layer pipeline) on the CUDA
+    kernels: figure of merit and its gradients w.r.t. the density grid and the thickness == the unmodified
+    reference's CPU autograd (tests/golden/autograd_o3.npz).  Also as a batch of two identical points."""
+    import torcwa_b200
+    from oracle.autograd_case import CASE, fom
+    g = np.load(os.path.join(golden_dir, "autograd_o3.npz"))
+    dev = torch.device("cuda:0")
+    rho = torch.from_numpy(g["rho"]).to(dev).requires_grad_(True)
+    thick = torch.tensor(CASE["thickness"], dtype=torch.float64, device=dev, requires_grad=True)
+    sim = torcwa_b200.rcwa(freq=torch.tensor(1.0 / CASE["lam"], dtype=torch.float64), order=CASE["order"], L=CASE["L"],
+                           dtype=torch.complex128, device=dev)
+    value = fom(sim, rho, thick)
+    value.backward()
+    assert abs(float(value.detach()) - float(g["fom"])) <= 1e-10 * abs(float(g["fom"]))
+    gr = rho.grad.cpu().numpy()
+    print("grad_rho rel err:", np.linalg.norm(gr - g["grad_rho"]) / np.linalg.norm(g["grad_rho"]))
+    assert np.linalg.norm(gr - g["grad_rho"]) <= 1e-8 * np.linalg.norm(g["grad_rho"])
+    assert abs(float(thick.grad) - float(g["grad_thickness"])) <= 1e-8 * abs(float(g["grad_thickness"]))
+    # batched: two design points, each with its own density -> per-point gradients
+    rho2 = torch.from_numpy(g["rho"]).to(dev)[None].repeat(2, 1, 1).requires_grad_(True)
+    sim2 = torcwa_b200.rcwa(freq=torch.full((2,), 1.0 / CASE["lam"], dtype=torch.float64), order=CASE["order"], L=CASE["L"],
+                            dtype=torch.complex128, device=dev)
+    v2 = fom(sim2, rho2, torch.tensor(CASE["thickness"], dtype=torch.float64, device=dev))
+    v2.backward()
+    assert abs(float(v2.detach()) - 2 * float(g["fom"])) <= 1e-9 * abs(float(g["fom"]))
+    for b in range(2):
+        assert np.linalg.norm(rho2.grad[b].cpu().numpy() - g["grad_rho"]) <= 1e-8 * np.linalg.norm(g["grad_rho"])

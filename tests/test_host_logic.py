@@ -93,3 +93,20 @@ def test_finished_simulation_is_freed_by_refcount(cpu_double):
         assert ref() is None
     finally:
         gc.enable()
+
+
+def test_differentiable_pipeline_matches_reference_autograd(cpu_double, golden_dir):
+    """Gradients of a topology-optimisation style figure of merit w.r.t. the density grid and the layer thickness:
+    torcwa_b200's differentiable path (autograd wrappers around the C-ABI ops, here the CPU double) == the unmodified
+    reference's autograd (tests/golden/autograd_o3.npz, tools/make_golden_autograd.py)."""
+    from oracle.autograd_case import CASE, fom
+    g = np.load(os.path.join(golden_dir, "autograd_o3.npz"))
+    rho = torch.from_numpy(g["rho"]).clone().requires_grad_(True)
+    thick = torch.tensor(CASE["thickness"], dtype=torch.float64, requires_grad=True)
+    sim = cpu_double.rcwa(freq=torch.tensor(1.0 / CASE["lam"], dtype=torch.float64), order=CASE["order"], L=CASE["L"],
+                          dtype=torch.complex128, device=CPU)
+    value = fom(sim, rho, thick)
+    value.backward()
+    assert abs(float(value.detach()) - float(g["fom"])) <= 1e-10 * abs(float(g["fom"]))
+    assert np.linalg.norm(rho.grad.numpy() - g["grad_rho"]) <= 1e-8 * np.linalg.norm(g["grad_rho"])
+    assert abs(float(thick.grad) - float(g["grad_thickness"])) <= 1e-8 * abs(float(g["grad_thickness"]))

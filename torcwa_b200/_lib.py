@@ -183,6 +183,13 @@ def lu_solve_right(LU, perm, tinv, Bm):
     return X
 
 
+def right_solve(Bm, A):
+    """X = Bm @ inv(A) ([nb,r,n], [nb,n,n]); returns (X, info). A is preserved."""
+    LU = A.clone()
+    perm, info, tinv = lu_factor_(LU)
+    return lu_solve_right(LU, perm, tinv, Bm), info
+
+
 def inverse(A):
     """inv(A) for [nb,n,n] via X*A = I; returns (inv, info). A is preserved."""
     LU = A.clone()

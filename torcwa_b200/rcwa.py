@@ -22,6 +22,7 @@ import weakref
 import torch
 
 from . import _lib
+from . import autodiff
 from ._bd import bd, bd_diag, bd_inv, bd_mul, sqrt_upper, v_matrix
 
 # The reference's pi is mistyped (torcwa/rcwa.py:5); omega = 2*pi*freq enters every layer phase, so
@@ -103,6 +104,7 @@ class rcwa:
         self.kz_norm, self.E_eigvec, self.H_eigvec = [], [], []
         self.Cf, self.Cb = [], []
         self.layer_S11, self.layer_S21, self.layer_S12, self.layer_S22 = [], [], [], []
+        self._diff = False         # a layer asked for gradients: the cascade runs on the differentiable primitives
         self._layers = []          # internal: per layer [S11, S21] complex128 [B,n,n]
         self.eig_info = []         # per patterned layer: int32 [B] status of the eigensolver
 
@@ -211,7 +213,7 @@ class rcwa:
             return True
         return self._batched and v.dim() == 1 and v.shape[0] == self._B     # per-point scalar (new)
 
-    def _conv(self, grid):
+    def _conv(self, grid, differentiable=False):
         """Convolution matrix of a sampled cell, [B,N,N] complex128 (CUDA stage 1)."""
         grid = torch.as_tensor(grid, device=self._device)
         want_real = torch.float32 if self._dtype == torch.complex64 else torch.float64
@@ -222,6 +224,8 @@ class rcwa:
             raise ValueError('batched material must have leading dimension %d' % self._B)
         if grid.shape[-2] < 4 * self.order[0] + 1 or grid.shape[-1] < 4 * self.order[1] + 1:
             raise IndexError('material grid too coarse for the Fourier order (needs >= 4*order+1 samples)')
+        if differentiable:
+            return autodiff.ConvMat.apply(grid, self.order[0], self.order[1], self._B)
         return _lib.convmat(grid, self.order[0], self.order[1], nb=self._B)
 
     def add_layer(self, thickness, eps=1., mu=1.):
@@ -233,12 +237,31 @@ class rcwa:
         thick = (thick.expand(B) if thick.numel() == 1 else thick).contiguous()
         omega = (self._omega64.expand(B) if self._omega64.numel() == 1 else self._omega64).contiguous()
 
+        diff = any(isinstance(v, torch.Tensor) and v.requires_grad for v in (eps, mu, thickness))
+        if diff:
+            self._diff = True
         if he and hm:
-            S11, S21, kz = self._homogeneous_layer(self._b(eps), self._b(mu), omega, thick)
+            S11, S21, kz = self._homogeneous_layer(self._b(eps), self._b(mu), omega, thick, diff)
             if self._store:
                 self.eps_conv.append(self._pub(self._b(eps)[:, None, None] * torch.eye(N, dtype=_C, device=self._device)))
                 self.mu_conv.append(self._pub(self._b(mu)[:, None, None] * torch.eye(N, dtype=_C, device=self._device)))
                 self.E_eigvec.append(self._pub(torch.eye(2 * N, dtype=_C, device=self._device).expand(B, -1, -1)))
+        elif diff:
+            # gradients requested: same algebra on the differentiable primitives (torcwa_b200/autodiff.py)
+            eyeN = torch.eye(N, dtype=_C, device=self._device)
+            E = self._b(eps)[:, None, None] * eyeN if he else self._conv(eps, differentiable=True)
+            if hm:
+                mu_s = self._b(mu)
+                Mc, nu = mu_s[:, None, None] * eyeN, (1 / mu_s)[:, None, None] * eyeN
+            else:
+                Mc = self._conv(mu, differentiable=True)
+                nu = autodiff.inverse(Mc)
+            S11, S21, kz, W, P, Q = autodiff.patterned_layer(E, Mc, nu, kx, ky, self._Vf_inv, omega, thick)
+            self.eig_info.append(torch.zeros(B, dtype=torch.int32, device=self._device))   # Eig raises on non-convergence
+            if self._store:
+                self.eps_conv.append(self._pub(E)); self.mu_conv.append(self._pub(Mc))
+                self.P.append(self._pub(P)); self.Q.append(self._pub(Q))
+                self.E_eigvec.append(self._pub(W))
         else:
             E = self._b(eps)[:, None, None] * torch.eye(N, dtype=_C, device=self._device) if he else self._conv(eps)
             E = E.contiguous()
@@ -277,7 +300,7 @@ class rcwa:
             self.layer_S11.append(s11); self.layer_S21.append(s21)
             self.layer_S12.append(s21); self.layer_S22.append(s11)      # single-layer symmetry
 
-    def _homogeneous_layer(self, eps, mu, omega, thick):
+    def _homogeneous_layer(self, eps, mu, omega, thick, diff=False):
         """Analytic modes (rcwa.py:1206-1222: W = I, kz = conj-branch sqrt) pushed through the
         minimal layer-S algebra in 2x2-block form; returns dense S11, S21 and kz [B,2N]."""
         kx, ky = self._kx, self._ky
@@ -291,13 +314,16 @@ class rcwa:
         Tp = bd_mul(onep, bd_inv(onep + bd_mul(Bm, onem)))        # R+ M+^-1
         Tm = bd_mul(-onem, bd_inv(onem + bd_mul(Bm, onep)))       # R- M-^-1
         eye = bd_diag(torch.ones_like(kz1))
-        S11 = _lib.blockdiag_dense((Tp + Tm).contiguous())
-        S21 = _lib.blockdiag_dense((Tp - Tm - eye).contiguous())
+        dense = autodiff.blockdiag_dense if diff else _lib.blockdiag_dense
+        S11 = dense((Tp + Tm).contiguous())
+        S21 = dense((Tp - Tm - eye).contiguous())
         return S11, S21, torch.cat((kz1, kz1), dim=1)
 
     # ------------------------------------------------------------------ cascade (rcwa.py:173-211)
     def solve_global_smatrix(self):
         B, n = self._B, 2 * self.order_N
+        if self._diff:
+            return self._solve_global_smatrix_differentiable()
         if self.layer_N > 0:
             s11, s21 = self._layers[0]
             S = [s11, s21, s21, s11]
@@ -315,6 +341,27 @@ class rcwa:
         self._S = S
         self.S = [self._pub(s) for s in S]
         self.C = [[], []]      # mode-coefficient propagation is row (f1) of the scope table: not built
+
+    def _solve_global_smatrix_differentiable(self):
+        """The same left fold (rcwa.py:173-211) on the differentiable star product."""
+        B, n = self._B, 2 * self.order_N
+        if self.layer_N > 0:
+            s11, s21 = self._layers[0]
+            S = [s11, s21, s21, s11]
+            for i in range(1, self.layer_N):
+                n11, n21 = self._layers[i]
+                S = autodiff.redheffer(S, [n11, n21, n21, n11])
+        else:
+            eye = torch.eye(n, dtype=_C, device=self._device).expand(B, -1, -1).contiguous()
+            zero = torch.zeros((B, n, n), dtype=_C, device=self._device)
+            S = [eye, zero, zero.clone(), eye.clone()]
+        if hasattr(self, 'Sin'):
+            S = autodiff.redheffer([autodiff.blockdiag_dense(s) for s in self._Sin], S)
+        if hasattr(self, 'Sout'):
+            S = autodiff.redheffer(S, [autodiff.blockdiag_dense(s) for s in self._Sout])
+        self._S = S
+        self.S = [self._pub(s) for s in S]
+        self.C = [[], []]
 
     # ------------------------------------------------------------------ readout (rcwa.py:300-524)
     def _matching_indices(self, orders):
