@@ -110,3 +110,19 @@ def test_differentiable_pipeline_matches_reference_autograd(cpu_double, golden_d
     assert abs(float(value.detach()) - float(g["fom"])) <= 1e-10 * abs(float(g["fom"]))
     assert np.linalg.norm(rho.grad.numpy() - g["grad_rho"]) <= 1e-8 * np.linalg.norm(g["grad_rho"])
     assert abs(float(thick.grad) - float(g["grad_thickness"])) <= 1e-8 * abs(float(g["grad_thickness"]))
+
+
+def test_diffraction_angle_and_return_layer_match_reference(cpu_double, golden_dir):
+    g = np.load(os.path.join(golden_dir, "misc_stack_o3.npz"))
+    sim = C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, **kw), C.CASES["stack_o3"], torch.complex128)
+    orders = g["orders"].tolist()
+    for layer in ("input", "output"):
+        for unit in ("radian", "degree"):
+            inc, azi = sim.diffraction_angle(orders, layer=layer, unit=unit)
+            np.testing.assert_allclose(inc.numpy(), g["inc_%s_%s" % (layer, unit)], rtol=0, atol=1e-13)
+            np.testing.assert_allclose(azi.numpy(), g["azi_%s_%s" % (layer, unit)], rtol=0, atol=1e-13)
+    e, m = sim.return_layer(0, nx=20, ny=26)
+    assert np.abs(e.numpy() - g["eps_rec"]).max() <= 1e-12 * np.abs(g["eps_rec"]).max()
+    assert np.abs(m.numpy() - g["mu_rec"]).max() <= 1e-12
+    with pytest.warns(UserWarning):
+        sim.diffraction_angle(orders, layer="sideways")

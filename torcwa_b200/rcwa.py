@@ -363,6 +363,60 @@ class rcwa:
         self.S = [self._pub(s) for s in S]
         self.C = [[], []]
 
+    # ------------------------------------------------------------------ small utilities (rcwa.py:214-298)
+    def diffraction_angle(self, orders, *, layer='output', unit='radian'):
+        """Inclination and azimuth of the selected diffraction orders in the input or output half space
+        (rcwa.py:214-262).  Unbatched: tensors of shape [len(orders)]; batched: [B, len(orders)]."""
+        orders = torch.as_tensor(orders, dtype=torch.int64, device=self._device).reshape([-1, 2])
+        if layer in ['i', 'in', 'input']:
+            layer = 'input'
+        elif layer in ['o', 'out', 'output']:
+            layer = 'output'
+        else:
+            warnings.warn('Invalid layer. Set as output layer.', UserWarning)
+            layer = 'output'
+        if unit in ['r', 'rad', 'radian']:
+            unit = 'radian'
+        elif unit in ['d', 'deg', 'degree']:
+            unit = 'degree'
+        else:
+            warnings.warn('Invalid unit. Set as radian.', UserWarning)
+            unit = 'radian'
+        idx = self._matching_indices(orders)
+        eps, mu = (self.eps_in, self.mu_in) if layer == 'input' else (self.eps_out, self.mu_out)
+        kx, ky = self._kx[:, idx], self._ky[:, idx]
+        kt = torch.sqrt(kx ** 2 + ky ** 2)
+        kz = torch.sqrt((self._b(eps) * self._b(mu))[:, None] - kx ** 2 - ky ** 2)
+        inc = torch.atan2(kt.real, kz.real)
+        azi = torch.atan2(ky.real, kx.real)
+        if unit == 'degree':
+            inc, azi = (180. / pi) * inc, (180. / pi) * azi
+        inc, azi = inc.to(self._rdtype), azi.to(self._rdtype)
+        return (inc, azi) if self._batched else (inc[0], azi[0])
+
+    def return_layer(self, layer_num, nx=100, ny=100):
+        """eps and mu of a layer on an nx x ny grid, recovered from the truncated Fourier series held in the
+        convolution matrices (rcwa.py:264-298): coefficient (i, j), |i| <= 2ox, |j| <= 2oy, is read from the first
+        column (non-negative index) or first row (negative index) of the Toeplitz matrix.  Needs the stored
+        convolution matrices (store_intermediates=True for batched simulations)."""
+        if not self.eps_conv:
+            raise RuntimeError('return_layer needs the stored convolution matrices: construct with store_intermediates=True')
+        ox, oy = int(self.order[0]), int(self.order[1])
+        wy = 2 * oy + 1
+        i = torch.arange(-2 * ox, 2 * ox + 1, device=self._device)[:, None].expand(4 * ox + 1, 4 * oy + 1)
+        j = torch.arange(-2 * oy, 2 * oy + 1, device=self._device)[None, :].expand(4 * ox + 1, 4 * oy + 1)
+        ip, jp = torch.clamp(i, min=0), torch.clamp(j, min=0)         # contribution to the row index
+        im, jm = torch.clamp(-i, min=0), torch.clamp(-j, min=0)       # contribution to the column index
+        row, col = ip * wy + jp, im * wy + jm
+        out = []
+        for conv in (self.eps_conv[layer_num], self.mu_conv[layer_num]):
+            c = conv if self._batched else conv[None]
+            fftgrid = torch.zeros((c.shape[0], nx, ny), dtype=self._dtype, device=self._device)
+            fftgrid[:, i % nx, j % ny] = c[:, row, col]
+            rec = torch.fft.ifftn(fftgrid, dim=(-2, -1)) * nx * ny
+            out.append(rec if self._batched else rec[0])
+        return out[0], out[1]
+
     # ------------------------------------------------------------------ readout (rcwa.py:300-524)
     def _matching_indices(self, orders):
         # clamps out-of-range orders to the truncation edge, in place like the reference (rcwa.py:1115-1122)
