@@ -221,3 +221,25 @@ def test_differentiable_pipeline_gradients_vs_reference_autograd(golden_dir):
     assert abs(float(v2.detach()) - 2 * float(g["fom"])) <= 1e-9 * abs(float(g["fom"]))
     for b in range(2):
         assert np.linalg.norm(rho2.grad[b].cpu().numpy() - g["grad_rho"]) <= 1e-8 * np.linalg.norm(g["grad_rho"])
+
+
+def test_sources_and_fields_vs_reference(golden_dir):
+    """Field reconstruction (scope row f1) on the CUDA kernels: lazily built mode coefficients + field_xz / field_yz /
+    field_xy in the half spaces, patterned and homogeneous layers, forward xy and backward ps sources == the unmodified
+    reference (tests/golden/fields_stack_o3.npz).  Fields do not depend on the eigenvector basis, so this also checks
+    that our eigenvectors (different order / normalisation than LAPACK's) are used consistently."""
+    import torcwa_b200
+    from oracle.fields_case import build, SOURCES, planes
+    g = np.load(os.path.join(golden_dir, "fields_stack_o3.npz"))
+    sim = build(lambda **kw: torcwa_b200.rcwa(device=torch.device("cuda:0"), **kw))
+    worst = 0.0
+    for sname, setter in SOURCES.items():
+        setter(sim)
+        for pname, getter in planes().items():
+            E, H = getter(sim)
+            got = np.stack([t.cpu().numpy() for t in E + H])
+            ref = g["%s_%s" % (sname, pname)]
+            err = np.abs(got - ref).max() / np.abs(ref).max()
+            worst = max(worst, err)
+            assert err <= 1e-8, (sname, pname, err)
+    print("fields: worst relative error vs reference", worst)

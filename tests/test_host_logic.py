@@ -126,3 +126,29 @@ def test_diffraction_angle_and_return_layer_match_reference(cpu_double, golden_d
     assert np.abs(m.numpy() - g["mu_rec"]).max() <= 1e-12
     with pytest.warns(UserWarning):
         sim.diffraction_angle(orders, layer="sideways")
+
+
+def test_sources_and_fields_match_reference(cpu_double, golden_dir):
+    """source_planewave / source_fourier (xy and ps notation, forward and backward) and field_xz / field_yz / field_xy
+    in the half spaces and inside patterned and homogeneous layers == the unmodified reference
+    (tests/golden/fields_stack_o3.npz, tools/make_golden_fields.py).  The mode coefficients are built lazily from the
+    stored layer intermediates; the fused forward path is untouched."""
+    from oracle.fields_case import build, SOURCES, planes
+    import sys
+    import torcwa_b200.fields as F
+    F._lib = sys.modules["fake_lib"]
+    try:
+        g = np.load(os.path.join(golden_dir, "fields_stack_o3.npz"))
+        sim = build(lambda **kw: cpu_double.rcwa(device=CPU, **kw))
+        for sname, setter in SOURCES.items():
+            setter(sim)
+            for pname, getter in planes().items():
+                E, H = getter(sim)
+                got = np.stack([t.numpy() for t in E + H])
+                ref = g["%s_%s" % (sname, pname)]
+                err = np.abs(got - ref).max() / np.abs(ref).max()
+                assert err <= 1e-9, (sname, pname, err)
+        assert len(sim.Cf) == 3 and len(sim.C[0]) == 3 and sim.H_eigvec[0].shape == (98, 98)
+    finally:
+        from torcwa_b200 import _lib as real
+        F._lib = real

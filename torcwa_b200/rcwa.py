@@ -104,6 +104,8 @@ class rcwa:
         self.kz_norm, self.E_eigvec, self.H_eigvec = [], [], []
         self.Cf, self.Cb = [], []
         self.layer_S11, self.layer_S21, self.layer_S12, self.layer_S22 = [], [], [], []
+        self._modes_src = []       # per layer (only when intermediates are stored): what the mode coefficients / fields need
+        self._modes_ready = False
         self._diff = False         # a layer asked for gradients: the cascade runs on the differentiable primitives
         self._layers = []          # internal: per layer [S11, S21] complex128 [B,n,n]
         self.eig_info = []         # per patterned layer: int32 [B] status of the eigensolver
@@ -241,8 +243,10 @@ class rcwa:
         if diff:
             self._diff = True
         if he and hm:
-            S11, S21, kz = self._homogeneous_layer(self._b(eps), self._b(mu), omega, thick, diff)
+            S11, S21, kz, Qbd = self._homogeneous_layer(self._b(eps), self._b(mu), omega, thick, diff)
             if self._store:
+                self._modes_src.append(dict(W=None, Q=Qbd.detach(), kz=kz.detach(), E=self._b(eps).detach(), M=self._b(mu).detach(),
+                                            thick=thick.detach(), omega=omega))
                 self.eps_conv.append(self._pub(self._b(eps)[:, None, None] * torch.eye(N, dtype=_C, device=self._device)))
                 self.mu_conv.append(self._pub(self._b(mu)[:, None, None] * torch.eye(N, dtype=_C, device=self._device)))
                 self.E_eigvec.append(self._pub(torch.eye(2 * N, dtype=_C, device=self._device).expand(B, -1, -1)))
@@ -262,6 +266,8 @@ class rcwa:
                 self.eps_conv.append(self._pub(E)); self.mu_conv.append(self._pub(Mc))
                 self.P.append(self._pub(P)); self.Q.append(self._pub(Q))
                 self.E_eigvec.append(self._pub(W))
+                self._modes_src.append(dict(W=W.detach(), Q=Q.detach(), kz=kz.detach(), E=E.detach(), M=Mc.detach(),
+                                            thick=thick.detach(), omega=omega))
         else:
             E = self._b(eps)[:, None, None] * torch.eye(N, dtype=_C, device=self._device) if he else self._conv(eps)
             E = E.contiguous()
@@ -279,6 +285,7 @@ class rcwa:
                 self.eps_conv.append(self._pub(E))
                 self.mu_conv.append(self._pub(M if M is not None else self._b(mu)[:, None, None] * torch.eye(N, dtype=_C, device=self._device)))
                 self.P.append(self._pub(P)); self.Q.append(self._pub(Q))
+            E_keep, M_keep = (E, M if M is not None else self._b(mu)) if self._store else (None, None)
             del E, M
             A = _lib.zgemm(P, Q)
             del P                                  # free early: a batch chunk is sized by its peak footprint
@@ -287,10 +294,10 @@ class rcwa:
             self.eig_info.append(info)
             kz = _lib.kz_branch(lam)
             S11, S21, info_s = _lib.layer_smatrix(W, kz, Q, self._Vf_inv, omega, thick)
-            del Q
             if self._store:
                 self.E_eigvec.append(self._pub(W))
-            del W
+                self._modes_src.append(dict(W=W, Q=Q, kz=kz, E=E_keep, M=M_keep, thick=thick, omega=omega))
+            del Q, W
         self.kz_norm.append(self._pub(kz))
         self.layer_N += 1
         self.thickness.append(thickness)
@@ -317,7 +324,7 @@ class rcwa:
         dense = autodiff.blockdiag_dense if diff else _lib.blockdiag_dense
         S11 = dense((Tp + Tm).contiguous())
         S21 = dense((Tp - Tm - eye).contiguous())
-        return S11, S21, torch.cat((kz1, kz1), dim=1)
+        return S11, S21, torch.cat((kz1, kz1), dim=1), Q
 
     # ------------------------------------------------------------------ cascade (rcwa.py:173-211)
     def solve_global_smatrix(self):
@@ -340,7 +347,8 @@ class rcwa:
             S, _ = _lib.redheffer(S, [_lib.blockdiag_dense(s.contiguous()) for s in self._Sout])
         self._S = S
         self.S = [self._pub(s) for s in S]
-        self.C = [[], []]      # mode-coefficient propagation is row (f1) of the scope table: not built
+        self.C = [[], []]      # filled on demand (fields.ensure_modes): the fused cascade does not carry mode coefficients
+        self._modes_ready = False
 
     def _solve_global_smatrix_differentiable(self):
         """The same left fold (rcwa.py:173-211) on the differentiable star product."""
@@ -416,6 +424,32 @@ class rcwa:
             rec = torch.fft.ifftn(fftgrid, dim=(-2, -1)) * nx * ny
             out.append(rec if self._batched else rec[0])
         return out[0], out[1]
+
+    # ------------------------------------------------------------------ sources and fields (rcwa.py:526-1112)
+    def source_planewave(self, *, amplitude=[1., 0.], direction='forward', notation='xy'):
+        """Plane-wave source in the zeroth order (rcwa.py:526-537)."""
+        self.source_fourier(amplitude=amplitude, orders=[0, 0], direction=direction, notation=notation)
+
+    def source_fourier(self, *, amplitude, orders, direction='forward', notation='xy'):
+        """Source given by amplitudes at selected diffraction orders (rcwa.py:539-596)."""
+        from . import fields
+        fields.source_fourier(self, amplitude, orders, direction, notation)
+
+    def field_xz(self, x_axis, z_axis, y):
+        """[Ex, Ey, Ez], [Hx, Hy, Hz] on the plane y = const (rcwa.py:598-775); tensors of shape [len(x), len(z)]."""
+        from . import fields
+        return fields.field_plane(self, 'xz', x_axis, z_axis, y)
+
+    def field_yz(self, y_axis, z_axis, x):
+        """[Ex, Ey, Ez], [Hx, Hy, Hz] on the plane x = const (rcwa.py:777-957); tensors of shape [len(y), len(z)]."""
+        from . import fields
+        return fields.field_plane(self, 'yz', y_axis, z_axis, x)
+
+    def field_xy(self, layer_num, x_axis, y_axis, z_prop=0.):
+        """[Ex, Ey, Ez], [Hx, Hy, Hz] on a plane z = const inside layer `layer_num` (-1: input, layer_N: output half
+        space), z_prop from the layer's lower boundary (rcwa.py:959-1112); tensors of shape [len(x), len(y)]."""
+        from . import fields
+        return fields.field_xy(self, layer_num, x_axis, y_axis, z_prop)
 
     # ------------------------------------------------------------------ readout (rcwa.py:300-524)
     def _matching_indices(self, orders):
