@@ -152,3 +152,15 @@ def test_sources_and_fields_match_reference(cpu_double, golden_dir):
     finally:
         from torcwa_b200 import _lib as real
         F._lib = real
+
+
+def test_pinv_instability_metrics_are_reported(cpu_double):
+    """avoid_Pinv_instability=True (rcwa.py:1249-1262): one metric per patterned layer, at round-off level for a
+    well-conditioned cell; the S-parameters are the same as without the flag (this path never forms P^-1)."""
+    case = C.CASES["ex1_o3"]
+    a = C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, avoid_Pinv_instability=True, **kw), case, torch.complex128)
+    b = C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, **kw), case, torch.complex128)
+    assert len(a.Pinv_instability) == 1 and len(a.Qinv_instability) == 1
+    assert 0.0 <= float(a.Pinv_instability[0]) < 1e-8 and 0.0 <= float(a.Qinv_instability[0]) < 1e-8
+    assert b.Pinv_instability is None
+    assert np.abs(C.probe(a) - C.probe(b)).max() == 0.0

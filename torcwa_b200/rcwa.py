@@ -287,6 +287,8 @@ class rcwa:
                 self.P.append(self._pub(P)); self.Q.append(self._pub(Q))
             E_keep, M_keep = (E, M if M is not None else self._b(mu)) if self._store else (None, None)
             del E, M
+            if self.avoid_Pinv_instability:
+                self._pinv_metrics(P, Q)
             A = _lib.zgemm(P, Q)
             del P                                  # free early: a batch chunk is sized by its peak footprint
             lam, W, info = _lib.eig(A)
@@ -306,6 +308,21 @@ class rcwa:
             s11, s21 = self._pub(S11), self._pub(S21)
             self.layer_S11.append(s11); self.layer_S21.append(s21)
             self.layer_S12.append(s21); self.layer_S22.append(s11)      # single-layer symmetry
+
+    def _pinv_metrics(self, P, Q):
+        """`avoid_Pinv_instability=True` (rcwa.py:1249-1262): the reference measures how badly P (and Q) invert,
+        max|P P^-1 - I| and max|P^-1 P - I|, to choose between H = P^-1 W Kz and H = Q W Kz^-1.  This path always
+        uses the second, inverse-free form, so the numbers are reported for the user only.  (The reference's Q
+        metric evaluates Q Q^-1 twice, :1253-1254; one evaluation is the same number.)"""
+        eye = torch.eye(P.shape[-1], dtype=_C, device=self._device)
+        Pi, _ = _lib.inverse(P)
+        m = torch.maximum((_lib.zgemm(P, Pi) - eye).abs().amax(dim=(1, 2)), (_lib.zgemm(Pi, P) - eye).abs().amax(dim=(1, 2)))
+        del Pi
+        Qi, _ = _lib.inverse(Q)
+        q = (_lib.zgemm(Q, Qi) - eye).abs().amax(dim=(1, 2))
+        del Qi
+        self.Pinv_instability.append((m if self._batched else m[0]).to(self._rdtype))
+        self.Qinv_instability.append((q if self._batched else q[0]).to(self._rdtype))
 
     def _homogeneous_layer(self, eps, mu, omega, thick, diff=False):
         """Analytic modes (rcwa.py:1206-1222: W = I, kz = conj-branch sqrt) pushed through the
