@@ -164,3 +164,17 @@ def test_pinv_instability_metrics_are_reported(cpu_double):
     assert 0.0 <= float(a.Pinv_instability[0]) < 1e-8 and 0.0 <= float(a.Qinv_instability[0]) < 1e-8
     assert b.Pinv_instability is None
     assert np.abs(C.probe(a) - C.probe(b)).max() == 0.0
+
+
+def test_numerical_failure_is_raised_once_at_solve(cpu_double, monkeypatch):
+    """A non-zero info word of any stage surfaces as torch.linalg.LinAlgError when the global S-matrix is complete."""
+    import fake_lib
+    real_eig = fake_lib.eig
+
+    def failing_eig(A):
+        w, V, info = real_eig(A)
+        info = info.clone(); info[0] = 7
+        return w, V, info
+    monkeypatch.setattr(fake_lib, "eig", failing_eig)
+    with pytest.raises(torch.linalg.LinAlgError, match="eigendecomposition"):
+        C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, **kw), C.CASES["ex1_o3"], torch.complex128)

@@ -5,6 +5,7 @@ fails, this module raises -- it never reroutes work to another implementation.
 """
 import ctypes
 import os
+import threading
 
 import torch
 
@@ -208,12 +209,11 @@ def pq_assemble(eta, E, kx, ky, mu_scalar=None, Mc=None, nu=None):
     return P, Q
 
 
-_host_flag = None
+_tls = threading.local()       # pinned polling flags of rcwa_eig: one buffer per host thread (calls may run concurrently)
 
 
 def eig(A):
     """A [nb,n,n] (destroyed) -> (w [nb,n], V [nb,n,n], info [nb])."""
-    global _host_flag
     lib = load()
     _c128(A, "A")
     nb, n = A.shape[0], A.shape[1]
@@ -222,10 +222,10 @@ def eig(A):
     info = torch.zeros((nb,), dtype=torch.int32, device=A.device)
     nbytes = lib.rcwa_eig_workspace_bytes(n, nb)
     ws = _ws(nbytes, A.device)
-    if _host_flag is None:
-        _host_flag = torch.zeros(16, dtype=torch.int32).pin_memory()
+    if getattr(_tls, "host_flag", None) is None:
+        _tls.host_flag = torch.zeros(16, dtype=torch.int32).pin_memory()
     _check(lib.rcwa_eig(_ptr(A), n, nb, _ptr(w), _ptr(V), _ptr(ws), nbytes, _ptr(info),
-                        ctypes.c_void_p(_host_flag.data_ptr()), _stream()), "rcwa_eig")
+                        ctypes.c_void_p(_tls.host_flag.data_ptr()), _stream()), "rcwa_eig")
     global last_eig_stats
     stats = torch.empty((nb, 4), dtype=torch.int32, device=A.device)
     _check(lib.rcwa_eig_stats(_ptr(ws), n, nb, _ptr(stats), _stream()), "rcwa_eig_stats")

@@ -109,6 +109,7 @@ class rcwa:
         self._diff = False         # a layer asked for gradients: the cascade runs on the differentiable primitives
         self._layers = []          # internal: per layer [S11, S21] complex128 [B,n,n]
         self.eig_info = []         # per patterned layer: int32 [B] status of the eigensolver
+        self._status = []          # (what, int32 [B] device tensor) of every factorisation / eigensolve: checked lazily
 
     # ------------------------------------------------------------------ helpers
     def _b(self, v):
@@ -272,6 +273,7 @@ class rcwa:
             E = self._b(eps)[:, None, None] * torch.eye(N, dtype=_C, device=self._device) if he else self._conv(eps)
             E = E.contiguous()
             eta, info_e = _lib.inverse(E)
+            self._status.append(('inverse of the permittivity convolution matrix (layer %d)' % self.layer_N, info_e))
             if hm:
                 P, Q = _lib.pq_assemble(eta, E, kx, ky, mu_scalar=self._b(mu).contiguous())
                 M = None
@@ -294,8 +296,10 @@ class rcwa:
             lam, W, info = _lib.eig(A)
             del A
             self.eig_info.append(info)
+            self._status.append(('eigendecomposition (layer %d): QR iteration did not converge' % self.layer_N, info))
             kz = _lib.kz_branch(lam)
             S11, S21, info_s = _lib.layer_smatrix(W, kz, Q, self._Vf_inv, omega, thick)
+            self._status.append(('layer S-matrix (layer %d): singular coupling matrix' % self.layer_N, info_s))
             if self._store:
                 self.E_eigvec.append(self._pub(W))
                 self._modes_src.append(dict(W=W, Q=Q, kz=kz, E=E_keep, M=M_keep, thick=thick, omega=omega))
@@ -353,19 +357,37 @@ class rcwa:
             S = [s11, s21, s21, s11]
             for i in range(1, self.layer_N):
                 n11, n21 = self._layers[i]
-                S, _ = _lib.redheffer(S, [n11, n21, n21, n11])
+                S, info_r = _lib.redheffer(S, [n11, n21, n21, n11])
+                self._status.append(('star product with layer %d' % i, info_r))
         else:
             eye = torch.eye(n, dtype=_C, device=self._device).expand(B, -1, -1).contiguous()
             zero = torch.zeros((B, n, n), dtype=_C, device=self._device)
             S = [eye, zero, zero.clone(), eye.clone()]
         if hasattr(self, 'Sin'):
-            S, _ = _lib.redheffer_bdleft(self._Sin, S)          # Sin is four-diagonal: O(n^2) instead of 6 GEMMs
+            S, info_r = _lib.redheffer_bdleft(self._Sin, S)     # Sin is four-diagonal: O(n^2) instead of 6 GEMMs
+            self._status.append(('star product with the input half space', info_r))
         if hasattr(self, 'Sout'):
-            S, _ = _lib.redheffer(S, [_lib.blockdiag_dense(s.contiguous()) for s in self._Sout])
+            S, info_r = _lib.redheffer(S, [_lib.blockdiag_dense(s.contiguous()) for s in self._Sout])
+            self._status.append(('star product with the output half space', info_r))
+        self._check_status()
         self._S = S
         self.S = [self._pub(s) for s in S]
         self.C = [[], []]      # filled on demand (fields.ensure_modes): the fused cascade does not carry mode coefficients
         self._modes_ready = False
+
+    def _check_status(self):
+        """Numerical status of everything enqueued so far: ONE device-to-host read of the per-matrix info words
+        (the reference's torch.linalg.eig / inv raise LinAlgError eagerly; here the kernels only record a status
+        and the host looks at it once, when the global S-matrix is complete)."""
+        if not self._status:
+            return
+        worst = torch.stack([i.to(self._device).abs().max() for _, i in self._status])
+        if int(worst.max()) != 0:
+            k = int(torch.nonzero(worst)[0])
+            what, info = self._status[k]
+            raise torch.linalg.LinAlgError('torcwa_b200: %s, batch entries %s (info = %s)'
+                                           % (what, torch.nonzero(info).flatten().tolist(), info[info != 0].tolist()))
+        self._status = []
 
     def _solve_global_smatrix_differentiable(self):
         """The same left fold (rcwa.py:173-211) on the differentiable star product."""
