@@ -1,21 +1,25 @@
 // Stage 2: batched complex128 non-Hermitian eigendecomposition, entirely on the device.
 // Replaces torch.linalg.eig in Eig.forward (/root/reference/torcwa/torch_eig.py:11-17; LAPACK
-// zgeev on CPU, cuSOLVER/MAGMA hybrid on CUDA).  Four phases per batch of matrices:
+// zgeev on CPU, cuSOLVER/MAGMA hybrid on CUDA).  Three phases per batch of matrices:
 //
 //  (1) Blocked Householder Hessenberg reduction  A = Z H Z^H  (hess.cu): per column one read-only
 //      streaming mat-vec over the trailing matrix (the HBM-bound kernel of the stage, exactly the
 //      algorithmic 16 n^3/3 bytes), per 64-column panel compact-WY block updates of A and Z on the
 //      DMMA GEMM.
-//  (2) Windowed multishift QR  H -> T (upper triangular), Z <- Z U:  chains of up to QR_NS
+//  (2) Windowed multishift QR with aggressive early deflation, Z <- Z U:  chains of up to QR_NS
 //      single-shift Givens bulges (spacing 2) are chased through a QR_W x QR_W diagonal window held
 //      in shared memory by ONE CTA per matrix, all bulges advancing one position per step; the
-//      window's accumulated unitary U is then applied to the off-diagonal row panel, column panel
-//      and to Z by three grouped DMMA GEMMs (zgemm.cu) over the whole batch.  Shifts =
-//      eigenvalues of the trailing QR_NS x QR_NS block (single-warp shifted QR in shared memory);
-//      deflation by the conservative LAPACK zlahqr criterion.  The host only enqueues
-//      (pass kernel, 2 GEMM launches) repeatedly and polls a device counter through pinned memory.
-//  (3) Eigenvectors of T by blocked back-substitution (one GEMM + one per-column small triangular
-//      solve per 32-row block), then V = Z X (GEMM) and unit 2-norm columns (LAPACK geev convention).
+//      window's accumulated unitary U is then applied to the off-diagonal row panel (main stream),
+//      the column panel and Z (side stream) by grouped DMMA GEMMs (zgemm.cu).  H is kept current
+//      only inside the active block.  AED: the trailing 48 x 48 window is Schur-factored on a copy
+//      (two-phase explicit-shift QR, barrier-free warp version), converged eigenvalues are deflated
+//      by the spike test, the rest become the next shifts.  Every serial piece is a resumable time
+//      slice (SM-clock budget): a launch lasts as long as its slowest matrix.  The batch runs as
+//      independently pipelined groups; the host only enqueues and polls a device counter through
+//      pinned memory.
+//  (3) Schur form T = Z^H A0 Z (upper tiles), eigenvectors of T by blocked back-substitution (one
+//      triangular-hinted GEMM + one per-column small triangular solve per 32-row block), then
+//      V = Z X (GEMM) and unit 2-norm columns (LAPACK geev convention).
 //
 // The single-CTA bodies (qr pass, shift solver, triangular solves) are phase-structured and are
 // also compiled for the CPU by the emulation build (-DRCWA_EMU, tests only).
