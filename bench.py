@@ -134,6 +134,8 @@ def bench_b200(args):
     torch.cuda.set_device(device)
     dist = None
     if world > 1:
+        # NCCL prints its version banner / debug lines to stdout by default: keep stdout for the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     case, mask, lams = sweep_inputs(args.order)
