@@ -246,7 +246,7 @@ def bench_b200(args):
                 "algorithmic_bytes_per_matrix": b_eig,
                 "hessenberg_phase_whole": {"achieved": achieved_h, "frac": achieved_h / hbm_peak, "ms_per_batch": t_h},
                 "eig_stage_whole": {"achieved": achieved_eig, "frac": achieved_eig / hbm_peak, "ms_per_batch": sim_stage["eig_ms"]}}
-        cpu = cpu_baseline(args.order, args.ref_dtype) if args.cpu_baseline else None
+        cpu = cpu_baseline(args.order, args.ref_dtype) if (args.cpu_baseline and world == 1) else None     # N = 1 only
         out = {
             "metric": "layers/sec (order %dx%d, c64)" % (args.order, args.order), "value": value, "unit": "layers/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak",
