@@ -32,22 +32,27 @@ os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from oracle import cases as C  # noqa: E402  (input builders only; the oracle itself is used by the reference legs)
+# oracle/ is imported only inside the CPU legs below (cpu_baseline / --impl reference); the B200 arm builds its
+# synthetic inputs with the product package's own rasteriser.
 
 N_SWEEP = 512
 LAM0, LAM1 = 400.0, 700.0
+# a-Si:H permittivity at 532 / 650 nm: cubic interpolation of the reference's example/Materials_data/aSiH.txt
+SI_EPS = {532.0: complex(12.011610263133004, 0.5259120147560001), 650.0: complex(10.362267239174999, 0.15362360819199997)}
 
 
 def eps_si(lam):
-    """Synthetic linear dispersion through the two a-Si:H points of oracle/cases.py."""
-    a, b = C.SI_EPS[532.0], C.SI_EPS[650.0]
+    """Synthetic linear dispersion through the two a-Si:H points above."""
+    a, b = SI_EPS[532.0], SI_EPS[650.0]
     return a + (lam - 532.0) / (650.0 - 532.0) * (b - a)
 
 
 def sweep_inputs(order):
-    case = dict(C.CASES["ex1_o15"])
-    case["order"] = [order, order]
-    mask = C.rectangle_grid(300.0, 300.0, 300, 300, 180.0, 100.0, 150.0, 150.0, 0.0, 1000.0, torch.float32)
+    """Example1 cell (Example1.ipynb:40-57): 300 x 300 nm period, 180 x 100 nm pillar, 300 x 300 samples, glass substrate."""
+    import torcwa_b200
+    case = {"order": [order, order], "L": [300.0, 300.0], "eps_in": 1.46 ** 2}
+    geo = torcwa_b200.geometry(Lx=300.0, Ly=300.0, nx=300, ny=300, edge_sharpness=1000.0, dtype=torch.float32, device=torch.device("cpu"))
+    mask = geo.rectangle(Wx=180.0, Wy=100.0, Cx=150.0, Cy=150.0)
     lams = torch.linspace(LAM0, LAM1, N_SWEEP, dtype=torch.float32)
     return case, mask, lams
 
@@ -379,6 +384,7 @@ def tensor_roofline(A):
 # ------------------------------------------------------------------------------------------- CPU legs
 def oracle_point(order, cdtype, lam=532.0):
     """One design point (one patterned layer) through the oracle = the reference's dense CPU algebra."""
+    from oracle import cases as C
     from oracle.rcwa_oracle import OracleSim
     case = dict(C.CASES["ex1_o15"])
     case["order"] = [order, order]
