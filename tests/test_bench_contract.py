@@ -38,3 +38,11 @@ def test_b200_arm_fails_loudly_without_a_gpu():
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0
     assert "{" not in r.stdout          # no number is printed from a CPU fallback
+
+
+def test_product_package_and_bench_import_do_not_load_the_oracle():
+    """oracle/ is test infrastructure: neither the product package nor importing bench.py (its B200 arm) may load it."""
+    code = ("import sys; sys.path.insert(0, %r); import torcwa_b200, bench; "
+            "bad = [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]; assert not bad, bad") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-1500:]
