@@ -51,3 +51,20 @@ def test_shard_bounds_cover_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def test_chunked_and_points_per_call():
+    import torch
+    from torcwa_b200 import sweep
+    calls = []
+
+    def solve(lo, hi):
+        calls.append((lo, hi))
+        return torch.arange(lo, hi, dtype=torch.float64)[:, None].to(torch.complex128)
+    out = sweep.chunked(solve, 128)(10, 400)
+    assert calls == [(10, 138), (138, 266), (266, 394), (394, 400)]
+    assert torch.equal(out[:, 0].real, torch.arange(10, 400, dtype=torch.float64))
+    assert sweep.points_per_call(15, free_bytes=178 * 2 ** 30) == 128           # a whole B200: capped at 128
+    assert sweep.points_per_call(15, free_bytes=40 * 2 ** 30) == 45             # 40 GB free
+    assert sweep.points_per_call([21, 21], free_bytes=178 * 2 ** 30) == 55      # BASELINE config 3 (n = 3698)
+    assert sweep.points_per_call(25, free_bytes=2 ** 30) == 1

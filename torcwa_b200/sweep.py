@@ -43,3 +43,26 @@ def solve_sweep(solve_slice, n_points, group=None):
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     lo, hi = shard_bounds(n_points, rank, world)
     return gather_sparams(solve_slice(lo, hi), n_points, group)
+
+
+# ------------------------------------------------------------------------------------------ chunking within one GPU
+def points_per_call(order, free_bytes=None, device=None, safety=0.8):
+    """How many design points one `rcwa` object should carry on this GPU.  The peak of a patterned layer is about 11
+    live n x n complex128 matrices per point (layer S-matrix: W, Q, S11, S21 + 6 workspace; star product: 2 + 4
+    outputs + 5 workspace), n = 2 (2 ox + 1)(2 oy + 1): 0.65 GB per point at order 15, i.e. 128
+    points on a 180 GB B200.  Throughput is flat from 128 points on (measured), so the result is capped there."""
+    ox, oy = (order, order) if isinstance(order, int) else (int(order[0]), int(order[1]))
+    n = 2 * (2 * ox + 1) * (2 * oy + 1)
+    if free_bytes is None:
+        free_bytes, _ = torch.cuda.mem_get_info(device)
+    per_point = 11 * n * n * 16 * 1.15
+    return max(1, min(128, int(safety * free_bytes / per_point)))
+
+
+def chunked(solve_slice, chunk):
+    """Wrap solve_slice(lo, hi) -> [hi-lo, K] so that it is called on pieces of at most `chunk` points (one `rcwa`
+    object each) and the pieces are concatenated: the way to run a 512-point sweep on one GPU."""
+    def run(lo, hi):
+        parts = [solve_slice(a, min(a + chunk, hi)) for a in range(lo, hi, chunk)]
+        return torch.cat(parts, dim=0) if parts else solve_slice(lo, hi)
+    return run
