@@ -227,3 +227,45 @@ def test_random_stacks_match_oracle(cpu_double, seed):
     ref = run(lambda **kw: OracleSim(**kw))
     scale = max(np.abs(ref).max(), 1e-30)
     assert np.abs(mine - ref).max() <= 1e-9 * scale, np.abs(mine - ref).max() / scale
+
+
+def test_batched_fields_equal_per_point_fields(cpu_double):
+    """Fields of a batched sweep (three wavelengths, per-point thickness) == the fields of three separate unbatched
+    simulations, plane by plane."""
+    import sys
+    import torcwa_b200.fields as F
+    F._lib = sys.modules["fake_lib"]
+    try:
+        case = C.CASES["stack_o3"]
+        cd = torch.complex128
+        lams = torch.tensor([600.0, 650.0, 710.0], dtype=torch.float64)
+        layers = C.build_layers(case, cd)[:2]
+        thick0 = torch.tensor([200.0, 180.0, 230.0], dtype=torch.float64)
+        x = torch.linspace(0.0, 300.0, 5, dtype=torch.float64)
+        z = torch.tensor([-30.0, 50.0, 190.0, 250.0, 400.0], dtype=torch.float64)
+
+        def solve(freq, t0):
+            sim = cpu_double.rcwa(freq=freq, order=case["order"], L=case["L"], dtype=cd, device=CPU, store_intermediates=True)
+            sim.add_input_layer(eps=case["eps_in"]); sim.add_output_layer(eps=case["eps_out"])
+            sim.set_incident_angle(inc_ang=case["inc"], azi_ang=case["azi"])
+            sim.add_layer(thickness=t0, eps=layers[0][1])
+            sim.add_layer(thickness=layers[1][0], eps=layers[1][1])
+            sim.solve_global_smatrix()
+            sim.source_fourier(amplitude=[[0.7, 0.2], [0.1, -0.4j]], orders=[[0, 0], [1, -1]], direction="forward", notation="ps")
+            return sim
+        sb = solve(1 / lams, thick0)
+        Eb, Hb = sb.field_xz(x, z, 40.0)
+        Exy, Hxy = sb.field_xy(0, x, x, 60.0)
+        assert Eb[0].shape == (3, 5, 5)
+        for b in range(3):
+            s1 = solve(1 / lams[b], float(thick0[b]))
+            E1, H1 = s1.field_xz(x, z, 40.0)
+            E2, H2 = s1.field_xy(0, x, x, 60.0)
+            for k in range(3):
+                assert float((Eb[k][b] - E1[k]).abs().max()) <= 1e-11 * float(E1[k].abs().max() + 1e-30)
+                assert float((Hb[k][b] - H1[k]).abs().max()) <= 1e-11 * float(H1[k].abs().max() + 1e-30)
+                assert float((Exy[k][b] - E2[k]).abs().max()) <= 1e-11 * float(E2[k].abs().max() + 1e-30)
+                assert float((Hxy[k][b] - H2[k]).abs().max()) <= 1e-11 * float(H2[k].abs().max() + 1e-30)
+    finally:
+        from torcwa_b200 import _lib as real
+        F._lib = real

@@ -13,7 +13,9 @@ asked for, the mode coefficients are built once, lazily, from what the simulatio
 Dense O(n^3) work (products, inverses) runs on the CUDA GEMM / LU kernels through `_lib`; the rest is O(n^2)
 torch glue.  Fields are physical quantities: they do not depend on the normalisation or order of the
 eigenvectors, so they agree with the reference although W comes from a different eigensolver.
-Unbatched simulations only (a batched sweep would need [B, ...] planes; not built).
+
+Batched simulations (needs store_intermediates=True): every design point is processed through the same,
+unbatched code on a one-point view of the simulation (`_PointView`), and the planes are stacked to [B, ...].
 """
 import warnings
 
@@ -43,6 +45,62 @@ def _dense_bd(d4):
     return torch.cat((torch.cat((a, b), 1), torch.cat((c, d), 1)), 0)
 
 
+# ------------------------------------------------------------------------------------------ batched simulations
+class _PointView:
+    """One design point of a batched simulation, presented as an unbatched simulation: every per-point tensor is
+    sliced to [b:b+1], everything else is delegated.  The field code below only ever sees unbatched objects."""
+    _SLICED = ('_kx', '_ky', '_Vf', '_Vf_inv', '_Vi', '_Vo', '_omega64')
+
+    def __init__(self, sim, b):
+        object.__setattr__(self, '_sim', sim)
+        object.__setattr__(self, '_pt', b)
+        self._batched = False
+        self._modes_ready = False
+        self._modes_src = [{k: (v if v is None else v[b:b + 1]) for k, v in rec.items()} for rec in sim._modes_src]
+        self._layers = [[x[b:b + 1] for x in lay] for lay in sim._layers]
+        self._S = [x[b:b + 1] for x in sim._S]
+        if hasattr(sim, '_Sin'):
+            self._Sin = [x[b:b + 1] for x in sim._Sin]
+        if hasattr(sim, '_Sout'):
+            self._Sout = [x[b:b + 1] for x in sim._Sout]
+        self.thickness = [t.reshape(-1)[b] if (isinstance(t, torch.Tensor) and t.numel() == sim._B and sim._B > 1) else t
+                          for t in sim.thickness]
+
+    def __getattr__(self, name):
+        sim, b = object.__getattribute__(self, '_sim'), object.__getattribute__(self, '_pt')
+        v = getattr(sim, name)
+        if name in _PointView._SLICED:
+            return v[b:b + 1]
+        return v
+
+    def _b(self, v):
+        return self._sim._b(v)[self._pt:self._pt + 1]
+
+    def _pub(self, t):
+        return t.to(self._sim._dtype)[0]
+
+    def _matching_indices(self, orders):
+        return self._sim._matching_indices(orders)
+
+
+def _stack_points(sim, fn):
+    """Run fn on every point's view and stack the six field planes to [B, ...]."""
+    if not hasattr(sim, '_source_spec'):
+        raise RuntimeError('define a source first (source_planewave / source_fourier)')
+    outs = []
+    for b in range(sim._B):
+        view = sim._views.get(b)
+        if view is None or view._sim_solve_id != id(sim._S):
+            view = _PointView(sim, b)
+            view._sim_solve_id = id(sim._S)
+            source_fourier(view, *sim._source_spec)
+            sim._views[b] = view
+        outs.append(fn(view))
+    E = [torch.stack([o[0][k] for o in outs]) for k in range(3)]
+    H = [torch.stack([o[1][k] for o in outs]) for k in range(3)]
+    return E, H
+
+
 # ------------------------------------------------------------------------------------------ sources
 def source_fourier(sim, amplitude, orders, direction, notation):
     amplitude = torch.as_tensor(amplitude, dtype=sim._dtype, device=sim._device).reshape([-1, 2])
@@ -57,8 +115,13 @@ def source_fourier(sim, amplitude, orders, direction, notation):
     if notation not in ['xy', 'ps']:
         warnings.warn('Invalid amplitude notation. Set as xy notation.', UserWarning)
         notation = 'xy'
-    if sim._batched:
-        raise NotImplementedError('sources / fields are built for unbatched simulations only')
+    if sim._batched and not isinstance(sim, _PointView):
+        # one source specification for the whole sweep; the ps -> xy rotation depends on each point's wavevectors,
+        # so the amplitude vector is built per point (on its view) when a field is asked for
+        sim.source_direction = direction
+        sim._source_spec = (amplitude, orders, direction, notation)
+        sim._views = {}
+        return
     idx = sim._matching_indices(orders)
     N = sim.order_N
     sim.source_direction = direction
@@ -136,8 +199,6 @@ def ensure_modes(sim):
     """Build H_eigvec, Cf, Cb per layer and the propagated coefficient lists sim.C (once per solve)."""
     if sim._modes_ready:
         return
-    if sim._batched:
-        raise NotImplementedError('sources / fields are built for unbatched simulations only')
     if len(sim._modes_src) != sim.layer_N:
         raise RuntimeError('fields need the per-layer intermediates: construct the simulation with store_intermediates=True')
     if not hasattr(sim, '_S'):
@@ -278,6 +339,8 @@ def field_plane(sim, plane, t_axis, z_axis, other):
     if type(t_axis) != torch.Tensor or type(z_axis) != torch.Tensor:
         warnings.warn('%s and z axis must be torch.Tensor type. Return None.' % plane[0], UserWarning)
         return None
+    if sim._batched and not isinstance(sim, _PointView):
+        return _stack_points(sim, lambda v: field_plane(v, plane, t_axis, z_axis, other))
     coef = _coefficients_along_z(sim, z_axis)                                         # [6, N, nz]
     t = t_axis.to(device=sim._device, dtype=torch.float64).reshape(-1, 1)
     om = sim._omega64[0]
@@ -297,6 +360,8 @@ def field_xy(sim, layer_num, x_axis, y_axis, z_prop):
     if type(x_axis) != torch.Tensor or type(y_axis) != torch.Tensor:
         warnings.warn('x and y axis must be torch.Tensor type. Return None.', UserWarning)
         return None
+    if sim._batched and not isinstance(sim, _PointView):
+        return _stack_points(sim, lambda v: field_xy(v, layer_num, x_axis, y_axis, z_prop))
     ensure_modes(sim)
     if not hasattr(sim, '_E_i'):
         raise RuntimeError('define a source first (source_planewave / source_fourier)')
