@@ -37,7 +37,9 @@
 #define QR_LD 65           // shared-memory leading dimension (odd: conflict-free column access)
 #define QR_NS 16           // max simultaneous shifts / bulges
 #define QR_SMALL 48         // active blocks up to this size are Schur-factored directly in shared memory
+#ifndef QR_AED_W
 #define QR_AED_W 48         // aggressive-early-deflation window
+#endif
 // Time-slice budgets of the serial pieces of a pass.  A launch lasts as long as its slowest matrix, and with
 // ~100 matrices in a batch some matrix is in its most expensive segment in EVERY launch (measured: mean
 // own work 117 us per pass, launch duration 400 us), so every segment type is cut to about the duration of a
@@ -1058,7 +1060,8 @@ extern "C" int emu_qr(cplx* H, cplx* Z, int n, int max_passes, int* stats) {
     }
     stats[0] = st.sweeps; stats[1] = st.passes; stats[2] = st.done; stats[3] = st.small_solves;
     stats[4] = st.aeds; stats[5] = st.aed_deflated;
-    stats[6] = (int)st.band_active; stats[7] = (int)st.band_total;
+    stats[6] = st.cnt[1];            // bulge-chain windows (each one costs three update GEMMs on the device)
+    stats[7] = (int)(100.0 * (double)st.band_active / (double)(st.band_total > 0 ? st.band_total : 1));
     return st.done ? st.info : -1;
 }
 
