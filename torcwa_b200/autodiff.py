@@ -25,7 +25,6 @@ from . import _lib
 from .torch_eig import Eig
 
 _C = torch.complex128
-_OPS = {"N": "N", "H": "H"}
 
 
 class ZGemm(torch.autograd.Function):
