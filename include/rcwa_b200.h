@@ -59,6 +59,28 @@ int rcwa_zgemm_batched(int opa, int opb, int M, int N, int K, double alpha_re, d
                        double beta_re, double beta_im, void* C, int ldc, long long stride_c,
                        int nb, void* gemm_scratch, void* stream);
 
+/* The same product on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM, operands staged by
+ * TMA): every number is split into `slices` (2..8) signed 8-bit digits after a per-row (A) / per-column (B) power-of-two
+ * scaling, the digit products are exact int8 x int8 -> int32 GEMMs, and the result is re-assembled in fp64 -- error
+ * relative to (row scale of A) x (column scale of B), measured on random matrices: slices 4: 4e-8, 5: 2e-10, 6: 8e-13,
+ * 7: 3e-15, 8: 3e-16 (fp64-grade); 4-5 are enough for the complex64 API.  alpha is real.  `ws`: rcwa_zgemm_tc_workspace_bytes(M,N,K,nb,
+ * slices) for one pass over the batch; any size down to rcwa_zgemm_tc_workspace_bytes(M,N,K,1,slices) works (chunked).
+ * Replaces the same torch.matmul call sites (rcwa.py:1236,1264,1276-1281,1291-1294). */
+size_t rcwa_zgemm_tc_workspace_bytes(int M, int N, int K, int nb, int slices);
+int rcwa_zgemm_tc_batched(int slices, int opa, int opb, int M, int N, int K, double alpha,
+                          const void* A, int lda, long long stride_a, const void* B, int ldb, long long stride_b,
+                          double beta_re, double beta_im, void* C, int ldc, long long stride_c,
+                          int nb, void* ws, size_t ws_bytes, void* stream);
+/* Test / diagnostic entry points of that path.  rcwa_tc_split: the digit split on its own -- X [nb] matrices (ld, stride);
+ * rows_contiguous = 1: the R scaled vectors are the rows of X (Kc entries each), 0: its columns (X is Kc x R);
+ * planes: int8 [nb, 3 (re, im, re+im), slices, R, Kp], Kp = Kc rounded up to 128, digit 0 most significant;
+ * ex: int32 [nb, R] with value = 2^(ex + 2 - 8 slices) * sum_d digit_d 256^(slices-1-d).
+ * rcwa_tc_schedule (host only): the load / MMA / release table the kernel walks per K chunk; ops [128] words, meta [64] =
+ * {groups, ops, then per group: first level, levels, first op, ops, loads}. */
+int rcwa_tc_split(const void* X, int ld, long long stride, int rows_contiguous, int R, int Kc, int slices, int conj,
+                  void* planes, int* ex, int nb, void* stream);
+int rcwa_tc_schedule(int slices, int levels, unsigned* ops, int* meta);
+
 /* Tuning / profiling entry points (not needed by a binding; used by bench.py and tools/).
  * rcwa_zgemm_batched_cfg: the same product on an explicit kernel configuration:
  *   cfg = tile | 8*m3;  tile 0: 64x128, 1: 128x64 (256 threads, one CTA/SM, long K), 2: 64x64, 3: 128x32,

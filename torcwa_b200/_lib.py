@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("RCWA_B200_LIB", "librcwa_b200.so"
 
 EXPORTS = [
     "rcwa_b200_abi_version", "rcwa_gemm_scratch_bytes", "rcwa_convmat_workspace_bytes", "rcwa_convmat",
-    "rcwa_zgemm_batched", "rcwa_zgemm_batched_cfg", "rcwa_set_tuning", "rcwa_get_tuning", "rcwa_lu_tinv_bytes", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
+    "rcwa_zgemm_batched", "rcwa_zgemm_batched_cfg", "rcwa_zgemm_tc_workspace_bytes", "rcwa_zgemm_tc_batched", "rcwa_tc_split", "rcwa_tc_schedule", "rcwa_set_tuning", "rcwa_get_tuning", "rcwa_lu_tinv_bytes", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
     "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_eig_stats", "rcwa_eig_profile", "rcwa_hessenberg", "rcwa_hessenberg_matvec_probe", "rcwa_hessenberg_panel_width", "rcwa_kz_branch", "rcwa_eig_backward_workspace_bytes", "rcwa_eig_backward", "rcwa_layer_smatrix_workspace_bytes",
     "rcwa_layer_smatrix", "rcwa_redheffer_workspace_bytes", "rcwa_redheffer", "rcwa_redheffer_bdleft", "rcwa_blockdiag_dense",
 ]
@@ -27,6 +27,10 @@ _SIGS = {
     "rcwa_convmat": (_i, [_vp, _i, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rcwa_zgemm_batched": (_i, [_i, _i, _i, _i, _i, _d, _d, _vp, _i, _ll, _vp, _i, _ll, _d, _d, _vp, _i, _ll, _i, _vp, _vp]),
     "rcwa_zgemm_batched_cfg": (_i, [_i, _i, _i, _i, _i, _i, _d, _d, _vp, _i, _ll, _vp, _i, _ll, _d, _d, _vp, _i, _ll, _i, _vp, _vp]),
+    "rcwa_zgemm_tc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "rcwa_zgemm_tc_batched": (_i, [_i, _i, _i, _i, _i, _i, _d, _vp, _i, _ll, _vp, _i, _ll, _d, _d, _vp, _i, _ll, _i, _vp, _sz, _vp]),
+    "rcwa_tc_split": (_i, [_vp, _i, _ll, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "rcwa_tc_schedule": (_i, [_i, _i, _vp, _vp]),
     "rcwa_set_tuning": (_i, [_i, _i]),
     "rcwa_get_tuning": (_i, [_i]),
     "rcwa_lu_tinv_bytes": (_sz, [_i, _i]),
@@ -154,6 +158,52 @@ def zgemm(A, B, opa="N", opb="N", alpha=1.0, beta=0.0, out=None, cfg=None):
                                   _ptr(A), A.shape[2], A.shape[1] * A.shape[2], _ptr(B), B.shape[2], B.shape[1] * B.shape[2],
                                   be.real, be.imag, _ptr(out), N, M * N, nb, _ptr(gs), _stream()), "rcwa_zgemm_batched")
     return out
+
+
+def zgemm_tc(A, B, opa="N", opb="N", alpha=1.0, beta=0.0, out=None, slices=7, ws_bytes=None):
+    """The same product on tcgen05 (int8 digit products, include/rcwa_b200.h: rcwa_zgemm_tc_batched); alpha real."""
+    lib = load()
+    _c128(A, "A"); _c128(B, "B")
+    nb = A.shape[0]
+    M = A.shape[1] if opa == "N" else A.shape[2]
+    K = A.shape[2] if opa == "N" else A.shape[1]
+    N = B.shape[2] if opb == "N" else B.shape[1]
+    if out is None:
+        out = torch.empty((nb, M, N), dtype=torch.complex128, device=A.device)
+        beta = 0.0
+    _c128(out, "out")
+    nbytes = int(ws_bytes) if ws_bytes else lib.rcwa_zgemm_tc_workspace_bytes(M, N, K, nb, int(slices))
+    ws = _ws(nbytes, A.device)
+    be = complex(beta)
+    _check(lib.rcwa_zgemm_tc_batched(int(slices), _OPS[opa], _OPS[opb], M, N, K, float(alpha),
+                                     _ptr(A), A.shape[2], A.shape[1] * A.shape[2], _ptr(B), B.shape[2], B.shape[1] * B.shape[2],
+                                     be.real, be.imag, _ptr(out), N, M * N, nb, _ptr(ws), nbytes, _stream()), "rcwa_zgemm_tc_batched")
+    return out
+
+
+def tc_split(X, rows_contiguous, slices, conj=False):
+    """Digit split of the tcgen05 GEMM on its own (tests): X [nb,a,b] -> (planes int8 [nb,3,slices,R,Kp], ex int32 [nb,R])."""
+    lib = load()
+    _c128(X, "X")
+    nb = X.shape[0]
+    R, Kc = (X.shape[1], X.shape[2]) if rows_contiguous else (X.shape[2], X.shape[1])
+    Kp = (Kc + 127) // 128 * 128
+    planes = torch.empty((nb, 3, slices, R, Kp), dtype=torch.int8, device=X.device)
+    ex = torch.empty((nb, R), dtype=torch.int32, device=X.device)
+    _check(lib.rcwa_tc_split(_ptr(X), X.shape[2], X.shape[1] * X.shape[2], int(bool(rows_contiguous)), R, Kc, int(slices), int(bool(conj)),
+                             _ptr(planes), _ptr(ex), nb, _stream()), "rcwa_tc_split")
+    return planes, ex
+
+
+def tc_schedule(slices, levels=4):
+    """Host-only: the per-K-chunk op table of the tcgen05 GEMM -> (ops list, groups list of dicts)."""
+    lib = load()
+    ops = (ctypes.c_uint * 128)()
+    meta = (ctypes.c_int * 64)()
+    _check(lib.rcwa_tc_schedule(int(slices), int(levels), ops, meta), "rcwa_tc_schedule")
+    groups = [dict(d0=meta[2 + 5 * g], nl=meta[3 + 5 * g], op0=meta[4 + 5 * g], nops=meta[5 + 5 * g], nloads=meta[6 + 5 * g])
+              for g in range(meta[0])]
+    return list(ops)[:meta[1]], groups
 
 
 def lu_factor_(A):

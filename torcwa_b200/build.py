@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "librcwa_b200.so")
 EMU_LIB = os.path.join(ROOT, "tests", "_emu", "librcwa_emu.so")
-CU_FILES = ["zgemm.cu", "convmat.cu", "assemble.cu", "lu.cu", "hess.cu", "eig.cu", "api.cu"]
+CU_FILES = ["zgemm.cu", "tc_gemm.cu", "convmat.cu", "assemble.cu", "lu.cu", "hess.cu", "eig.cu", "api.cu"]
 EMU_FILES = ["lu.cu", "eig.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -66,6 +66,58 @@ int rcwa_zgemm_batched_cfg(int cfg, int opa, int opb, int M, int N, int K, doubl
                                 C(beta_re, beta_im), (cplx*)Cm, ldc, sc, nb, (ZGemmProblem*)gs, S(stream)));
 }
 
+size_t rcwa_zgemm_tc_workspace_bytes(int M, int N, int K, int nb, int slices) {
+    if (M <= 0 || N <= 0 || K <= 0 || slices < 2 || slices > TC_MAXS) return 0;
+    return tc_workspace_bytes(M, N, K, nb, slices);
+}
+
+int rcwa_zgemm_tc_batched(int slices, int opa, int opb, int M, int N, int K, double alpha,
+                          const void* A, int lda, long long sa, const void* B, int ldb, long long sb,
+                          double beta_re, double beta_im, void* Cm, int ldc, long long sc, int nb, void* ws, size_t ws_bytes, void* stream) {
+    if (slices < 2 || slices > TC_MAXS) return -1;
+    if (opa < 0 || opa > 2) return -2;
+    if (opb < 0 || opb > 2) return -3;
+    if (M <= 0) return -4;
+    if (N <= 0) return -5;
+    if (K <= 0 || K > 16000) return -6;
+    if (!A) return -8;
+    if (!B) return -11;
+    if (!Cm) return -16;
+    if (nb <= 0) return -19;
+    if (!ws || ws_bytes < tc_workspace_min_bytes(M, N, K, slices)) return -20;
+    if (!tc_supported(slices, M, N, K)) return RCWA_ERR_CUDA - (int)cudaErrorNotSupported;
+    return cu(tc_zgemm_strided(slices, opa, opb, M, N, K, alpha, (const cplx*)A, lda, sa, (const cplx*)B, ldb, sb,
+                               C(beta_re, beta_im), (cplx*)Cm, ldc, sc, nb, (char*)ws, ws_bytes, S(stream)));
+}
+
+int rcwa_tc_split(const void* X, int ld, long long stride, int rows_contiguous, int R, int Kc, int slices, int conj,
+                  void* planes, int* ex, int nb, void* stream) {
+    if (!X) return -1;
+    if (R <= 0) return -5;
+    if (Kc <= 0) return -6;
+    if (slices < 2 || slices > TC_MAXS) return -7;
+    if (!planes) return -9;
+    if (!ex) return -10;
+    if (nb <= 0) return -11;
+    return cu(tc_split_debug((const cplx*)X, ld, stride, rows_contiguous, R, Kc, slices, conj, (signed char*)planes, ex, nb, S(stream)));
+}
+
+int rcwa_tc_schedule(int slices, int levels, unsigned* ops, int* meta) {
+    if (slices < 2 || slices > TC_MAXS) return -1;
+    if (levels < 1 || levels > 4) return -2;
+    if (!ops) return -3;
+    if (!meta) return -4;
+    TcSchedule sch;
+    tc_build_schedule(slices, levels, &sch);
+    for (int i = 0; i < TC_MAXOPS; ++i) ops[i] = i < sch.nops ? sch.ops[i] : 0u;
+    meta[0] = sch.ngroups; meta[1] = sch.nops;
+    for (int g = 0; g < sch.ngroups; ++g) {
+        meta[2 + 5 * g] = sch.g[g].d0; meta[3 + 5 * g] = sch.g[g].nl; meta[4 + 5 * g] = sch.g[g].op0;
+        meta[5 + 5 * g] = sch.g[g].nops; meta[6 + 5 * g] = sch.g[g].nloads;
+    }
+    return 0;
+}
+
 int rcwa_set_tuning(int key, int value) {
     if (key < 0 || key > 15) return -1;
     gemm_set_tuning(key, value);

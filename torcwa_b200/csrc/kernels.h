@@ -33,6 +33,26 @@ cudaError_t zgemm_strided(int opa, int opb, int M, int N, int K, cplx alpha, con
                           int batch, ZGemmProblem* scratch, cudaStream_t st, int flags = 0);   // flags: ZGEMM_* structure hints
 
 
+// ---- tc_gemm.cu: complex fp64-grade GEMM from int8 digit products on tcgen05 (see the file header)
+#define TC_MAXS 8            // most digits (slices) per number
+#define TC_MAXOPS 128
+#define TC_OP_LOAD_A 0u      // op word: bits 0-1 type; loads: bits 2-5 digit index;
+#define TC_OP_LOAD_B 1u      //   MMA: bits 2-6 / 7-11 = index of the A / B load inside this (group, K chunk) iteration, bits 12-13 level - d0,
+#define TC_OP_MMA 2u         //   bit 14 first MMA of that level in the iteration, bit 15 / 16 = last use of the A / B slot (release it)
+#define TC_E_ZERO (-100000)  // exponent marker of an all-zero row / column
+struct TcGroup { int d0, nl, op0, nops, nloads; };
+struct TcSchedule { int s, ngroups, nops, pad; TcGroup g[TC_MAXS]; unsigned ops[TC_MAXOPS]; };
+void tc_build_schedule(int s, int nl, TcSchedule* sch);
+size_t tc_workspace_bytes(int M, int N, int K, int nb, int s);      // split storage for the whole batch
+size_t tc_workspace_min_bytes(int M, int N, int K, int s);          // ... for one matrix (the routine then runs in chunks)
+bool tc_supported(int s, int M, int N, int K);
+// C = alpha op(A) op(B) + beta C with s digits per number (alpha real); ws >= tc_workspace_min_bytes
+cudaError_t tc_zgemm_strided(int s, int opa, int opb, int M, int N, int K, double alpha, const cplx* A, int lda, long long sa,
+                             const cplx* B, int ldb, long long sb, cplx beta, cplx* C, int ldc, long long sc, int batch,
+                             char* ws, size_t ws_bytes, cudaStream_t st);
+cudaError_t tc_split_debug(const cplx* X, int ld, long long stride, int rows_contiguous, int R, int Kc, int s, int conj,
+                           signed char* out, int* ex, int nmat, cudaStream_t st);
+
 // ---- convmat.cu
 size_t convmat_workspace_elems(int nx, int ny, int nb, int ox, int oy);
 cudaError_t convmat(const void* grid, int grid_type, long long grid_stride, int nx, int ny, int nb, int ox, int oy,
