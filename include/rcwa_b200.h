@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RCWA_B200_ABI_VERSION 1
+#define RCWA_B200_ABI_VERSION 2
 
 /* grid element types for rcwa_convmat */
 #define RCWA_GRID_F32 0
@@ -75,11 +75,12 @@ int rcwa_zgemm_tc_batched(int slices, int opa, int opb, int M, int N, int K, dou
  * rows_contiguous = 1: the R scaled vectors are the rows of X (Kc entries each), 0: its columns (X is Kc x R);
  * planes: int8 [nb, 3 (re, im, re+im), slices, R, Kp], Kp = Kc rounded up to 128, digit 0 most significant;
  * ex: int32 [nb, R] with value = 2^(ex + 2 - 8 slices) * sum_d digit_d 256^(slices-1-d).
- * rcwa_tc_schedule (host only): the load / MMA / release table the kernel walks per K chunk; ops [128] words, meta [64] =
- * {groups, ops, then per group: first level, levels, first op, ops, loads}. */
+ * rcwa_tc_schedule (host only): the load / MMA / release schedule of one K chunk; ops [128] words (issue order), meta [64] =
+ * {groups, ops, then per group: first level, levels, first op, ops, loads, MMAs}; loads [8*16] and mmas [8*32] (optional):
+ * the compact per-role tables the kernel walks (bit layout in csrc/kernels.h). */
 int rcwa_tc_split(const void* X, int ld, long long stride, int rows_contiguous, int R, int Kc, int slices, int conj,
                   void* planes, int* ex, int nb, void* stream);
-int rcwa_tc_schedule(int slices, int levels, unsigned* ops, int* meta);
+int rcwa_tc_schedule(int slices, int levels, unsigned* ops, int* meta, unsigned* loads, unsigned* mmas);
 
 /* Tuning / profiling entry points (not needed by a binding; used by bench.py and tools/).
  * rcwa_zgemm_batched_cfg: the same product on an explicit kernel configuration:
@@ -168,25 +169,29 @@ int rcwa_eig_backward(const void* lam, const void* X, const void* glam, const vo
  * Vf^-1 (free-space E->H matrix, rcwa.py:1143-1147), omega[nb], thickness[nb] (fp64).
  * Outputs S11 (= S22) and S21 (= S12) of the single layer, [nb,n,n].
  * Minimal algebra: V = Q W Kz^-1, two LU right-solves; replaces
- * rcwa._solve_layer_smatrix, rcwa.py:1244-1281 (dense inv of the 4N x 4N coupling matrix). */
-size_t rcwa_layer_smatrix_workspace_bytes(int N, int nb);
+ * rcwa._solve_layer_smatrix, rcwa.py:1244-1281 (dense inv of the 4N x 4N coupling matrix).
+ * gemm_slices (here and in the star products): 0 = every dense product on the fp64 tensor pipe (DMMA; the complex128
+ * contract); 2..8 = the n x n x n products and the K = 512 block updates of the triangular solves run on the tcgen05
+ * int8-digit GEMM with that many digits (see rcwa_zgemm_tc_batched; 5 keeps the complex64 API's 1e-4 gate with three
+ * orders of margin).  The workspace size depends on it. */
+size_t rcwa_layer_smatrix_workspace_bytes(int N, int nb, int gemm_slices);
 int rcwa_layer_smatrix(const void* W, const void* kz, const void* Q, const void* vfinv,
                        const double* omega, const double* thickness, int nb, int N,
-                       void* S11, void* S21, void* ws, int* info, void* stream);
+                       void* S11, void* S21, void* ws, int* info, int gemm_slices, void* stream);
 
 /* ---- stage 3b: Redheffer star product -----------------------------------------------------
  * out = Sm (*) Sn, each S = {S11,S21,S12,S22} of [nb,n,n]; outputs must not alias inputs.
  * One LU + two right-solves + 8 GEMMs; replaces rcwa._RS_prod, rcwa.py:1283-1294. */
-size_t rcwa_redheffer_workspace_bytes(int n, int nb);
+size_t rcwa_redheffer_workspace_bytes(int n, int nb, int gemm_slices);
 int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const out[4],
-                   int nb, int n, void* ws, int* info, void* stream);
+                   int nb, int n, void* ws, int* info, int gemm_slices, void* stream);
 
 /* Same product when the LEFT factor is a half-space / homogeneous-layer S-matrix, i.e. each of its four
  * blocks is itself four diagonals: Sm_bd[k] = [nb,4,N] (order 11,12,21,22 inside each block; the
  * reference builds these densely, rcwa.py:1157-1164).  Six of the eight GEMMs become O(n^2) row/column
  * combinations.  n = 2N; workspace as rcwa_redheffer. */
 int rcwa_redheffer_bdleft(const void* const Sm_bd[4], const void* const Sn[4], void* const out[4],
-                          int nb, int N, void* ws, int* info, void* stream);
+                          int nb, int N, void* ws, int* info, int gemm_slices, void* stream);
 
 /* dense [nb,2N,2N] from four diagonals d4 [nb,4,N] (order 11,12,21,22): half-space and
  * homogeneous-layer blocks (rcwa.py:1157-1181, :1206-1222). */

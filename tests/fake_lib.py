@@ -82,7 +82,7 @@ def blockdiag_dense(d4):
     return torch.cat((torch.cat((a, b), 2), torch.cat((c, d), 2)), 1)
 
 
-def layer_smatrix(W, kz, Q, vfinv, omega, thickness):
+def layer_smatrix(W, kz, Q, vfinv, omega, thickness, slices=0):
     n = W.shape[1]
     V = (Q @ W) / kz[:, None, :]
     Bm = blockdiag_dense(vfinv) @ V
@@ -93,14 +93,14 @@ def layer_smatrix(W, kz, Q, vfinv, omega, thickness):
     return Tp + Tm, Tp - Tm - torch.eye(n, dtype=W.dtype), torch.zeros(W.shape[0], dtype=torch.int32)
 
 
-def redheffer(Sm, Sn):
+def redheffer(Sm, Sn, slices=0):
     n = Sm[0].shape[1]
     Di = torch.linalg.inv(torch.eye(n, dtype=Sm[0].dtype) - Sm[2] @ Sn[1])
     Y1, Y2, G = Sn[0] @ Di, Sn[1] @ Di, Sm[2] @ Sn[3]
     return [Y1 @ Sm[0], Sm[1] + Sm[3] @ (Y2 @ Sm[0]), Sn[2] + Y1 @ G, Sm[3] @ (Sn[3] + Y2 @ G)], torch.zeros(Sm[0].shape[0], dtype=torch.int32)
 
 
-def redheffer_bdleft(Sm_bd, Sn):
+def redheffer_bdleft(Sm_bd, Sn, slices=0):
     return redheffer([blockdiag_dense(x) for x in Sm_bd], Sn)
 
 

@@ -129,3 +129,57 @@ def simulate_schedule(ops, groups, s, ring, nkc=3, repeats=3):
         for idx in (m[0], m[1]):
             assert released_by[idx] >= j, "slot used after its release"
     return pairs
+
+
+def simulate_compact(groups, ring, nkc=3, repeats=3):
+    """Walk the compact per-role tables exactly as the kernel's producer and issuer warps do (slot cursors with wrap,
+    acquire counts, releases); returns the (d0, p, q, level, first) products of one K chunk per group and asserts that
+    every MMA only touches slots that hold the load it means, that are acquired, and that the ring cannot deadlock."""
+    pairs = []
+    loads = []                 # global load sequence: (is_b, digit)
+    mmas = []                  # (load index a, load index b, relA, relB)
+    acquired_total = 0
+    for rep in range(repeats):
+        for g in groups:
+            for kc in range(nkc):
+                base = len(loads)
+                for w in g["loads"]:
+                    loads.append((w & 1, w >> 1))
+                acq_iter = 0
+                for w in g["mmas"]:
+                    ia, ib = w & 31, (w >> 5) & 31
+                    acq_iter += (w >> 15) & 15
+                    assert ia < acq_iter and ib < acq_iter, "operand not acquired"
+                    assert ia < g["nloads"] and ib < g["nloads"]
+                    la, lb = loads[base + ia], loads[base + ib]
+                    assert la[0] == 0 and lb[0] == 1
+                    lvl = (w >> 10) & 3
+                    mmas.append((base + ia, base + ib, (w >> 13) & 1, (w >> 14) & 1))
+                    if rep == 0 and kc == 0:
+                        pairs.append((g["d0"], la[1], lb[1], lvl, (w >> 12) & 1))
+                assert acq_iter == g["nloads"], "every load of an iteration is acquired inside it"
+                acquired_total += acq_iter
+    released_by = {}
+    for j, m in enumerate(mmas):
+        if m[2]:
+            assert m[0] not in released_by
+            released_by[m[0]] = j
+        if m[3]:
+            assert m[1] not in released_by
+            released_by[m[1]] = j
+    assert len(released_by) == len(loads)
+    issued, done = 0, 0
+    progress = True
+    while progress:
+        progress = False
+        while issued < len(loads) and (issued < ring or released_by[issued - ring] < done):
+            issued += 1
+            progress = True
+        while done < len(mmas) and max(mmas[done][0], mmas[done][1]) < issued:
+            done += 1
+            progress = True
+    assert issued == len(loads) and done == len(mmas), "ring deadlock"
+    for j, m in enumerate(mmas):
+        assert released_by[m[0]] >= j and released_by[m[1]] >= j, "slot used after its release"
+        # a slot must still hold this load when the MMA runs: the load that overwrites it (index + ring) cannot be issued before the release
+    return pairs

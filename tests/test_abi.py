@@ -22,7 +22,7 @@ def test_library_builds_loads_and_exports_everything():
     for name in names:
         assert hasattr(lib, name), name
     assert sorted(_lib.EXPORTS) == names          # the Python binding covers exactly the header
-    assert _lib.load().rcwa_b200_abi_version() == 1
+    assert _lib.load().rcwa_b200_abi_version() == 2
 
 
 def test_argument_checks_do_not_touch_the_gpu():

@@ -204,3 +204,57 @@ def test_blockdiag_dense():
         ref = torch.cat([torch.cat([torch.diag(d4[b, 0]), torch.diag(d4[b, 1])], 1),
                          torch.cat([torch.diag(d4[b, 2]), torch.diag(d4[b, 3])], 1)], 0)
         assert torch.equal(D[b], ref)
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 engine of the S-matrix stage
+def _well_conditioned(nb, n, seed):
+    """random matrices with a dominant diagonal (like the coupling matrices of the path: cond ~ 1e2-1e3)"""
+    A = rnd(nb, n, n, seed=seed) / np.sqrt(n)
+    return (A + 2.0 * torch.eye(n, dtype=torch.complex128, device=dev())).contiguous()
+
+
+@pytest.mark.parametrize("N,nb", [(169, 3), (961, 2)])
+@pytest.mark.parametrize("slices,tol", [(5, 2e-8), (8, 1e-12)])
+def test_layer_smatrix_and_redheffer_tc_vs_dmma(N, nb, slices, tol):
+    """The S-matrix stage with its dense products on the tcgen05 int8-digit GEMM (gemm_slices = 5 / 8: products, and the
+    512-wide right-looking triangular solves) against the same stage on the fp64 DMMA kernels (gemm_slices = 0)."""
+    from torcwa_b200 import _lib
+    d = dev()
+    n = 2 * N
+    W = _well_conditioned(nb, n, 31)
+    Q = rnd(nb, n, n, seed=32) / np.sqrt(n)
+    kz = (rnd(nb, n, seed=33) * 0.3 + 1.0).contiguous()
+    kz = torch.complex(kz.real.abs() + 0.2, kz.imag.abs())
+    vfinv = (rnd(nb, 4, N, seed=34) * 0.2 + torch.tensor([1.0, 0.0, 0.0, 1.0], dtype=torch.complex128, device=d)[None, :, None]).contiguous()
+    omega = torch.full((nb,), 2 * np.pi / 532.0, dtype=torch.float64, device=d)
+    thick = torch.full((nb,), 100.0, dtype=torch.float64, device=d)
+    r11, r21, info0 = _lib.layer_smatrix(W, kz, Q, vfinv, omega, thick, slices=0)
+    s11, s21, info1 = _lib.layer_smatrix(W, kz, Q, vfinv, omega, thick, slices=slices)
+    assert int(info0.abs().max()) == 0 and int(info1.abs().max()) == 0
+    e = max(rel(s11, r11), rel(s21, r21))
+    print("layer S-matrix, %d digits vs fp64: %.2e" % (slices, e))
+    assert e < tol
+    Sm = [(0.4 * rnd(nb, n, n, seed=40 + k) / np.sqrt(n)).contiguous() for k in range(4)]
+    Sn = [(0.4 * rnd(nb, n, n, seed=50 + k) / np.sqrt(n)).contiguous() for k in range(4)]
+    ref, i0 = _lib.redheffer(Sm, Sn, slices=0)
+    out, i1 = _lib.redheffer(Sm, Sn, slices=slices)
+    assert int(i0.abs().max()) == 0 and int(i1.abs().max()) == 0
+    e = max(rel(out[k], ref[k]) for k in range(4))
+    print("star product, %d digits vs fp64: %.2e" % (slices, e))
+    assert e < tol
+    bd = [rnd(nb, 4, N, seed=60 + k) * 0.3 for k in range(4)]
+    refb, _ = _lib.redheffer_bdleft(bd, Sn, slices=0)
+    outb, _ = _lib.redheffer_bdleft(bd, Sn, slices=slices)
+    assert max(rel(outb[k], refb[k]) for k in range(4)) < tol
+
+
+def test_wrappers_follow_the_tensors_device():
+    """A second GPU (when the box has one): the wrappers make the tensors' device current."""
+    from torcwa_b200 import _lib
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    A = rnd(2, 70, 50, seed=1).to("cuda:1")
+    B = rnd(2, 50, 40, seed=2).to("cuda:1")
+    with torch.cuda.device(0):
+        out = _lib.zgemm(A, B)
+    assert out.device.index == 1 and rel(out, A @ B) < 1e-14

@@ -66,10 +66,13 @@ def test_parity_c128(name, golden_dir):
             assert np.abs(mine - g["kz2_sorted"][l]).max() <= 1e-9 * np.abs(mine).max()
 
 
-@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("name", SMALL + ["ex1_o15"])
 def test_parity_c64_api(name, golden_dir):
+    """complex64 API (fp64 eigensolver, S-matrix stage on the tcgen05 5-digit GEMM where the matrices are large enough
+    -- at order 15 every dense product and triangular-solve update of the stage) against the reference's complex128 run."""
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     sim = run(name, torch.complex64)
+    assert sim._digits == 5
     assert sim.S[0].dtype == torch.complex64
     sp = C.probe(sim)
     scale = np.abs(g["sparams_c128"]).max()
@@ -80,6 +83,21 @@ def test_parity_c64_api(name, golden_dir):
     assert new_vs_ref128 <= 1e-4
     for k in range(4):
         assert relfro(sim.S[k][:, g["S_cols_idx"]].cpu().numpy().astype(np.complex128), g["S_cols"][k]) <= 1e-4
+
+
+@pytest.mark.parametrize("digits,gate", [(0, 1e-10), (8, 1e-10), (7, 1e-9), (5, 1e-6), (4, 1e-4)])
+def test_order15_parity_vs_digits_of_the_tcgen05_engine(digits, gate, golden_dir):
+    """BASELINE config 2's size through the complex128 API with the S-matrix stage on the tcgen05 GEMM at 8 / 7 / 5 / 4
+    digits (0 = fp64 DMMA): distance to the reference's complex128 run.  8 digits keep the complex128 gate; 4-5 are the
+    complex64 API's engine."""
+    import torcwa_b200
+    g = np.load(os.path.join(golden_dir, "ex1_o15.npz"))
+    sim = C.run_case(lambda freq, order, L, dtype: torcwa_b200.rcwa(freq=freq, order=order, L=L, dtype=dtype, device=torch.device("cuda:0"),
+                                                                  gemm_digits=digits), C.CASES["ex1_o15"], torch.complex128)
+    sp = C.probe(sim)
+    err = np.abs(sp - g["sparams_c128"]).max() / np.abs(g["sparams_c128"]).max()
+    print("order 15, %d digits: S-parameter max err / max|S| = %.2e" % (digits, err))
+    assert err <= gate
 
 
 def test_batched_equals_unbatched():

@@ -27,6 +27,7 @@ def test_schedule_covers_all_pairs_and_ring_is_deadlock_free(s, nl):
     ops, groups = _lib.tc_schedule(s, nl)
     assert sum(g["nl"] for g in groups) == s
     pairs = tc_model.simulate_schedule(ops, groups, s, ring=12)
+    assert sorted(tc_model.simulate_compact(groups, ring=12)) == sorted(pairs)        # the tables the kernel actually walks
     want = sorted((p, q) for p in range(s) for q in range(s) if p + q <= s - 1)
     got = sorted((p, q) for (_, p, q, _, _) in pairs)
     assert got == want

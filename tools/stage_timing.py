@@ -12,6 +12,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--order", type=int, default=15)
 ap.add_argument("--nb", type=int, default=4)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--digits", type=int, default=0, help="tcgen05 digits of the S-matrix stage (0 = fp64 DMMA)")
 ap.add_argument("--residual", action="store_true", help="also report max |A W - W diag(lam)| / |A| of the eigendecomposition")
 a = ap.parse_args()
 d = torch.device("cuda:0")
@@ -39,13 +40,13 @@ for rep in range(2):
     e5 = ev(); del H, Z; lam, W, info = _lib.eig(A)
     e6 = ev(); kz = _lib.kz_branch(lam)
     om = sim._omega64.expand(a.nb).contiguous(); th = torch.full((a.nb,), float(thick), dtype=torch.float64, device=d)
-    S11, S21, _ = _lib.layer_smatrix(W, kz, Q, sim._Vf_inv, om, th)
-    e7 = ev(); S, _ = _lib.redheffer_bdleft(sim._Sin, [S11, S21, S21, S11])
+    S11, S21, _ = _lib.layer_smatrix(W, kz, Q, sim._Vf_inv, om, th, slices=a.digits)
+    e7 = ev(); S, _ = _lib.redheffer_bdleft(sim._Sin, [S11, S21, S21, S11], slices=a.digits)
     e8 = ev(); torch.cuda.synchronize()
     names = ["convmat", "inv(E)", "pq_assemble", "P@Q", "hessenberg(alone)", "eig(total)", "layer_smatrix", "redheffer(Sin*S)"]
     evs = [e0, e1, e2, e3, e4, e5, e6, e7, e8]
     t = {names[i]: evs[i].elapsed_time(evs[i + 1]) for i in range(8)}
-print(torch.cuda.get_device_name(0), f"order {a.order} n={2*sim.order_N} batch {a.nb}")
+print(torch.cuda.get_device_name(0), f"order {a.order} n={2*sim.order_N} batch {a.nb} digits {a.digits}")
 tot = sum(v for k, v in t.items() if k != "hessenberg(alone)")
 for k, v in t.items(): print(f"  {k:20s} {v:10.2f} ms  ({v/a.nb:9.2f} ms/point)")
 print(f"  total (excl. standalone hessenberg) {tot:.1f} ms -> {a.nb/tot*1e3:.3f} layers/s")

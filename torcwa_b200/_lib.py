@@ -30,7 +30,7 @@ _SIGS = {
     "rcwa_zgemm_tc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "rcwa_zgemm_tc_batched": (_i, [_i, _i, _i, _i, _i, _i, _d, _vp, _i, _ll, _vp, _i, _ll, _d, _d, _vp, _i, _ll, _i, _vp, _sz, _vp]),
     "rcwa_tc_split": (_i, [_vp, _i, _ll, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
-    "rcwa_tc_schedule": (_i, [_i, _i, _vp, _vp]),
+    "rcwa_tc_schedule": (_i, [_i, _i, _vp, _vp, _vp, _vp]),
     "rcwa_set_tuning": (_i, [_i, _i]),
     "rcwa_get_tuning": (_i, [_i]),
     "rcwa_lu_tinv_bytes": (_sz, [_i, _i]),
@@ -47,11 +47,11 @@ _SIGS = {
     "rcwa_kz_branch": (_i, [_vp, _vp, _ll, _vp]),
     "rcwa_eig_backward_workspace_bytes": (_sz, [_i, _i]),
     "rcwa_eig_backward": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _vp, _vp, _vp, _vp]),
-    "rcwa_layer_smatrix_workspace_bytes": (_sz, [_i, _i]),
-    "rcwa_layer_smatrix": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "rcwa_redheffer_workspace_bytes": (_sz, [_i, _i]),
-    "rcwa_redheffer": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
-    "rcwa_redheffer_bdleft": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "rcwa_layer_smatrix_workspace_bytes": (_sz, [_i, _i, _i]),
+    "rcwa_layer_smatrix": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "rcwa_redheffer_workspace_bytes": (_sz, [_i, _i, _i]),
+    "rcwa_redheffer": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    "rcwa_redheffer_bdleft": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "rcwa_blockdiag_dense": (_i, [_vp, _i, _i, _vp, _vp]),
 }
 
@@ -74,7 +74,7 @@ def load():
         for name, (res, args) in _SIGS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.rcwa_b200_abi_version() != 1:
+        if lib.rcwa_b200_abi_version() != 2:
             raise ImportError("torcwa_b200: ABI version mismatch")
         _lib = lib
         # development knob: RCWA_B200_TUNE="0=1,1=2" -> rcwa_set_tuning(key, value) (see include/rcwa_b200.h)
@@ -99,6 +99,32 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_device(fn):
+    """The library launches on the CURRENT device and stream: run every wrapper with the device of its first CUDA tensor
+    argument current, so that a simulation on cuda:1 works whatever device the caller left current (the reference accepts
+    any device index)."""
+    import functools
+
+    def first_cuda(args):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                return a.device
+            if isinstance(a, (list, tuple)):
+                d = first_cuda(a)
+                if d is not None:
+                    return d
+        return None
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        dev = first_cuda(args) or first_cuda(list(kw.values()))
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapped
+
+
 def _c128(t, name):
     if not (t.is_cuda and t.dtype == torch.complex128 and t.is_contiguous()):
         raise TypeError("%s must be a contiguous CUDA complex128 tensor" % name)
@@ -113,6 +139,7 @@ GRID_TYPES = {torch.float32: 0, torch.float64: 1, torch.complex64: 2, torch.comp
 
 
 # ------------------------------------------------------------------------------------------ wrappers
+@_on_device
 def convmat(grid, ox, oy, nb=None):
     """grid: [nx,ny] (shared) or [B,nx,ny]; -> E [B,N,N] complex128."""
     lib = load()
@@ -135,6 +162,7 @@ def convmat(grid, ox, oy, nb=None):
 _OPS = {"N": 0, "T": 1, "H": 2}
 
 
+@_on_device
 def zgemm(A, B, opa="N", opb="N", alpha=1.0, beta=0.0, out=None, cfg=None):
     """Batched C = alpha op(A) op(B) + beta C on [nb,*,*] complex128 tensors (cfg: explicit kernel configuration)."""
     lib = load()
@@ -160,6 +188,7 @@ def zgemm(A, B, opa="N", opb="N", alpha=1.0, beta=0.0, out=None, cfg=None):
     return out
 
 
+@_on_device
 def zgemm_tc(A, B, opa="N", opb="N", alpha=1.0, beta=0.0, out=None, slices=7, ws_bytes=None):
     """The same product on tcgen05 (int8 digit products, include/rcwa_b200.h: rcwa_zgemm_tc_batched); alpha real."""
     lib = load()
@@ -181,6 +210,7 @@ def zgemm_tc(A, B, opa="N", opb="N", alpha=1.0, beta=0.0, out=None, slices=7, ws
     return out
 
 
+@_on_device
 def tc_split(X, rows_contiguous, slices, conj=False):
     """Digit split of the tcgen05 GEMM on its own (tests): X [nb,a,b] -> (planes int8 [nb,3,slices,R,Kp], ex int32 [nb,R])."""
     lib = load()
@@ -196,16 +226,24 @@ def tc_split(X, rows_contiguous, slices, conj=False):
 
 
 def tc_schedule(slices, levels=4):
-    """Host-only: the per-K-chunk op table of the tcgen05 GEMM -> (ops list, groups list of dicts)."""
+    """Host-only: the per-K-chunk schedule of the tcgen05 GEMM -> (ops list, groups list of dicts incl. the compact
+    per-role tables `loads` / `mmas` the kernel walks)."""
     lib = load()
     ops = (ctypes.c_uint * 128)()
     meta = (ctypes.c_int * 64)()
-    _check(lib.rcwa_tc_schedule(int(slices), int(levels), ops, meta), "rcwa_tc_schedule")
-    groups = [dict(d0=meta[2 + 5 * g], nl=meta[3 + 5 * g], op0=meta[4 + 5 * g], nops=meta[5 + 5 * g], nloads=meta[6 + 5 * g])
-              for g in range(meta[0])]
+    loads = (ctypes.c_uint * (8 * 16))()
+    mmas = (ctypes.c_uint * (8 * 32))()
+    _check(lib.rcwa_tc_schedule(int(slices), int(levels), ops, meta, loads, mmas), "rcwa_tc_schedule")
+    groups = []
+    for g in range(meta[0]):
+        d = dict(d0=meta[2 + 6 * g], nl=meta[3 + 6 * g], op0=meta[4 + 6 * g], nops=meta[5 + 6 * g], nloads=meta[6 + 6 * g], nmma=meta[7 + 6 * g])
+        d["loads"] = list(loads)[16 * g:16 * g + d["nloads"]]
+        d["mmas"] = list(mmas)[32 * g:32 * g + d["nmma"]]
+        groups.append(d)
     return list(ops)[:meta[1]], groups
 
 
+@_on_device
 def lu_factor_(A):
     """In place on A [nb,n,n]; returns (perm, info, tinv)."""
     lib = load()
@@ -220,6 +258,7 @@ def lu_factor_(A):
     return perm, info, tinv
 
 
+@_on_device
 def lu_solve_right(LU, perm, tinv, Bm):
     """X = Bm @ inv(A) for factored LU [nb,n,n], Bm [nb,r,n]."""
     lib = load()
@@ -249,6 +288,7 @@ def inverse(A):
     return lu_solve_right(LU, perm, tinv, eye), info
 
 
+@_on_device
 def pq_assemble(eta, E, kx, ky, mu_scalar=None, Mc=None, nu=None):
     lib = load()
     nb, N = E.shape[0], E.shape[1]
@@ -262,6 +302,7 @@ def pq_assemble(eta, E, kx, ky, mu_scalar=None, Mc=None, nu=None):
 _tls = threading.local()       # pinned polling flags of rcwa_eig: one buffer per host thread (calls may run concurrently)
 
 
+@_on_device
 def eig(A):
     """A [nb,n,n] (destroyed) -> (w [nb,n], V [nb,n,n], info [nb])."""
     lib = load()
@@ -291,6 +332,7 @@ last_eig_stats = None
 last_eig_profile = None      # [nb,6,3] int64: {launches, SM cycles, longest segment} per QR pass segment (rcwa_eig_profile)
 
 
+@_on_device
 def hessenberg_(A):
     """A [nb,n,n] -> Hessenberg in place; returns Z [nb,n,n] with A_in = Z H Z^H."""
     lib = load()
@@ -303,6 +345,7 @@ def hessenberg_(A):
     return Z
 
 
+@_on_device
 def matvec_probe(A, ws, j):
     """One launch of the Hessenberg streaming mat-vec for column j (profiling; A is only read)."""
     lib = load()
@@ -315,6 +358,7 @@ def eig_workspace(n, nb, device):
     return _ws(lib.rcwa_eig_workspace_bytes(n, nb), device)
 
 
+@_on_device
 def eig_backward(lam, X, glam, gX, delta):
     """Gradient of the eigendecomposition (Eig.backward): lam [nb,n], X [nb,n,n], glam / gX or None -> (grad [nb,n,n], info)."""
     lib = load()
@@ -328,6 +372,7 @@ def eig_backward(lam, X, glam, gX, delta):
     return grad, info
 
 
+@_on_device
 def kz_branch(lam):
     lib = load()
     kz = torch.empty_like(lam)
@@ -335,54 +380,58 @@ def kz_branch(lam):
     return kz
 
 
-def layer_smatrix(W, kz, Q, vfinv, omega, thickness):
-    """-> (S11, S21, info) for the single layer (S22 = S11, S12 = S21)."""
+@_on_device
+def layer_smatrix(W, kz, Q, vfinv, omega, thickness, slices=0):
+    """-> (S11, S21, info) for the single layer (S22 = S11, S12 = S21).  slices: digits of the tcgen05 GEMM (0 = fp64 DMMA)."""
     lib = load()
     nb, n = W.shape[0], W.shape[1]
     N = n // 2
     S11 = torch.empty_like(W)
     S21 = torch.empty_like(W)
     info = torch.zeros((nb,), dtype=torch.int32, device=W.device)
-    ws = _ws(lib.rcwa_layer_smatrix_workspace_bytes(N, nb), W.device)
+    ws = _ws(lib.rcwa_layer_smatrix_workspace_bytes(N, nb, int(slices)), W.device)
     omega = omega.to(torch.float64).contiguous()
     thickness = thickness.to(torch.float64).contiguous()
     _check(lib.rcwa_layer_smatrix(_ptr(_c128(W, "W")), _ptr(_c128(kz, "kz")), _ptr(_c128(Q, "Q")), _ptr(_c128(vfinv, "vfinv")),
-                                  _ptr(omega), _ptr(thickness), nb, N, _ptr(S11), _ptr(S21), _ptr(ws), _ptr(info), _stream()),
+                                  _ptr(omega), _ptr(thickness), nb, N, _ptr(S11), _ptr(S21), _ptr(ws), _ptr(info), int(slices), _stream()),
            "rcwa_layer_smatrix")
     return S11, S21, info
 
 
-def redheffer(Sm, Sn):
+@_on_device
+def redheffer(Sm, Sn, slices=0):
     """Star product of two S-matrices given as lists [S11,S21,S12,S22] of [nb,n,n]; -> (list, info)."""
     lib = load()
     nb, n = Sm[0].shape[0], Sm[0].shape[1]
     out = [torch.empty_like(Sm[0]) for _ in range(4)]
     info = torch.zeros((nb,), dtype=torch.int32, device=Sm[0].device)
-    ws = _ws(lib.rcwa_redheffer_workspace_bytes(n, nb), Sm[0].device)
+    ws = _ws(lib.rcwa_redheffer_workspace_bytes(n, nb, int(slices)), Sm[0].device)
     arr = ctypes.c_void_p * 4
     a_m = arr(*[t.data_ptr() for t in (_c128(x, "Sm") for x in Sm)])
     a_n = arr(*[t.data_ptr() for t in (_c128(x, "Sn") for x in Sn)])
     a_o = arr(*[t.data_ptr() for t in out])
-    _check(lib.rcwa_redheffer(a_m, a_n, a_o, nb, n, _ptr(ws), _ptr(info), _stream()), "rcwa_redheffer")
+    _check(lib.rcwa_redheffer(a_m, a_n, a_o, nb, n, _ptr(ws), _ptr(info), int(slices), _stream()), "rcwa_redheffer")
     return out, info
 
 
-def redheffer_bdleft(Sm_bd, Sn):
+@_on_device
+def redheffer_bdleft(Sm_bd, Sn, slices=0):
     """Star product with a 2x2-block-diagonal left factor: Sm_bd = four [nb,4,N] tensors, Sn dense."""
     lib = load()
     nb, n = Sn[0].shape[0], Sn[0].shape[1]
     out = [torch.empty_like(Sn[0]) for _ in range(4)]
     info = torch.zeros((nb,), dtype=torch.int32, device=Sn[0].device)
-    ws = _ws(lib.rcwa_redheffer_workspace_bytes(n, nb), Sn[0].device)
+    ws = _ws(lib.rcwa_redheffer_workspace_bytes(n, nb, int(slices)), Sn[0].device)
     arr = ctypes.c_void_p * 4
     keep = [_c128(x.contiguous(), "Sm_bd") for x in Sm_bd]
     a_m = arr(*[t.data_ptr() for t in keep])
     a_n = arr(*[t.data_ptr() for t in (_c128(x, "Sn") for x in Sn)])
     a_o = arr(*[t.data_ptr() for t in out])
-    _check(lib.rcwa_redheffer_bdleft(a_m, a_n, a_o, nb, n // 2, _ptr(ws), _ptr(info), _stream()), "rcwa_redheffer_bdleft")
+    _check(lib.rcwa_redheffer_bdleft(a_m, a_n, a_o, nb, n // 2, _ptr(ws), _ptr(info), int(slices), _stream()), "rcwa_redheffer_bdleft")
     return out, info
 
 
+@_on_device
 def blockdiag_dense(d4):
     """d4 [nb,4,N] -> dense [nb,2N,2N]."""
     lib = load()

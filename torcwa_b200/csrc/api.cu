@@ -102,19 +102,23 @@ int rcwa_tc_split(const void* X, int ld, long long stride, int rows_contiguous, 
     return cu(tc_split_debug((const cplx*)X, ld, stride, rows_contiguous, R, Kc, slices, conj, (signed char*)planes, ex, nb, S(stream)));
 }
 
-int rcwa_tc_schedule(int slices, int levels, unsigned* ops, int* meta) {
+int rcwa_tc_schedule(int slices, int levels, unsigned* ops, int* meta, unsigned* loads, unsigned* mmas) {
     if (slices < 2 || slices > TC_MAXS) return -1;
     if (levels < 1 || levels > 4) return -2;
     if (!ops) return -3;
     if (!meta) return -4;
     TcSchedule sch;
     tc_build_schedule(slices, levels, &sch);
+    TcTables tab;
+    tc_compact_schedule(&sch, &tab);
     for (int i = 0; i < TC_MAXOPS; ++i) ops[i] = i < sch.nops ? sch.ops[i] : 0u;
     meta[0] = sch.ngroups; meta[1] = sch.nops;
     for (int g = 0; g < sch.ngroups; ++g) {
-        meta[2 + 5 * g] = sch.g[g].d0; meta[3 + 5 * g] = sch.g[g].nl; meta[4 + 5 * g] = sch.g[g].op0;
-        meta[5 + 5 * g] = sch.g[g].nops; meta[6 + 5 * g] = sch.g[g].nloads;
+        meta[2 + 6 * g] = sch.g[g].d0; meta[3 + 6 * g] = sch.g[g].nl; meta[4 + 6 * g] = sch.g[g].op0;
+        meta[5 + 6 * g] = sch.g[g].nops; meta[6 + 6 * g] = tab.nloads[g]; meta[7 + 6 * g] = tab.nmma[g];
     }
+    if (loads) for (int i = 0; i < TC_MAXS * TC_MAXLOADS; ++i) loads[i] = tab.loads[i];
+    if (mmas) for (int i = 0; i < TC_MAXS * TC_MAXMMAS; ++i) mmas[i] = tab.mmas[i];
     return 0;
 }
 
@@ -126,6 +130,8 @@ int rcwa_set_tuning(int key, int value) {
 int rcwa_get_tuning(int key) { return gemm_get_tuning(key); }
 
 size_t rcwa_lu_tinv_bytes(int n, int nb) { return align256(lu_tinv_elems(n, nb > 0 ? nb : 1) * sizeof(cplx)); }
+static size_t tinv_bytes(int n, int nb, int slices) { return align256(lu_tinv_elems(n, nb > 0 ? nb : 1, slices) * sizeof(cplx)); }
+static int norm_slices(int s) { return (s >= 2 && s <= TC_MAXS) ? s : 0; }
 
 int rcwa_lu_factor(void* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info, void* tinv, void* gs, void* stream) {
     if (!A) return -1;
@@ -270,13 +276,14 @@ int rcwa_eig_backward(const void* lam, const void* X, const void* glam, const vo
 }
 
 // workspace layout helpers ---------------------------------------------------------------------
-size_t rcwa_layer_smatrix_workspace_bytes(int N, int nb) {
+size_t rcwa_layer_smatrix_workspace_bytes(int N, int nb, int gemm_slices) {
     const size_t n = 2 * (size_t)N, mat = align256(n * n * nb * sizeof(cplx));
-    return 6 * mat + 2 * align256(n * nb * sizeof(int)) + rcwa_lu_tinv_bytes((int)n, nb) + rcwa_gemm_scratch_bytes(nb);
+    const int sl = norm_slices(gemm_slices);
+    return 6 * mat + 2 * align256(n * nb * sizeof(int)) + tinv_bytes((int)n, nb, sl) + rcwa_gemm_scratch_bytes(nb) + align256(tc_ctx_bytes((int)n, nb, sl));
 }
 
 int rcwa_layer_smatrix(const void* W, const void* kz, const void* Q, const void* vfinv, const double* omega,
-                       const double* thickness, int nb, int N, void* S11, void* S21, void* ws, int* info, void* stream) {
+                       const double* thickness, int nb, int N, void* S11, void* S21, void* ws, int* info, int gemm_slices, void* stream) {
     if (!W) return -1;
     if (!kz) return -2;
     if (!Q) return -3;
@@ -302,28 +309,31 @@ int rcwa_layer_smatrix(const void* W, const void* kz, const void* Q, const void*
     cplx* b5 = (cplx*)p; p += mat;
     int* ipiv = (int*)p; p += align256((size_t)n * nb * sizeof(int));
     int* perm = (int*)p; p += align256((size_t)n * nb * sizeof(int));
-    cplx* tinv = (cplx*)p; p += rcwa_lu_tinv_bytes(n, nb);
-    ZGemmProblem* gs = (ZGemmProblem*)p;
+    const int sl = norm_slices(gemm_slices);
+    cplx* tinv = (cplx*)p; p += tinv_bytes(n, nb, sl);
+    ZGemmProblem* gs = (ZGemmProblem*)p; p += rcwa_gemm_scratch_bytes(nb);
+    TcCtx tc = {sl, p, tc_ctx_bytes(n, nb, sl)};
     // QW = Q * W
-    CK(zgemm_strided(OP_N, OP_N, n, n, n, C(1, 0), (const cplx*)Q, n, ms, (const cplx*)W, n, ms, C(0, 0), b0, n, ms, nb, gs, st));
+    CK(gemm_auto(&tc, OP_N, OP_N, n, n, n, 1.0, (const cplx*)Q, n, ms, (const cplx*)W, n, ms, C(0, 0), b0, n, ms, nb, gs, st));
     // M+ (b1), M- (b2), R+ (b3), R- (b4)
     CK(layer_form((const cplx*)W, b0, (const cplx*)kz, (const cplx*)vfinv, omega, thickness, nb, N, b1, b2, b3, b4, st));
     // T+ = R+ M+^-1  -> b0
-    CK(lu_factor(b1, ms, n, n, nb, ipiv, perm, info, tinv, gs, st));
-    CK(lu_solve_right(b1, ms, n, n, perm, tinv, b3, ms, n, n, b0, ms, n, b5, nb, gs, st));
+    CK(lu_factor(b1, ms, n, n, nb, ipiv, perm, info, tinv, gs, st, true, sl));
+    CK(lu_solve_right(b1, ms, n, n, perm, tinv, b3, ms, n, n, b0, ms, n, b5, nb, gs, st, &tc));
     // T- = R- M-^-1  -> b3   (info keeps the first failure: the second factorisation does not clear it)
-    CK(lu_factor(b2, ms, n, n, nb, ipiv, perm, info, tinv, gs, st, false));
-    CK(lu_solve_right(b2, ms, n, n, perm, tinv, b4, ms, n, n, b3, ms, n, b5, nb, gs, st));
+    CK(lu_factor(b2, ms, n, n, nb, ipiv, perm, info, tinv, gs, st, false, sl));
+    CK(lu_solve_right(b2, ms, n, n, perm, tinv, b4, ms, n, n, b3, ms, n, b5, nb, gs, st, &tc));
     CK(layer_finish(b0, b3, nb, n, (cplx*)S11, (cplx*)S21, st));
     return 0;
 }
 
-size_t rcwa_redheffer_workspace_bytes(int n, int nb) {
+size_t rcwa_redheffer_workspace_bytes(int n, int nb, int gemm_slices) {
     const size_t mat = align256((size_t)n * n * nb * sizeof(cplx));
-    return 5 * mat + 2 * align256((size_t)n * nb * sizeof(int)) + rcwa_lu_tinv_bytes(n, nb) + rcwa_gemm_scratch_bytes(nb);
+    const int sl = norm_slices(gemm_slices);
+    return 5 * mat + 2 * align256((size_t)n * nb * sizeof(int)) + tinv_bytes(n, nb, sl) + rcwa_gemm_scratch_bytes(nb) + align256(tc_ctx_bytes(n, nb, sl));
 }
 
-int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const out[4], int nb, int n, void* ws, int* info, void* stream) {
+int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const out[4], int nb, int n, void* ws, int* info, int gemm_slices, void* stream) {
     if (!Sm) return -1;
     if (!Sn) return -2;
     if (!out) return -3;
@@ -347,21 +357,23 @@ int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const
     cplx* T = (cplx*)p; p += mat;
     int* ipiv = (int*)p; p += align256((size_t)n * nb * sizeof(int));
     int* perm = (int*)p; p += align256((size_t)n * nb * sizeof(int));
-    cplx* tinv = (cplx*)p; p += rcwa_lu_tinv_bytes(n, nb);
-    ZGemmProblem* gs = (ZGemmProblem*)p;
+    const int sl = norm_slices(gemm_slices);
+    cplx* tinv = (cplx*)p; p += tinv_bytes(n, nb, sl);
+    ZGemmProblem* gs = (ZGemmProblem*)p; p += rcwa_gemm_scratch_bytes(nb);
+    TcCtx tc = {sl, p, tc_ctx_bytes(n, nb, sl)};
     const cplx *Sm11 = (const cplx*)Sm[0], *Sm21 = (const cplx*)Sm[1], *Sm12 = (const cplx*)Sm[2], *Sm22 = (const cplx*)Sm[3];
     const cplx *Sn11 = (const cplx*)Sn[0], *Sn21 = (const cplx*)Sn[1], *Sn12 = (const cplx*)Sn[2], *Sn22 = (const cplx*)Sn[3];
     cplx *O11 = (cplx*)out[0], *O21 = (cplx*)out[1], *O12 = (cplx*)out[2], *O22 = (cplx*)out[3];
-    const cplx one = C(1, 0), zero = C(0, 0), mone = C(-1, 0);
+    const cplx one = C(1, 0), zero = C(0, 0);
     const size_t bytes = (size_t)ms * nb * sizeof(cplx);
-#define GEMM(a, b, beta, c) CK(zgemm_strided(OP_N, OP_N, n, n, n, one, a, n, ms, b, n, ms, beta, c, n, ms, nb, gs, st))
+#define GEMM(a, b, beta, c) CK(gemm_auto(&tc, OP_N, OP_N, n, n, n, 1.0, a, n, ms, b, n, ms, beta, c, n, ms, nb, gs, st))
     // D = I - Sm12 Sn21
     CK(set_identity(D, n, n, ms, nb, st));
-    CK(zgemm_strided(OP_N, OP_N, n, n, n, mone, Sm12, n, ms, Sn21, n, ms, one, D, n, ms, nb, gs, st));
-    CK(lu_factor(D, ms, n, n, nb, ipiv, perm, info, tinv, gs, st));
+    CK(gemm_auto(&tc, OP_N, OP_N, n, n, n, -1.0, Sm12, n, ms, Sn21, n, ms, one, D, n, ms, nb, gs, st));
+    CK(lu_factor(D, ms, n, n, nb, ipiv, perm, info, tinv, gs, st, true, sl));
     // Y1 = Sn11 D^-1 ; Y2 = Sn21 D^-1     (T is free until later: it is the solves' work buffer)
-    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn11, ms, n, n, Y1, ms, n, T, nb, gs, st));
-    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn21, ms, n, n, Y2, ms, n, T, nb, gs, st));
+    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn11, ms, n, n, Y1, ms, n, T, nb, gs, st, &tc));
+    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn21, ms, n, n, Y2, ms, n, T, nb, gs, st, &tc));
     // G = Sm12 Sn22
     GEMM(Sm12, Sn22, zero, G);
     // S11 = Y1 Sm11
@@ -381,7 +393,7 @@ int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const
     return 0;
 }
 
-int rcwa_redheffer_bdleft(const void* const Sm_bd[4], const void* const Sn[4], void* const out[4], int nb, int N, void* ws, int* info, void* stream) {
+int rcwa_redheffer_bdleft(const void* const Sm_bd[4], const void* const Sn[4], void* const out[4], int nb, int N, void* ws, int* info, int gemm_slices, void* stream) {
     if (!Sm_bd) return -1;
     if (!Sn) return -2;
     if (!out) return -3;
@@ -406,8 +418,10 @@ int rcwa_redheffer_bdleft(const void* const Sm_bd[4], const void* const Sn[4], v
     cplx* T = (cplx*)p; p += mat;
     int* ipiv = (int*)p; p += align256((size_t)n * nb * sizeof(int));
     int* perm = (int*)p; p += align256((size_t)n * nb * sizeof(int));
-    cplx* tinv = (cplx*)p; p += rcwa_lu_tinv_bytes(n, nb);
-    ZGemmProblem* gs = (ZGemmProblem*)p;
+    const int sl = norm_slices(gemm_slices);
+    cplx* tinv = (cplx*)p; p += tinv_bytes(n, nb, sl);
+    ZGemmProblem* gs = (ZGemmProblem*)p; p += rcwa_gemm_scratch_bytes(nb);
+    TcCtx tc = {sl, p, tc_ctx_bytes(n, nb, sl)};
     const cplx *m11 = (const cplx*)Sm_bd[0], *m21 = (const cplx*)Sm_bd[1], *m12 = (const cplx*)Sm_bd[2], *m22 = (const cplx*)Sm_bd[3];
     const cplx *Sn11 = (const cplx*)Sn[0], *Sn21 = (const cplx*)Sn[1], *Sn12 = (const cplx*)Sn[2], *Sn22 = (const cplx*)Sn[3];
     cplx *O11 = (cplx*)out[0], *O21 = (cplx*)out[1], *O12 = (cplx*)out[2], *O22 = (cplx*)out[3];
@@ -416,18 +430,18 @@ int rcwa_redheffer_bdleft(const void* const Sm_bd[4], const void* const Sn[4], v
     // D = I - Sm12 Sn21          (Sm12 is four diagonals: an O(n^2) row combination, not a GEMM)
     CK(set_identity(D, n, n, ms, nb, st));
     CK(bd_left_mul(m12, Sn21, nb, N, n, mone, one, D, st));
-    CK(lu_factor(D, ms, n, n, nb, ipiv, perm, info, tinv, gs, st));
-    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn11, ms, n, n, Y1, ms, n, T, nb, gs, st));      // Y1 = Sn11 D^-1 (T = work)
-    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn21, ms, n, n, Y2, ms, n, T, nb, gs, st));      // Y2 = Sn21 D^-1
+    CK(lu_factor(D, ms, n, n, nb, ipiv, perm, info, tinv, gs, st, true, sl));
+    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn11, ms, n, n, Y1, ms, n, T, nb, gs, st, &tc));      // Y1 = Sn11 D^-1 (T = work)
+    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn21, ms, n, n, Y2, ms, n, T, nb, gs, st, &tc));      // Y2 = Sn21 D^-1
     CK(bd_left_mul(m12, Sn22, nb, N, n, one, zero, G, st));                             // G = Sm12 Sn22
     CK(bd_right_mul(m11, Y1, nb, N, n, one, zero, O11, st));                            // S11 = Y1 Sm11
     CK(cudaMemcpyAsync(O12, Sn12, bytes, cudaMemcpyDeviceToDevice, st));                // S12 = Sn12 + Y1 G
-    CK(zgemm_strided(OP_N, OP_N, n, n, n, one, Y1, n, ms, G, n, ms, one, O12, n, ms, nb, gs, st));
+    CK(gemm_auto(&tc, OP_N, OP_N, n, n, n, 1.0, Y1, n, ms, G, n, ms, one, O12, n, ms, nb, gs, st));
     CK(bd_right_mul(m11, Y2, nb, N, n, one, zero, T, st));                              // S21 = Sm21 + Sm22 (Y2 Sm11)
     CK(bd_left_mul(m22, T, nb, N, n, one, zero, O21, st));
     CK(bd_add(m21, nb, N, one, O21, st));
     CK(cudaMemcpyAsync(T, Sn22, bytes, cudaMemcpyDeviceToDevice, st));                  // S22 = Sm22 (Sn22 + Y2 G)
-    CK(zgemm_strided(OP_N, OP_N, n, n, n, one, Y2, n, ms, G, n, ms, one, T, n, ms, nb, gs, st));
+    CK(gemm_auto(&tc, OP_N, OP_N, n, n, n, 1.0, Y2, n, ms, G, n, ms, one, T, n, ms, nb, gs, st));
     CK(bd_left_mul(m22, T, nb, N, n, one, zero, O22, st));
     return 0;
 }

@@ -236,8 +236,15 @@ cudaError_t hessenberg_blocked(cplx* A, int n, int nb, cplx* Z, char* wsb, cudaS
     cplx* Y = pan + (size_t)n * HB_NB;
     cplx* T = Y + (size_t)n * HB_NB;
     const size_t smem_col = sizeof(cplx) * ((size_t)n + 16 * HB_NB);
-    static bool attr_set = false;
-    if (!attr_set) { HK(cudaFuncSetAttribute(hb_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    {   // per-device attribute (one process may drive several GPUs)
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            HK(cudaFuncSetAttribute(hb_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+    }
     if (smem_col > 200 * 1024) return cudaErrorInvalidValue;
     const cplx one = C(1, 0), zero = C(0, 0), mone = C(-1, 0);
     const int last = n - 3;                                  // last column that gets a reflector

@@ -36,12 +36,23 @@ cudaError_t zgemm_strided(int opa, int opb, int M, int N, int K, cplx alpha, con
 // ---- tc_gemm.cu: complex fp64-grade GEMM from int8 digit products on tcgen05 (see the file header)
 #define TC_MAXS 8            // most digits (slices) per number
 #define TC_MAXOPS 128
+#define TC_MAXLOADS 16       // loads / MMA ops of one level group per K chunk
+#define TC_MAXMMAS 32
 #define TC_OP_LOAD_A 0u      // op word: bits 0-1 type; loads: bits 2-5 digit index;
 #define TC_OP_LOAD_B 1u      //   MMA: bits 2-6 / 7-11 = index of the A / B load inside this (group, K chunk) iteration, bits 12-13 level - d0,
 #define TC_OP_MMA 2u         //   bit 14 first MMA of that level in the iteration, bit 15 / 16 = last use of the A / B slot (release it)
 #define TC_E_ZERO (-100000)  // exponent marker of an all-zero row / column
-struct TcGroup { int d0, nl, op0, nops, nloads; };
+struct TcGroup { int d0, nl, op0, nops, nloads, nmma; };
+// The schedule in two forms: `ops` (loads and MMAs interleaved in issue order; what the tests reason about) and the
+// compact per-role tables the kernel walks:  loads[g][i] = bit 0: B operand, bits 1-4: digit;
+// mmas[g][i] = bits 0-4 / 5-9: A / B load index, 10-11 level, 12 first, 13 / 14 release A / B, 15-18 loads to acquire first.
 struct TcSchedule { int s, ngroups, nops, pad; TcGroup g[TC_MAXS]; unsigned ops[TC_MAXOPS]; };
+// steps[g][p] (two words): one A digit plane with ALL the B planes it multiplies in this group (<= 4 pairs, 16 MMAs):
+//   word 0 = bits 0-4 A load index, 5-7 pairs, 8-11 loads to acquire first, 12-16 (1 + index of the B load released after the step, 0 = none)
+//   word 1 = per pair j, byte j: bits 0-4 B load index, 5-6 level, 7 first MMA of that level in the iteration
+struct TcTables { int s, ngroups; int d0[TC_MAXS], nl[TC_MAXS], nloads[TC_MAXS], nmma[TC_MAXS], nsteps[TC_MAXS];
+                  unsigned loads[TC_MAXS * TC_MAXLOADS]; unsigned mmas[TC_MAXS * TC_MAXMMAS]; unsigned steps[TC_MAXS * TC_MAXS * 2]; };
+void tc_compact_schedule(const TcSchedule* sch, TcTables* tab);
 void tc_build_schedule(int s, int nl, TcSchedule* sch);
 size_t tc_workspace_bytes(int M, int N, int K, int nb, int s);      // split storage for the whole batch
 size_t tc_workspace_min_bytes(int M, int N, int K, int s);          // ... for one matrix (the routine then runs in chunks)
@@ -52,6 +63,15 @@ cudaError_t tc_zgemm_strided(int s, int opa, int opb, int M, int N, int K, doubl
                              char* ws, size_t ws_bytes, cudaStream_t st);
 cudaError_t tc_split_debug(const cplx* X, int ld, long long stride, int rows_contiguous, int R, int Kc, int s, int conj,
                            signed char* out, int* ex, int nmat, cudaStream_t st);
+
+// Which GEMM engine a composite routine uses for its dense products: slices = 0 -> fp64 DMMA (zgemm.cu) everywhere;
+// 2..8 -> products large enough to pay for the digit split go through the tcgen05 kernel with that many digits.
+struct TcCtx { int slices; char* ws; size_t ws_bytes; };
+// alpha real; falls back to the DMMA kernel for small shapes or when tc is null / off
+cudaError_t gemm_auto(const TcCtx* tc, int opa, int opb, int M, int N, int K, double alpha, const cplx* A, int lda, long long sa,
+                      const cplx* B, int ldb, long long sb, cplx beta, cplx* C, int ldc, long long sc, int batch,
+                      ZGemmProblem* gscratch, cudaStream_t st);
+size_t tc_ctx_bytes(int n, int nb, int slices);     // digit workspace a composite routine reserves for n x n x n products of a batch of nb
 
 // ---- convmat.cu
 size_t convmat_workspace_elems(int nx, int ny, int nb, int ox, int oy);
@@ -75,13 +95,14 @@ cudaError_t set_identity(cplx* A, int n, int lda, long long stride, int nb, cuda
 cudaError_t axpby(cplx alpha, const cplx* X, cplx beta, cplx* Y, size_t total, cudaStream_t st);
 
 // ---- lu.cu
-size_t lu_tinv_elems(int n, int nb);     // complex elements of the inverted-diagonal-block buffer of lu_factor
+// tc_slices >= 2: the factorisation prepares 512-wide inverted diagonal blocks for the tcgen05 solve (else 128-wide, DMMA)
+size_t lu_tinv_elems(int n, int nb, int tc_slices = 0);     // complex elements of the inverted-diagonal-block buffer of lu_factor
 cudaError_t lu_factor(cplx* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info, cplx* tinv,
-                      ZGemmProblem* gscratch, cudaStream_t st, bool clear_info = true);
-// Yw: work buffer shaped like X
+                      ZGemmProblem* gscratch, cudaStream_t st, bool clear_info = true, int tc_slices = 0);
+// Yw: work buffer shaped like X; tc (optional) must carry the same slices value the factorisation was given
 cudaError_t lu_solve_right(const cplx* LU, long long lustride, int n, int lda, const int* perm, const cplx* tinv,
                            const cplx* Bm, long long bstride, int ldb, int nrows, cplx* X, long long xstride, int ldx,
-                           cplx* Yw, int nb, ZGemmProblem* gscratch, cudaStream_t st);
+                           cplx* Yw, int nb, ZGemmProblem* gscratch, cudaStream_t st, const TcCtx* tc = nullptr);
 
 // ---- hess.cu
 size_t hessenberg_workspace_bytes(int n, int nb);

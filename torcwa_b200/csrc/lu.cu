@@ -25,7 +25,8 @@
 #endif
 
 #define LU_NB 32
-#define SOLVE_NB 128        // block size of the triangular solves (diagonal blocks are inverted once per factorisation)
+#define SOLVE_NB 128        // block size of the triangular solves on the fp64 (DMMA) path (diagonal blocks are inverted once per factorisation)
+#define SOLVE_NB_TC 512     // ... on the tcgen05 path: right-looking updates with K = 512 (tc_gemm.cu)
 
 // ------------------------------------------------------------------------------------------------
 // panel factorisation: rows [k0, k0+nbe) of A (n x n, leading dim lda), columns [k0, n)
@@ -221,29 +222,29 @@ __global__ void lu_colswap_kernel(cplx* A, long long stride, int n, int lda, int
 // One thread per column of the inverse (back-substitution down its own column; every thread reads the
 // same factor entry -> broadcast loads; the inverse column lives in the output itself).
 // Out-of-range rows/columns of the last block behave like an identity extension.
-__global__ void __launch_bounds__(SOLVE_NB)
-tri_inv_kernel(const cplx* __restrict__ LU, long long lustride, int n, int lda, cplx* __restrict__ tinv, int nblk) {
+__global__ void __launch_bounds__(SOLVE_NB_TC)
+tri_inv_kernel(const cplx* __restrict__ LU, long long lustride, int n, int lda, cplx* __restrict__ tinv, int nblk, int SNB) {
     const int kb = blockIdx.x, b = blockIdx.y, which = blockIdx.z, j = threadIdx.x;
-    const int k0 = kb * SOLVE_NB;
-    const int w = (n - k0 < SOLVE_NB) ? n - k0 : SOLVE_NB;
+    const int k0 = kb * SNB;
+    const int w = (n - k0 < SNB) ? n - k0 : SNB;
     const cplx* F = LU + (size_t)b * lustride + (size_t)k0 * lda + k0;
-    cplx* X = tinv + (((size_t)b * 2 + which) * nblk + kb) * SOLVE_NB * SOLVE_NB;
-    for (int i = 0; i < SOLVE_NB; ++i) X[i * SOLVE_NB + j] = C(i == j ? 1.0 : 0.0, 0.0);
+    cplx* X = tinv + (((size_t)b * 2 + which) * nblk + kb) * SNB * SNB;
+    for (int i = 0; i < SNB; ++i) X[i * SNB + j] = C(i == j ? 1.0 : 0.0, 0.0);
     if (j >= w) return;
     if (which == 0) {
         // U unit upper:  x_j = 1 ; x_i = -sum_{k=i+1..j} U[i][k] x_k   (i = j-1 .. 0)
         for (int i = j - 1; i >= 0; --i) {
             cplx acc = C(0, 0);
-            for (int k = i + 1; k <= j; ++k) acc = cfma(F[(size_t)i * lda + k], X[k * SOLVE_NB + j], acc);
-            X[i * SOLVE_NB + j] = cneg(acc);
+            for (int k = i + 1; k <= j; ++k) acc = cfma(F[(size_t)i * lda + k], X[k * SNB + j], acc);
+            X[i * SNB + j] = cneg(acc);
         }
     } else {
         // L lower (non-unit):  x_j = 1/L_jj ; x_i = -(sum_{k=j..i-1} L[i][k] x_k) / L_ii   (i = j+1 .. w-1)
-        X[j * SOLVE_NB + j] = cinv(F[(size_t)j * lda + j]);
+        X[j * SNB + j] = cinv(F[(size_t)j * lda + j]);
         for (int i = j + 1; i < w; ++i) {
             cplx acc = C(0, 0);
-            for (int k = j; k < i; ++k) acc = cfma(F[(size_t)i * lda + k], X[k * SOLVE_NB + j], acc);
-            X[i * SOLVE_NB + j] = cneg(cdiv(acc, F[(size_t)i * lda + i]));
+            for (int k = j; k < i; ++k) acc = cfma(F[(size_t)i * lda + k], X[k * SNB + j], acc);
+            X[i * SNB + j] = cneg(cdiv(acc, F[(size_t)i * lda + i]));
         }
     }
 }
@@ -287,10 +288,15 @@ __global__ void gather_cols_kernel(const cplx* __restrict__ Bm, long long bstrid
 namespace rcwa {
 
 // A: [B] matrices n x n (lda, stride) overwritten by L\U; ipiv, perm: [B,n] ints; info: [B] ints
-size_t lu_tinv_elems(int n, int nb) { return (size_t)nb * 2 * ((n + SOLVE_NB - 1) / SOLVE_NB) * SOLVE_NB * SOLVE_NB; }
+int lu_solve_block(int tc_slices) { return tc_slices >= 2 ? SOLVE_NB_TC : SOLVE_NB; }
+size_t lu_tinv_elems(int n, int nb, int tc_slices) {
+    const int S = lu_solve_block(tc_slices);
+    return (size_t)nb * 2 * ((n + S - 1) / S) * S * S;
+}
 
 cudaError_t lu_factor(cplx* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info, cplx* tinv,
-                      ZGemmProblem* gscratch, cudaStream_t st, bool clear_info) {
+                      ZGemmProblem* gscratch, cudaStream_t st, bool clear_info, int tc_slices) {
+    const int SNB = lu_solve_block(tc_slices);
     if (clear_info) cudaMemsetAsync(info, 0, sizeof(int) * nb, st);
     const cplx one = C(1, 0), mone = C(-1, 0);
     for (int k0 = 0; k0 < n; k0 += LU_NB) {
@@ -301,7 +307,7 @@ cudaError_t lu_factor(cplx* A, long long stride, int n, int lda, int nb, int* ip
         if (rem > 0) {
             // A21 := A21 * U11^-1 (in place: one tile spans the nbe <= 32 columns).  `tinv` is free until the end of the
             // factorisation and serves as the scratch of the inverted diagonal block.
-            const long long ustride = (long long)2 * ((n + SOLVE_NB - 1) / SOLVE_NB) * SOLVE_NB * SOLVE_NB;
+            const long long ustride = (long long)2 * ((n + SNB - 1) / SNB) * SNB * SNB;
             tri_inv_panel_kernel<<<nb, LU_NB, 0, st>>>(A, stride, lda, k0, nbe, tinv, ustride);
             cudaError_t e = zgemm_strided(OP_N, OP_N, rem, nbe, nbe, one, A + (size_t)(k0 + nbe) * lda + k0, lda, stride,
                                           tinv, LU_NB, ustride, C(0, 0), A + (size_t)(k0 + nbe) * lda + k0, lda, stride, nb, gscratch, st);
@@ -314,8 +320,8 @@ cudaError_t lu_factor(cplx* A, long long stride, int n, int lda, int nb, int* ip
         }
     }
     lu_perm_kernel<<<nb, 256, n * sizeof(int), st>>>(ipiv, n, perm);
-    const int nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
-    tri_inv_kernel<<<dim3(nblk, nb, 2), SOLVE_NB, 0, st>>>(A, stride, n, lda, tinv, nblk);
+    const int nblk = (n + SNB - 1) / SNB;
+    tri_inv_kernel<<<dim3(nblk, nb, 2), SNB, 0, st>>>(A, stride, n, lda, tinv, nblk, SNB);
     return cudaGetLastError();
 }
 
@@ -326,8 +332,37 @@ cudaError_t lu_factor(cplx* A, long long stride, int n, int lda, int nb, int* ip
 // of rank-32 updates.
 cudaError_t lu_solve_right(const cplx* LU, long long lustride, int n, int lda, const int* perm, const cplx* tinv,
                            const cplx* Bm, long long bstride, int ldb, int nrows, cplx* X, long long xstride, int ldx,
-                           cplx* Yw, int nb, ZGemmProblem* gscratch, cudaStream_t st) {
+                           cplx* Yw, int nb, ZGemmProblem* gscratch, cudaStream_t st, const TcCtx* tc) {
     const cplx one = C(1, 0), mone = C(-1, 0), zero = C(0, 0);
+    if (tc && tc->slices >= 2) {
+        // tcgen05 path: RIGHT-looking over SOLVE_NB_TC-wide column blocks, so that every product has K = 512 and each
+        // operand block is split into digits once:   Y_k = X_k Uinv_k ;  X_{>k} -= Y_k U_{k,>k}   (forward), then
+        // Z_k = Y_k Linv_k ;  Y_{<k} -= Z_k L_{k,<k}   (backward; Z overwrites the X buffer).
+        const int S = SOLVE_NB_TC, nblk = (n + S - 1) / S;
+        const long long tstride = (long long)2 * nblk * S * S;
+        const cplx* Uinv = tinv;
+        const cplx* Linv = tinv + (size_t)nblk * S * S;
+        gather_cols_kernel<<<dim3(nrows, nb), 256, 0, st>>>(Bm, bstride, ldb, perm, n, X, xstride, ldx);
+#define SK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
+        for (int kb = 0; kb < nblk; ++kb) {
+            const int c0 = kb * S, w = (n - c0 < S) ? n - c0 : S, c1 = c0 + w;
+            SK(gemm_auto(tc, OP_N, OP_N, nrows, w, w, 1.0, X + c0, ldx, xstride, Uinv + (size_t)kb * S * S, S, tstride, zero,
+                         Yw + c0, ldx, xstride, nb, gscratch, st));
+            if (c1 < n)
+                SK(gemm_auto(tc, OP_N, OP_N, nrows, n - c1, w, -1.0, Yw + c0, ldx, xstride, LU + (size_t)c0 * lda + c1, lda, lustride, one,
+                             X + c1, ldx, xstride, nb, gscratch, st));
+        }
+        for (int kb = nblk - 1; kb >= 0; --kb) {
+            const int c0 = kb * S, w = (n - c0 < S) ? n - c0 : S;
+            SK(gemm_auto(tc, OP_N, OP_N, nrows, w, w, 1.0, Yw + c0, ldx, xstride, Linv + (size_t)kb * S * S, S, tstride, zero,
+                         X + c0, ldx, xstride, nb, gscratch, st));
+            if (c0 > 0)
+                SK(gemm_auto(tc, OP_N, OP_N, nrows, c0, w, -1.0, X + c0, ldx, xstride, LU + (size_t)c0 * lda, lda, lustride, one,
+                             Yw, ldx, xstride, nb, gscratch, st));
+        }
+#undef SK
+        return cudaGetLastError();
+    }
     const int nblk = (n + SOLVE_NB - 1) / SOLVE_NB;
     const long long tstride = (long long)2 * nblk * SOLVE_NB * SOLVE_NB;      // per matrix
     const cplx* Uinv = tinv;

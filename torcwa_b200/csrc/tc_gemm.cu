@@ -35,7 +35,7 @@ void tc_build_schedule(int s, int nl, TcSchedule* sch) {
     for (int d0 = 0; d0 < s; d0 += nl) {
         TcGroup& g = sch->g[sch->ngroups++];
         const int d1 = (d0 + nl - 1 < s - 1) ? d0 + nl - 1 : s - 1;
-        g.d0 = d0; g.nl = d1 - d0 + 1; g.op0 = sch->nops; g.nloads = 0;
+        g.d0 = d0; g.nl = d1 - d0 + 1; g.op0 = sch->nops; g.nloads = 0; g.nmma = 0;
         int loaded_b[TC_MAXS]; bool first[4] = {true, true, true, true};
         for (int q = 0; q < TC_MAXS; ++q) loaded_b[q] = -1;
         const int pmax = d1;                                   // d1 <= s - 1
@@ -55,9 +55,53 @@ void tc_build_schedule(int s, int nl, TcSchedule* sch) {
                 if (p == last_p_of_q) op |= 1u << 16;          // last use of B_q
                 first[l] = false;
                 sch->ops[sch->nops++] = op;
+                ++g.nmma;
             }
         }
         g.nops = sch->nops - g.op0;
+    }
+}
+
+void tc_compact_schedule(const TcSchedule* sch, TcTables* tab) {
+    tab->s = sch->s; tab->ngroups = sch->ngroups;
+    for (int gi = 0; gi < sch->ngroups; ++gi) {
+        const TcGroup& g = sch->g[gi];
+        int nl = 0, nm = 0, seen = 0, acquired = 0;
+        for (int o = g.op0; o < g.op0 + g.nops; ++o) {
+            const unsigned op = sch->ops[o], type = op & 3u;
+            if (type != TC_OP_MMA) {
+                tab->loads[gi * TC_MAXLOADS + nl++] = (type == TC_OP_LOAD_B ? 1u : 0u) | (((op >> 2) & 15u) << 1);
+                ++seen;
+            } else {
+                const unsigned ia = (op >> 2) & 31u, ib = (op >> 7) & 31u;
+                const int need = (int)(ia > ib ? ia : ib) + 1;
+                const int nacq = need > acquired ? need - acquired : 0;
+                acquired += nacq;
+                tab->mmas[gi * TC_MAXMMAS + nm++] = ia | (ib << 5) | (((op >> 12) & 3u) << 10) | (((op >> 14) & 1u) << 12) |
+                                                    (((op >> 15) & 1u) << 13) | (((op >> 16) & 1u) << 14) | ((unsigned)nacq << 15);
+            }
+        }
+        (void)seen;
+        tab->d0[gi] = g.d0; tab->nl[gi] = g.nl; tab->nloads[gi] = nl; tab->nmma[gi] = nm;
+        // steps: consecutive MMA ops that share their A load
+        int ns = 0;
+        for (int i = 0; i < nm;) {
+            const unsigned w = tab->mmas[gi * TC_MAXMMAS + i], ia = w & 31u;
+            unsigned w0 = ia, w1 = 0, nacq = 0, relb = 0;
+            int np = 0;
+            while (i < nm && (tab->mmas[gi * TC_MAXMMAS + i] & 31u) == ia && np < 4) {
+                const unsigned m = tab->mmas[gi * TC_MAXMMAS + i];
+                w1 |= ((((m >> 5) & 31u)) | (((m >> 10) & 3u) << 5) | (((m >> 12) & 1u) << 7)) << (8 * np);
+                nacq += (m >> 15) & 15u;
+                if ((m >> 14) & 1u) relb = 1u + ((m >> 5) & 31u);     // at most one B plane has its last use in a step
+                ++np; ++i;
+            }
+            w0 |= (unsigned)np << 5 | nacq << 8 | relb << 12;
+            tab->steps[(gi * TC_MAXS + ns) * 2] = w0;
+            tab->steps[(gi * TC_MAXS + ns) * 2 + 1] = w1;
+            ++ns;
+        }
+        tab->nsteps[gi] = ns;
     }
 }
 
@@ -71,7 +115,9 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 128;          // tile rows / col
 constexpr int TC_SLOT = TC_BM * TC_BK;                          // 16 KB
 constexpr int TC_RING = 12;
 constexpr int TC_THREADS = 384;                                  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
-constexpr int TC_SMEM = TC_RING * TC_SLOT + 1024 /*alignment slack*/ + 512 /*barriers*/;
+constexpr int TC_TAB_GROUPS = 2;                                 // level groups the kernel supports (s <= 8 at 4 levels per group)
+constexpr int TC_TAB_BYTES = TC_TAB_GROUPS * TC_RING * TC_MAXS * 64;
+constexpr int TC_SMEM = TC_RING * TC_SLOT + 1024 /*alignment slack*/ + 512 /*barriers*/ + TC_TAB_BYTES;
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,6 +143,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// one lane of a converged warp (the predicate ptxas understands as "single thread": no ELECT loops around uniform-datapath ops)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n .reg .b32 rx;\n .reg .pred px;\n elect.sync rx|px, 0xFFFFFFFF;\n @px mov.s32 %0, 1;\n}" : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -115,6 +167,13 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
 // instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 __device__ __forceinline__ uint32_t tc_idesc(int n) { return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24); }
 
+// the MMAs of one (A plane, B plane) pair over one K chunk (nk x 32 bytes)
+__device__ __forceinline__ void tc_issue_pair(uint32_t dcol, uint64_t da, uint64_t db, uint32_t idesc, uint32_t keep, int nk) {
+    tc_mma_i8(dcol, da, db, idesc, keep);
+    if (nk > 1) tc_mma_i8(dcol, da + 2, db + 2, idesc, 1u);
+    if (nk > 2) tc_mma_i8(dcol, da + 4, db + 4, idesc, 1u);
+    if (nk > 3) tc_mma_i8(dcol, da + 6, db + 6, idesc, 1u);
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
@@ -136,7 +195,7 @@ struct TcParams {
 // ------------------------------------------------------------------------------------------------ the GEMM kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const __grid_constant__ TcSchedule sch, const __grid_constant__ TcParams prm) {
+               const __grid_constant__ TcTables sch, const __grid_constant__ TcParams prm) {
     extern __shared__ char smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;           // 1024-byte aligned ring (swizzle atom)
     const uint32_t bars = sbase + TC_RING * TC_SLOT;                          // full[RING], empty[RING], tfull, tempty (8 B each), tmem ptr
@@ -144,7 +203,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t tmem_slot = bar_tempty + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = sch.s;
-
+    // Issue table: for every (level group, ring position of the iteration's first load, step) the ready-made operands of
+    // the issue, 64 bytes: [0] A descriptor low word, [1] pairs | loads to acquire << 4 | empty-barrier offset of A << 8 |
+    // (B released ? 1 : 0) << 16 | its barrier offset << 17, then per pair j: [2+2j] B descriptor low word,
+    // [3+2j] accumulator column | first << 9 -- the issuer's per-step work is three 16-byte shared loads, the waits and
+    // the tcgen05 instructions themselves.
+    const uint32_t tab = bars + 512;
+    {
+        const uint32_t lo0 = (sbase & 0x3FFFFu) >> 4;
+        uint32_t* T = reinterpret_cast<uint32_t*>(smem_raw + (tab - smem_u32(smem_raw)));
+        for (int idx = threadIdx.x; idx < sch.ngroups * TC_RING * TC_MAXS; idx += blockDim.x) {
+            const int g = idx / (TC_RING * TC_MAXS), bs = (idx / TC_MAXS) % TC_RING, st = idx % TC_MAXS;
+            const uint32_t w0 = sch.steps[(g * TC_MAXS + st) * 2], w1 = sch.steps[(g * TC_MAXS + st) * 2 + 1];
+            const uint32_t sa = (bs + (w0 & 31u)) % TC_RING, np = (w0 >> 5) & 7u, relb = (w0 >> 12) & 31u;
+            uint32_t* e = T + (size_t)idx * 16;
+            e[0] = lo0 + sa * (TC_SLOT >> 4);
+            e[1] = np | (((w0 >> 8) & 15u) << 4) | ((8u * sa) << 8) | (relb ? (1u << 16) | ((8u * ((bs + relb - 1u) % TC_RING)) << 17) : 0u);
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t pj = (w1 >> (8 * j)) & 255u;
+                e[2 + 2 * j] = lo0 + ((bs + (pj & 31u)) % TC_RING) * (TC_SLOT >> 4);
+                e[3 + 2 * j] = (((pj >> 5) & 3u) * TC_BN) | (((pj >> 7) & 1u) << 9);
+            }
+        }
+    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_RING; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
         mbar_init(bar_tfull, 1);
@@ -163,75 +244,86 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     const int items = prm.nmat * prm.mt * prm.nt;
 
-    // register budget: 168 per thread at launch (64 K / 384); the data-movement warpgroup hands its surplus to the epilogue
+    // Both data-movement roles run as WARP-UNIFORM loops (all 32 lanes walk the table; the asynchronous instruction itself
+    // is issued by one elected lane): the compiler keeps the bookkeeping in uniform registers, and the per-op work is a
+    // few dozen instructions.  (A loop inside `if (lane == 0)` made ptxas wrap every UTCIMMA in an ELECT loop -- 130
+    // instructions per four MMAs, measured 880 cycles per op against 256 cycles of tensor work.)
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;" ::: "memory");
     if (warp == 0) {
-        // ===================================================== TMA producer (one thread)
-        if (lane == 0) {
-            unsigned cnt = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int b = item / (prm.mt * prm.nt), rem = item % (prm.mt * prm.nt);
-                const int m0 = (rem / prm.nt) * TC_BM, n0 = (rem % prm.nt) * TC_BN;
-                for (int t = 0; t < 3; ++t) {
-                    const int plane0 = (b * 3 + t) * s;
-                    for (int g = 0; g < sch.ngroups; ++g) {
-                        const int op0 = sch.g[g].op0, op1 = op0 + sch.g[g].nops;
-                        for (int kc = 0; kc < prm.nkc; ++kc) {
-                            for (int o = op0; o < op1; ++o) {
-                                const unsigned op = sch.ops[o];
-                                const unsigned type = op & 3u;
-                                if (type == TC_OP_MMA) continue;
-                                const unsigned slot = cnt % TC_RING, par = (cnt / TC_RING) & 1u;
-                                mbar_wait(bar_empty + 8 * slot, par ^ 1u);
+        // ===================================================== TMA producer
+        unsigned slot = 0, par = 1;                      // parity to wait for on empty[slot]: starts at 1 (fresh barrier passes)
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int b = item / (prm.mt * prm.nt), rem = item % (prm.mt * prm.nt);
+            const int m0 = (rem / prm.nt) * TC_BM, n0 = (rem % prm.nt) * TC_BN;
+            for (int t = 0; t < 3; ++t) {
+                const int plane0 = (b * 3 + t) * s;
+                for (int g = 0; g < sch.ngroups; ++g) {
+                    const int l0 = g * TC_MAXLOADS, nloads = sch.nloads[g];
+                    for (int kc = 0; kc < prm.nkc; ++kc) {
+                        for (int i = 0; i < nloads; ++i) {
+                            const uint32_t w = sch.loads[l0 + i];                 // bit 0: B operand, bits 1-4: digit
+                            mbar_wait(bar_empty + 8 * slot, par);
+                            if (elect_one()) {
                                 mbar_expect_tx(bar_full + 8 * slot, TC_SLOT);
-                                const int slice = (op >> 2) & 15;
-                                if (type == TC_OP_LOAD_A) tma_load_3d(sbase + slot * TC_SLOT, &mapA, bar_full + 8 * slot, kc * TC_BK, m0, plane0 + slice);
-                                else tma_load_3d(sbase + slot * TC_SLOT, &mapB, bar_full + 8 * slot, kc * TC_BK, n0, plane0 + slice);
-                                ++cnt;
+                                tma_load_3d(sbase + slot * TC_SLOT, (w & 1u) ? &mapB : &mapA, bar_full + 8 * slot, kc * TC_BK,
+                                            (w & 1u) ? n0 : m0, plane0 + (int)(w >> 1));
                             }
+                            __syncwarp();
+                            if (++slot == TC_RING) { slot = 0; par ^= 1u; }
                         }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer (one thread)
-        if (lane == 0) {
-            unsigned base = 0, acq = 0, grp = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int rem = item % (prm.mt * prm.nt);
-                const int n0 = (rem % prm.nt) * TC_BN;
-                int ncols = prm.N - n0; if (ncols > TC_BN) ncols = TC_BN;
-                const uint32_t idesc = tc_idesc((ncols + 15) & ~15);
-                for (int t = 0; t < 3; ++t) {
-                    for (int g = 0; g < sch.ngroups; ++g, ++grp) {
-                        // the epilogue must have drained the accumulators of the previous group
-                        mbar_wait(bar_tempty, (grp & 1u) ^ 1u);
-                        tc_fence_after();
-                        const int op0 = sch.g[g].op0, op1 = op0 + sch.g[g].nops, nloads = sch.g[g].nloads;
-                        for (int kc = 0; kc < prm.nkc; ++kc) {
-                            const int nk = (kc == prm.nkc - 1) ? prm.nk_last : TC_BK / 32;
-                            for (int o = op0; o < op1; ++o) {
-                                const unsigned op = sch.ops[o];
-                                if ((op & 3u) != TC_OP_MMA) continue;
-                                const unsigned ia = base + ((op >> 2) & 31u), ib = base + ((op >> 7) & 31u);
-                                const unsigned need = (ia > ib ? ia : ib);
-                                while (acq <= need) { mbar_wait(bar_full + 8 * (acq % TC_RING), (acq / TC_RING) & 1u); ++acq; }
-                                tc_fence_after();
-                                const uint32_t sa = ia % TC_RING, sb = ib % TC_RING;
-                                const uint64_t da = tc_smem_desc(sbase + sa * TC_SLOT), db = tc_smem_desc(sbase + sb * TC_SLOT);
-                                const uint32_t dcol = tmem_base + ((op >> 12) & 3u) * TC_BN;
-                                const bool fresh = (kc == 0) && ((op >> 14) & 1u);
-                                for (int k = 0; k < nk; ++k)
-                                    tc_mma_i8(dcol, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (fresh && k == 0) ? 0u : 1u);
-                                if ((op >> 15) & 1u) tc_commit(bar_empty + 8 * sa);
-                                if ((op >> 16) & 1u) tc_commit(bar_empty + 8 * sb);
+        // ===================================================== MMA issuer
+        const uint32_t desc_hi = (uint32_t)(tc_smem_desc(0) >> 32);
+        unsigned aslot = 0, apar = 0;                    // acquire cursor: next load to wait for on full[aslot]
+        unsigned bslot = 0;                              // ring slot of load 0 of the current (group, K chunk) iteration
+        unsigned grp = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int rem = item % (prm.mt * prm.nt);
+            const int n0 = (rem % prm.nt) * TC_BN;
+            int ncols = prm.N - n0; if (ncols > TC_BN) ncols = TC_BN;
+            const uint32_t idesc = tc_idesc((ncols + 15) & ~15);
+            for (int t = 0; t < 3; ++t) {
+                for (int g = 0; g < sch.ngroups; ++g, ++grp) {
+                    mbar_wait(bar_tempty, (grp & 1u) ^ 1u);          // the epilogue has drained the previous group's accumulators
+                    tc_fence_after();
+                    const int ns = sch.nsteps[g], nloads = sch.nloads[g];
+                    for (int kc = 0; kc < prm.nkc; ++kc) {
+                        const int nk = (kc == prm.nkc - 1) ? prm.nk_last : TC_BK / 32;
+                        const uint32_t tp = tab + (uint32_t)((g * TC_RING + bslot) * TC_MAXS) * 64u;
+                        const uint32_t fresh_mask = (kc == 0) ? (1u << 9) : 0u;
+                        for (int i = 0; i < ns; ++i) {
+                            uint4 e0, e1, e2;
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e0.x), "=r"(e0.y), "=r"(e0.z), "=r"(e0.w) : "r"(tp + 64u * i));
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e1.x), "=r"(e1.y), "=r"(e1.z), "=r"(e1.w) : "r"(tp + 64u * i + 16u));
+                            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e2.x), "=r"(e2.y), "=r"(e2.z), "=r"(e2.w) : "r"(tp + 64u * i + 32u));
+                            for (unsigned n = (e0.y >> 4) & 15u; n > 0; --n) {
+                                mbar_wait(bar_full + 8 * aslot, apar);
+                                if (++aslot == TC_RING) { aslot = 0; apar ^= 1u; }
                             }
-                            base += nloads;
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint32_t np = e0.y & 15u;
+                                const uint64_t da = ((uint64_t)desc_hi << 32) | e0.x;
+                                tc_issue_pair(tmem_base + (e0.w & 511u), da, ((uint64_t)desc_hi << 32) | e0.z, idesc, (e0.w & fresh_mask) ? 0u : 1u, nk);
+                                if (np > 1) tc_issue_pair(tmem_base + (e1.y & 511u), da, ((uint64_t)desc_hi << 32) | e1.x, idesc, (e1.y & fresh_mask) ? 0u : 1u, nk);
+                                if (np > 2) tc_issue_pair(tmem_base + (e1.w & 511u), da, ((uint64_t)desc_hi << 32) | e1.z, idesc, (e1.w & fresh_mask) ? 0u : 1u, nk);
+                                if (np > 3) tc_issue_pair(tmem_base + (e2.y & 511u), da, ((uint64_t)desc_hi << 32) | e2.x, idesc, (e2.y & fresh_mask) ? 0u : 1u, nk);
+                                tc_commit(bar_empty + ((e0.y >> 8) & 255u));                           // A plane: its last use is this step
+                                if (e0.y & (1u << 16)) tc_commit(bar_empty + ((e0.y >> 17) & 255u));    // the B plane that is done
+                            }
+                            __syncwarp();
                         }
-                        tc_commit(bar_tfull);
+                        bslot += nloads;
+                        if (bslot >= TC_RING) bslot -= TC_RING;
+                        if (bslot >= TC_RING) bslot -= TC_RING;
                     }
+                    if (elect_one()) tc_commit(bar_tfull);
+                    __syncwarp();
                 }
             }
         }
@@ -257,8 +349,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < 64; ++c) acc[c] = 0.0;
                 for (int g = 0; g < sch.ngroups; ++g, ++grp) {
-                    const int nl = sch.g[g].nl;
-                    const double w = pow2d(-8 * (sch.g[g].d0 + nl - 1));
+                    const int nl = sch.nl[g];
+                    const double w = pow2d(-8 * (sch.d0[g] + nl - 1));
                     mbar_wait(bar_tfull, grp & 1u);
                     tc_fence_after();
 #pragma unroll
@@ -387,17 +479,24 @@ tc_split_rows_kernel(const cplx* __restrict__ src, int ld, long long stride, int
     }
 }
 
-// column maxima of src [Kc rows][R cols]: thread per column (coalesced across the warp)
+// column maxima of src [Kc rows][R cols]: thread per column (coalesced across the warp), the K range split over
+// blockIdx.y; the per-range exponents meet in an atomicMax on ex (pre-filled with TC_E_ZERO)
+constexpr int TCM_K = 64;
+__global__ void tc_fill_int_kernel(int* p, size_t n, int v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
 __global__ void __launch_bounds__(128)
 tc_colmax_kernel(const cplx* __restrict__ src, int ld, long long stride, int R, int Kc, int* __restrict__ ex) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.z;
     if (j >= R) return;
+    const int k0 = blockIdx.y * TCM_K, k1 = (k0 + TCM_K < Kc) ? k0 + TCM_K : Kc;
     const cplx* p = src + (size_t)b * stride + j;
     double mx = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < Kc; ++k) { const cplx v = p[(size_t)k * ld]; mx = fmax(mx, fabs(v.x) + fabs(v.y)); }
+#pragma unroll 8
+    for (int k = k0; k < k1; ++k) { const cplx v = p[(size_t)k * ld]; mx = fmax(mx, fabs(v.x) + fabs(v.y)); }
     const int e = tc_exponent(mx);
-    ex[(size_t)b * R + j] = e;          // TC_E_ZERO marks an all-zero column until the split kernel has consumed it
+    if (e != TC_E_ZERO) atomicMax(&ex[(size_t)b * R + j], e);      // TC_E_ZERO marks an all-zero column until the split kernel has consumed it
 }
 
 // operand whose "rows" are the COLUMNS of src [Kc rows][R cols] (ld): tile of 32 columns x 64 k, transposed through
@@ -485,7 +584,9 @@ cudaError_t tc_split(const cplx* X, int ld, long long stride, bool rows_contiguo
     if (rows_contiguous) {
         tc_split_rows_kernel<<<dim3(R, nmat), 256, 0, st>>>(X, ld, stride, R, Kc, Kp, s, conj, out, ex);
     } else {
-        tc_colmax_kernel<<<dim3((R + 127) / 128, nmat), 128, 0, st>>>(X, ld, stride, R, Kc, ex);
+        const size_t nex = (size_t)R * nmat;
+        tc_fill_int_kernel<<<(unsigned)((nex + 255) / 256), 256, 0, st>>>(ex, nex, TC_E_ZERO);
+        tc_colmax_kernel<<<dim3((R + 127) / 128, (Kc + TCM_K - 1) / TCM_K, nmat), 128, 0, st>>>(X, ld, stride, R, Kc, ex);
         const size_t smem = (size_t)3 * s * TCS_J * TCS_LDW * 4;
         if (smem > 48 * 1024) cudaFuncSetAttribute(tc_split_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         tc_split_cols_kernel<<<dim3((R + TCS_J - 1) / TCS_J, Kp / TCS_K, nmat), 256, smem, st>>>(X, ld, stride, R, Kc, Kp, s, conj, out, ex);
@@ -505,7 +606,7 @@ size_t tc_workspace_bytes(int M, int N, int K, int nb, int s) {
 }
 size_t tc_workspace_min_bytes(int M, int N, int K, int s) { return tc_bytes_per_matrix(M, N, K, s); }
 
-bool tc_supported(int s, int M, int N, int K) { return s >= 2 && s <= TC_MAXS && M > 0 && N > 0 && K > 0 && tc_encoder() != nullptr; }
+bool tc_supported(int s, int M, int N, int K) { return s >= 2 && s <= TC_MAXS && (s + 3) / 4 <= TC_TAB_GROUPS && M > 0 && N > 0 && K > 0 && tc_encoder() != nullptr; }
 
 cudaError_t tc_zgemm_strided(int s, int opa, int opb, int M, int N, int K, double alpha, const cplx* A, int lda, long long sa,
                              const cplx* B, int ldb, long long sb, cplx beta, cplx* Cm, int ldc, long long sc, int batch,
@@ -520,8 +621,10 @@ cudaError_t tc_zgemm_strided(int s, int opa, int opb, int M, int N, int K, doubl
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);   // per device; cheap, so unconditional
-    TcSchedule sch;
-    tc_build_schedule(s, 4, &sch);
+    TcSchedule full;
+    tc_build_schedule(s, 4, &full);
+    TcTables sch;
+    tc_compact_schedule(&full, &sch);
     char* p = ws;
     signed char* Asl = (signed char*)p; p += al256((size_t)3 * s * M * Kp) * chunk;
     signed char* Bsl = (signed char*)p; p += al256((size_t)3 * s * N * Kp) * chunk;
@@ -555,6 +658,22 @@ cudaError_t tc_zgemm_strided(int s, int opa, int opb, int M, int N, int K, doubl
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+size_t tc_ctx_bytes(int n, int nb, int slices) {
+    if (slices < 2) return 0;
+    const int chunk = nb < 16 ? (nb > 0 ? nb : 1) : 16;          // digits of 16 matrices at a time keep the kernel's grid full
+    return tc_bytes_per_matrix(n, n, n, slices) * (size_t)chunk;
+}
+
+cudaError_t gemm_auto(const TcCtx* tc, int opa, int opb, int M, int N, int K, double alpha, const cplx* A, int lda, long long sa,
+                      const cplx* B, int ldb, long long sb, cplx beta, cplx* Cm, int ldc, long long sc, int batch,
+                      ZGemmProblem* gscratch, cudaStream_t st) {
+    // the digit path pays a split of both operands (~O(MK + KN) bytes each way): only for products with enough work per element
+    const bool big = M >= 256 && N >= 128 && K >= 256;
+    if (tc && tc->slices >= 2 && big && tc_supported(tc->slices, M, N, K) && tc->ws_bytes >= tc_workspace_min_bytes(M, N, K, tc->slices))
+        return tc_zgemm_strided(tc->slices, opa, opb, M, N, K, alpha, A, lda, sa, B, ldb, sb, beta, Cm, ldc, sc, batch, tc->ws, tc->ws_bytes, st);
+    return zgemm_strided(opa, opb, M, N, K, C(alpha, 0.0), A, lda, sa, B, ldb, sb, beta, Cm, ldc, sc, batch, gscratch, st);
 }
 
 // debugging / tests: the split on its own

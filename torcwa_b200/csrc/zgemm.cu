@@ -253,11 +253,14 @@ template <int BM, int BN, int WM, int WN, int OPA, int OPB, bool M3, int MINB, i
 cudaError_t launch_cfg(const ZGemmProblem* probs, int nprob, int max_tiles, cplx alpha, cplx beta, cudaStream_t st) {
     constexpr size_t smem = (size_t)STAGES * BK * ((BM + 2) + (BN + 2)) * sizeof(cplx);
     constexpr int nthr = (BM / WM) * (BN / WN) * 32;
-    static bool attr_set = false;   // idempotent attribute; benign if raced
-    if (!attr_set) {
+    // the attribute is per DEVICE: remember it per device (idempotent; benign if raced between host threads)
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(zgemm_grouped_kernel<BM, BN, WM, WN, OPA, OPB, M3, MINB, BAND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     dim3 grid(max_tiles, nprob);
     zgemm_grouped_kernel<BM, BN, WM, WN, OPA, OPB, M3, MINB, BAND><<<grid, nthr, smem, st>>>(probs, alpha, beta);

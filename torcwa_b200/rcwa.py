@@ -16,6 +16,7 @@ Arithmetic: all device work is complex128 ("fp64 internals behind the c64 API", 
 torch is used for device memory, streams and O(N) per-order bookkeeping only; there is no torch
 fallback for the dense stages -- if the CUDA library is missing the constructor raises.
 """
+import os
 import warnings
 import weakref
 
@@ -49,10 +50,17 @@ class rcwa:
                  stable_eig_grad=True,
                  avoid_Pinv_instability=False,
                  max_Pinv_instability=0.005,
-                 store_intermediates=None):
+                 store_intermediates=None,
+                 gemm_digits=None):
         """Same parameters as the reference (torcwa/rcwa.py:9-35).  ``store_intermediates``
         (new): keep per-layer P, Q, eigenvectors, convolution matrices as attributes
-        (default: only for unbatched sims, where the reference keeps them)."""
+        (default: only for unbatched sims, where the reference keeps them).
+        ``gemm_digits`` (new): engine of the dense products of the S-matrix stage (layer S-matrix, star
+        products, their triangular solves): 0 = fp64 tensor pipe (DMMA), 2..8 = tcgen05 int8-digit GEMM with
+        that many 8-bit digits per number (include/rcwa_b200.h: rcwa_zgemm_tc_batched).  Default: 5 for
+        complex64 simulations (2e-10-grade products, far inside the API's single precision), 0 for complex128;
+        the environment variable RCWA_B200_GEMM_DIGITS overrides the complex64 default.  The eigensolver always
+        runs in fp64 (SURVEY.md finding 5)."""
         if dtype != torch.complex64 and dtype != torch.complex128:
             warnings.warn('Invalid simulation data type. Set as torch.complex64.', UserWarning)
             dtype = torch.complex64
@@ -61,6 +69,9 @@ class rcwa:
         if device is None:
             device = torch.device('cuda')
         self._device = torch.device(device)
+        if gemm_digits is None:
+            gemm_digits = int(os.environ.get('RCWA_B200_GEMM_DIGITS', '5')) if dtype == torch.complex64 else 0
+        self._digits = int(gemm_digits) if 2 <= int(gemm_digits) <= 8 else 0
         if self._device.type != 'cuda' and not _TEST_ALLOW_NON_CUDA:
             raise RuntimeError('torcwa_b200 runs on CUDA devices only (no CPU path); got device=%s' % device)
         _lib.load()   # fail loudly, now, if the CUDA library is missing
@@ -298,7 +309,7 @@ class rcwa:
             self.eig_info.append(info)
             self._status.append(('eigendecomposition (layer %d): QR iteration did not converge' % self.layer_N, info))
             kz = _lib.kz_branch(lam)
-            S11, S21, info_s = _lib.layer_smatrix(W, kz, Q, self._Vf_inv, omega, thick)
+            S11, S21, info_s = _lib.layer_smatrix(W, kz, Q, self._Vf_inv, omega, thick, slices=self._digits)
             self._status.append(('layer S-matrix (layer %d): singular coupling matrix' % self.layer_N, info_s))
             if self._store:
                 self.E_eigvec.append(self._pub(W))
@@ -357,17 +368,17 @@ class rcwa:
             S = [s11, s21, s21, s11]
             for i in range(1, self.layer_N):
                 n11, n21 = self._layers[i]
-                S, info_r = _lib.redheffer(S, [n11, n21, n21, n11])
+                S, info_r = _lib.redheffer(S, [n11, n21, n21, n11], slices=self._digits)
                 self._status.append(('star product with layer %d' % i, info_r))
         else:
             eye = torch.eye(n, dtype=_C, device=self._device).expand(B, -1, -1).contiguous()
             zero = torch.zeros((B, n, n), dtype=_C, device=self._device)
             S = [eye, zero, zero.clone(), eye.clone()]
         if hasattr(self, 'Sin'):
-            S, info_r = _lib.redheffer_bdleft(self._Sin, S)     # Sin is four-diagonal: O(n^2) instead of 6 GEMMs
+            S, info_r = _lib.redheffer_bdleft(self._Sin, S, slices=self._digits)     # Sin is four-diagonal: O(n^2) instead of 6 GEMMs
             self._status.append(('star product with the input half space', info_r))
         if hasattr(self, 'Sout'):
-            S, info_r = _lib.redheffer(S, [_lib.blockdiag_dense(s.contiguous()) for s in self._Sout])
+            S, info_r = _lib.redheffer(S, [_lib.blockdiag_dense(s.contiguous()) for s in self._Sout], slices=self._digits)
             self._status.append(('star product with the output half space', info_r))
         self._check_status()
         self._S = S
@@ -406,9 +417,11 @@ class rcwa:
             S = autodiff.redheffer([autodiff.blockdiag_dense(s) for s in self._Sin], S)
         if hasattr(self, 'Sout'):
             S = autodiff.redheffer(S, [autodiff.blockdiag_dense(s) for s in self._Sout])
+        self._check_status()         # info words of the fused (non-differentiable) layers of a mixed stack
         self._S = S
         self.S = [self._pub(s) for s in S]
         self.C = [[], []]
+        self._modes_ready = False
 
     # ------------------------------------------------------------------ small utilities (rcwa.py:214-298)
     def diffraction_angle(self, orders, *, layer='output', unit='radian'):
