@@ -4,7 +4,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--points P] [--order O]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...      # the reference's own CPU path (oracle port), host cores
+    python bench.py --impl reference ...      # the UNMODIFIED reference (baseline/_ref) on the host cores
+    python bench.py --config 3|5 ...          # BASELINE configs[2] (order 21, 8 layers, complex128) / configs[4] (forward + backward)
 
 One "step" = one chunk of P wavelengths of the 512-point sweep (Example1 cell, a-Si:H pillar with a
 synthetic linear dispersion, SiO2 half space) through
@@ -62,6 +63,70 @@ def make_grids(mask, lams):
     return mask[None] * e[:, None, None] + (1.0 - mask)[None]
 
 
+# ------------------------------------------------------------------------------------------- the unmodified reference
+def reference_module():
+    """kch3782/torcwa as installed (unmodified) into baseline/_ref by `pip install --no-deps --target baseline/_ref
+    /root/reference`; None if it is not there."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "torcwa")):
+        return None
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        import torcwa
+        return torcwa
+    except Exception:
+        return None
+
+
+def reference_point(torcwa, order, cdtype, lam, device, mask=None):
+    """One design point of the workload's unit (Example1 cell, one patterned layer + SiO2 half space) through the
+    reference's own public API and stock code path; returns (seconds, t_xx)."""
+    rd = torch.float32 if cdtype == torch.complex64 else torch.float64
+    if mask is None:
+        import torcwa_b200
+        geo = torcwa_b200.geometry(Lx=300.0, Ly=300.0, nx=300, ny=300, edge_sharpness=1000.0, dtype=rd, device=torch.device("cpu"))
+        mask = geo.rectangle(Wx=180.0, Wy=100.0, Cx=150.0, Cy=150.0).to(device)
+    e = eps_si(float(lam))
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sim = torcwa.rcwa(freq=1 / torch.tensor(float(lam), dtype=rd, device=device), order=[order, order], L=[300.0, 300.0], dtype=cdtype, device=device)
+    sim.add_input_layer(eps=1.46 ** 2)
+    sim.set_incident_angle(inc_ang=0.0, azi_ang=0.0)
+    sim.add_layer(thickness=300.0, eps=mask * e + (1.0 - mask))
+    sim.solve_global_smatrix()
+    t = sim.S_parameters(orders=[0, 0], direction="forward", port="transmission", polarization="xx", ref_order=[0, 0])
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    return time.perf_counter() - t0, complex(t.reshape(-1)[0]), mask
+
+
+def cuda_baseline(order, points=8, warm=2):
+    """The reference's PyTorch-CUDA path (unmodified baseline/_ref, device='cuda', allow_tf32=False as its README asks,
+    sequential loop over wavelengths as its examples do) on the same GPU, in the same run: the denominator of the
+    north star's '>= 10x the reference PyTorch-CUDA path' (BASELINE.md 3.2)."""
+    torcwa = reference_module()
+    if torcwa is None:
+        return {"unavailable": "baseline/_ref is missing"}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = {"impl": "unmodified reference (baseline/_ref), device='cuda', allow_tf32=False", "warmups": warm, "points": points}
+    lams = np.linspace(LAM0, LAM1, points + warm)
+    for name, cd in (("c64", torch.complex64), ("c128", torch.complex128)):
+        ts, mask = [], None
+        try:
+            for i, lam in enumerate(lams):
+                dt, _, mask = reference_point(torcwa, order, cd, lam, dev, mask)
+                if i >= warm:
+                    ts.append(dt)
+            out[name] = {"layers_per_s": len(ts) / sum(ts), "s_per_layer": sum(ts) / len(ts)}
+        except Exception as ex:            # report, do not hide
+            out[name] = {"error": str(ex)[:200]}
+        torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     def __init__(self, index):
@@ -109,7 +174,7 @@ def count_my_launches(fn):
     mine = ("zgemm_grouped", "fill_strided", "dft_rows", "dft_cols", "toeplitz", "pq_assemble", "kz_branch", "layer_form", "layer_finish",
             "blockdiag_dense", "identity_kernel", "axpby", "lu_panel", "lu_perm", "lu_colswap", "tri_inv", "gather_cols", "eig_backward", "conj_transpose", "hess_step",
             "hess_fused", "hess_advance", "hb_col", "hb_matvec", "hb_zero", "bd_left_mul", "bd_right_mul", "bd_add", "qr_pass", "qr_init", "qr_count", "qr_finish", "qr_stats", "diag_extract", "tnorm", "trevc_block",
-            "colnorm", "colscale")
+            "colnorm", "colscale", "tc_gemm_kernel", "tc_split_rows", "tc_split_cols", "tc_colmax", "tc_fill_int", "tc_fix_exponent")
     try:
         from torch.profiler import profile, ProfilerActivity
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -216,7 +281,7 @@ def bench_b200(args):
         sim_stage, A_eig = stage_times(case, grids_res[sl0][:Ps].contiguous(), freq_res[sl0][:Ps].contiguous(), device)
         torch.cuda.empty_cache()
         mv = matvec_roofline(A_eig)
-        tz = tensor_roofline(A_eig)
+        tz = tensor_roofline(A_eig, digits=int(os.environ.get('RCWA_B200_GEMM_DIGITS', '5')))
         del A_eig
         torch.cuda.empty_cache()
         b_eig = 16.0 * (n ** 3 / 3.0 + 2.0 * n * n)                      # SURVEY.md 8d, s = 16 (fp64 internals)
@@ -238,20 +303,25 @@ def bench_b200(args):
         except Exception:
             pass
         cupti_mv = per_kernel.get("hb_matvec")
-        roof = {"bound": "hbm", "kernel": "hb_matvec_kernel: streaming mat-vec y = A[k0+1:n, j+1:n] u_j of the blocked Hessenberg phase of rcwa_eig "
-                                          "(one launch per column; launches of %d sampled columns timed ALONE with CUDA events on the launching stream, batch %d)"
-                                          % (mv["launches"], Ps),
-                "achieved": mv["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": mv["gbs"] / hbm_peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_launch": mv["bytes_per_launch"], "us_per_launch": mv["us_per_launch"],
-                "in_step_cupti": None if not cupti_mv else {
-                    "launches": cupti_mv[0], "us_per_launch": cupti_mv[1] / max(cupti_mv[0], 1),
-                    "achieved": P * (b_eig - 32.0 * n * n) / max(cupti_mv[1], 1e-9) / 1e3,
-                    "note": "all %d launches of one step (CUPTI durations): P * 16 n^3/3 bytes / total kernel time" % cupti_mv[0]},
+        # roofline of the eig stage = B_eig / t_eig over the WHOLE stage (Hessenberg + QR + eigenvectors);
+        # the phases that are not HBM-bound (QR: fp64 tensor pipe + serial chain) pull it far below the streaming kernel's own
+        # fraction, which is reported beside it.
+        roof = {"bound": "hbm", "kernel": "rcwa_eig (whole stage: blocked Hessenberg reduction + multishift QR/AED + eigenvectors), batch %d; "
+                                          "algorithmic bytes B_eig = 16 (n^3/3 + 2 n^2) per matrix (SURVEY.md 8d, s = 16: fp64 internals)" % Ps,
+                "achieved": achieved_eig, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_eig / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "ms_per_batch": sim_stage["eig_ms"],
                 "algorithmic_bytes_per_matrix": b_eig,
                 "hessenberg_phase_whole": {"achieved": achieved_h, "frac": achieved_h / hbm_peak, "ms_per_batch": t_h},
-                "eig_stage_whole": {"achieved": achieved_eig, "frac": achieved_eig / hbm_peak, "ms_per_batch": sim_stage["eig_ms"]}}
+                "streaming_kernel_alone": {
+                    "kernel": "hb_matvec_kernel: y = A[k0+1:n, j+1:n] u_j, one launch per column (%d sampled columns timed alone with CUDA events, batch %d)" % (mv["launches"], Ps),
+                    "achieved": mv["gbs"], "frac": mv["gbs"] / hbm_peak, "bytes_per_launch": mv["bytes_per_launch"], "us_per_launch": mv["us_per_launch"],
+                    "traffic_offline_ncu": traffic, "traffic_note": "dram bytes of ONE captured launch (profiles/roofline_traffic.json) scaled to this launch size; not measured in this run",
+                    "in_step_cupti": None if not cupti_mv else {
+                        "launches": cupti_mv[0], "us_per_launch": cupti_mv[1] / max(cupti_mv[0], 1),
+                        "achieved": P * (b_eig - 32.0 * n * n) / max(cupti_mv[1], 1e-9) / 1e3}}}
         cpu = cpu_baseline(args.order, args.ref_dtype) if (args.cpu_baseline and world == 1) else None     # N = 1 only
+        torch.cuda.empty_cache()
+        cuda_ref = cuda_baseline(args.order) if (args.cuda_baseline and world == 1) else None
         out = {
             "metric": "layers/sec (order %dx%d, c64)" % (args.order, args.order), "value": value, "unit": "layers/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak",
@@ -274,6 +344,11 @@ def bench_b200(args):
             "kernel_launches_and_avg_us": {k: [v[0], round(v[1] / max(v[0], 1), 1)] for k, v in
                                            sorted(per_kernel.items(), key=lambda kv: -kv[1][1])[:8]} if launches else None,
             "cpu_baseline": cpu,
+            "cuda_baseline": cuda_ref,
+            "vs_reference_cuda": None if not cuda_ref or "c64" not in cuda_ref or "layers_per_s" not in cuda_ref["c64"] else {
+                "value_over_c64": value / world / cuda_ref["c64"]["layers_per_s"],
+                "value_over_c128": None if "layers_per_s" not in cuda_ref.get("c128", {}) else value / world / cuda_ref["c128"]["layers_per_s"],
+                "note": "per-GPU throughput of this arm / the unmodified reference on the same GPU in the same run"},
         }
         print(json.dumps(out))
     if world > 1:
@@ -354,10 +429,13 @@ def matvec_roofline(A):
     return {"gbs": byts / (ms * 1e-3) / 1e9, "launches": len(cols), "bytes_per_launch": byts / len(cols), "us_per_launch": 1e3 * ms / len(cols)}
 
 
-def tensor_roofline(A):
-    """fp64 tensor pipe: one batched n x n x n complex product on our DMMA kernel and on cuBLAS (torch.matmul), CUDA events.
-    MEASURED_PEAKS.json has no fp64 figure; the denominator is the nominal dense fp64 tensor peak of B200 (40 TFLOP/s),
-    with cuBLAS zgemm measured beside it."""
+def tensor_roofline(A, digits=5):
+    """Tensor pipes, measured in this run with CUDA events on batched n x n x n complex products:
+      * fp64 (DMMA, mma.sync): our kernel, against the fp64 tensor peak MEASURED here as a sustained cuBLAS dgemm (8192^3,
+        back to back for ~1 s) -- MEASURED_PEAKS.json has no fp64 entry;
+      * tcgen05 (kind::i8, the engine of the complex64 API's S-matrix stage): the digit GEMM at `digits` and at 8 digits,
+        int8 ops actually issued / time, against 2 x the measured dense bf16 rate of MEASURED_PEAKS.json (kind::i8 runs at
+        twice the kind::f16 rate on sm_100a; there is no measured int8 entry)."""
     from torcwa_b200 import _lib
     nb = min(A.shape[0], 8)
     n = A.shape[1]
@@ -375,10 +453,35 @@ def tensor_roofline(A):
     ms = t(lambda: _lib.zgemm(X, Y, out=out))
     ms_c = t(lambda: torch.matmul(X, Y))
     fl = 8.0 * n ** 3 * nb
-    return {"bound": "tensor", "kernel": "zgemm_grouped_kernel<32,128,+3M> (batched %d x n^3 complex product, n=%d; fp64 DMMA mma.sync, tcgen05 has no f64 kind)" % (nb, n),
-            "achieved": fl / ms / 1e9, "peak": 40.0, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / 40.0,
-            "peak_source": "nominal B200 dense fp64 tensor (no fp64 entry in MEASURED_PEAKS.json)", "cublas_zgemm_same_shape": fl / ms_c / 1e9,
-            "note": "flops counted as 8 n^3 per complex product; the 3-multiplication kernel issues 6 n^3"}
+    # measured fp64 tensor peak: sustained cuBLAS dgemm
+    D1 = torch.randn(8192, 8192, dtype=torch.float64, device=A.device)
+    D2 = torch.randn(8192, 8192, dtype=torch.float64, device=A.device)
+    ms_d = t(lambda: torch.matmul(D1, D2), reps=20)
+    fp64_peak = 2.0 * 8192.0 ** 3 / ms_d / 1e9
+    del D1, D2
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16 = float(peaks.get("bf16_tflops", 1590.0))
+    res = {"bound": "tensor", "kernel": "zgemm_grouped_kernel<32,128,+3M> (batched %d x n^3 complex product, n=%d; fp64 DMMA mma.sync, tcgen05 has no f64 kind)" % (nb, n),
+           "achieved": fl / ms / 1e9, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / fp64_peak,
+           "peak_source": "measured in this run: sustained cuBLAS dgemm 8192^3 (20 back to back)", "cublas_zgemm_same_shape": fl / ms_c / 1e9,
+           "note": "flops counted as 8 n^3 per complex product; the 3-multiplication kernel issues 6 n^3"}
+    tc = {}
+    for dg in sorted({int(digits), 8} - {0}):
+        try:
+            ms_t = t(lambda: _lib.zgemm_tc(X, Y, slices=dg, out=out))
+            ops = 2.0 * 3 * (dg * (dg + 1) // 2) * n ** 3 * nb
+            tc["digits_%d" % dg] = {"ms": ms_t, "speedup_vs_dmma": ms / ms_t, "equivalent_fp64_tflops": fl / ms_t / 1e9,
+                                    "int8_tops_issued": ops / ms_t / 1e9, "frac_of_int8_peak": ops / ms_t / 1e9 / (2.0 * bf16)}
+        except Exception as ex:
+            tc["digits_%d" % dg] = {"error": str(ex)[:200]}
+    res["tcgen05"] = {"kernel": "tc_gemm_kernel (tcgen05.mma kind::i8, TMEM accumulators, TMA-staged digit planes) incl. the digit split of both operands",
+                      "int8_peak_tops": 2.0 * bf16, "int8_peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json" if peaks else "2 x fallback 1590",
+                      "tensor_pipe_active_pct_ncu": "see profiles/ (ncu sm__pipe_tensor_cycles_active of tc_gemm_kernel)", **tc}
+    return res
 
 
 # ------------------------------------------------------------------------------------------- CPU legs
@@ -408,48 +511,304 @@ def ref_threads():
     return min(os.cpu_count() or 1, 16)
 
 
+def cpu_point(order, cd, lam):
+    """One design point on the host: the unmodified reference (baseline/_ref) if present, else the oracle port."""
+    torcwa = reference_module()
+    if torcwa is not None:
+        dt, t, _ = reference_point(torcwa, order, cd, lam, torch.device("cpu"))
+        return dt, t, "reference"
+    dt, t = oracle_point(order, cd, lam)
+    return dt, t, "port"
+
+
 def cpu_baseline(order, ref_dtype="c128"):
     torch.set_num_threads(ref_threads())
     cd = torch.complex128 if ref_dtype == "c128" else torch.complex64
-    dt, _ = oracle_point(order, cd)
-    return {"value": 1.0 / dt, "unit": "layers/s", "cores": torch.get_num_threads(), "host_cores": os.cpu_count(), "kind": "port",
-            "sample": "1 design point (1 patterned layer, order %dx%d, %s) through oracle/rcwa_oracle.py (the reference's dense algebra on torch/MKL), "
+    dt, _, kind = cpu_point(order, cd, 532.0)
+    return {"value": 1.0 / dt, "unit": "layers/s", "cores": torch.get_num_threads(), "host_cores": os.cpu_count(), "kind": kind,
+            "sample": "1 design point (1 patterned layer, order %dx%d, %s) through %s, "
                       "%d threads (of %d; 128 threads measured 20x slower), %.1f s. %s"
-                      % (order, order, ref_dtype, torch.get_num_threads(), os.cpu_count(), dt, REF_DTYPE_NOTE if ref_dtype == "c128" else "")}
+                      % (order, order, ref_dtype, "the unmodified reference (baseline/_ref, device='cpu')" if kind == "reference" else "oracle/rcwa_oracle.py",
+                         torch.get_num_threads(), os.cpu_count(), dt, REF_DTYPE_NOTE if ref_dtype == "c128" else "")}
 
 
 def bench_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.config != 2:
+        return bench_reference_config(args)
     torch.set_num_threads(ref_threads())
-    K, W = args.steps, min(args.warmup, 1)
+    K, W = args.steps, args.warmup
     budget = args.ref_budget_s
     t_start = time.perf_counter()
     lams = np.linspace(LAM0, LAM1, N_SWEEP)
     cd = torch.complex128 if args.ref_dtype == "c128" else torch.complex64
-    for s in range(W):
-        oracle_point(args.order, cd, float(lams[s]))
+    kind, warm_done = "port", 0
+    for s in range(W):                     # warm-ups as requested, as long as the time budget allows two timed steps after them
+        dt, _, kind = cpu_point(args.order, cd, float(lams[s]))
+        warm_done += 1
+        if time.perf_counter() - t_start + 3 * dt > budget:
+            break
     done, total = 0, 0.0
     for s in range(K):
-        dt, _ = oracle_point(args.order, cd, float(lams[(W + s) % N_SWEEP]))
+        dt, _, kind = cpu_point(args.order, cd, float(lams[(W + s) % N_SWEEP]))
         total += dt
         done += 1
         if time.perf_counter() - t_start + dt > budget:
             break
     value = done / total
     n = 2 * (2 * args.order + 1) ** 2
+    impl = "the unmodified reference (baseline/_ref: torcwa.rcwa, device='cpu')" if kind == "reference" else "oracle/rcwa_oracle.py (port)"
     print(json.dumps({
         "impl": "reference", "metric": "layers/sec (order %dx%d, c64)" % (args.order, args.order), "value": value, "unit": "layers/s",
-        "n_gpus": args.gpus, "steps": done, "requested_steps": K, "warmup": W, "ms_per_step": 1e3 * total / done, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": done, "requested_steps": K, "warmup": warm_done, "requested_warmup": W, "ms_per_step": 1e3 * total / done, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.ref_dtype, "data": "synthetic (same cell and sweep as the B200 arm)",
         "note": REF_DTYPE_NOTE if args.ref_dtype == "c128" else "",
-        "config": {"workload": "BASELINE configs[1] unit: order %dx%d (n=%d), 1 patterned layer + SiO2 half space, one wavelength per step"
-                               % (args.order, args.order, n), "points_per_step": 1},
-        "cpu_baseline": {"value": value, "unit": "layers/s", "cores": torch.get_num_threads(), "host_cores": os.cpu_count(), "kind": "port",
-                         "sample": "%d x 1 design point through oracle/rcwa_oracle.py on %d torch threads" % (done, torch.get_num_threads())},
+        "config": {"workload": "BASELINE configs[1] unit: order %dx%d (n=%d), 1 patterned layer + SiO2 half space, one wavelength per step, through %s"
+                               % (args.order, args.order, n, impl), "points_per_step": 1},
+        "cpu_baseline": {"value": value, "unit": "layers/s", "cores": torch.get_num_threads(), "host_cores": os.cpu_count(), "kind": kind,
+                         "sample": "%d x 1 design point through %s on %d torch threads (steps and warm-ups capped by --ref-budget-s %.0f)"
+                                   % (done, impl, torch.get_num_threads(), budget)},
         "e2e": {"value": value, "unit": "layers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ------------------------------------------------------------------------------------------- BASELINE configs[2] and configs[4]
+SU8 = 1.6 ** 2
+
+
+def config3_inputs(P):
+    """Example1-1 style stack (Example1-1.ipynb:58-69,159-177): four a-Si:H bars (180 x 100 nm) in SU-8 rotated by
+    0 / 30 / 60 / 90 degrees, 200 nm each, separated by 100 nm SU-8 spacers = 8 layers; wavelengths 600-700 nm."""
+    import math
+    import torcwa_b200
+    geo = torcwa_b200.geometry(Lx=300.0, Ly=300.0, nx=300, ny=300, edge_sharpness=1000.0, dtype=torch.float64, device=torch.device("cpu"))
+    masks = torch.stack([geo.rectangle(Wx=180.0, Wy=100.0, Cx=150.0, Cy=150.0, theta=th) for th in (0.0, math.pi / 6, math.pi / 3, math.pi / 2)])
+    lams = torch.linspace(600.0, 700.0, N_SWEEP, dtype=torch.float64)
+    return masks, lams
+
+
+def step_config3(masks_dev, lam_dev, order, device):
+    import torcwa_b200
+    P = lam_dev.shape[0]
+    e = torch.tensor([eps_si(float(l)) for l in lam_dev.cpu()], dtype=torch.complex128, device=device)
+    sim = torcwa_b200.rcwa(freq=1.0 / lam_dev, order=[order, order], L=[300.0, 300.0], dtype=torch.complex128, device=device)
+    sim.add_input_layer(eps=1.46 ** 2)
+    sim.set_incident_angle(inc_ang=0.0, azi_ang=0.0)
+    for k in range(4):
+        grid = masks_dev[k][None] * e[:, None, None] + (1.0 - masks_dev[k])[None] * SU8
+        sim.add_layer(thickness=200.0, eps=grid)
+        del grid
+        sim.add_layer(thickness=100.0, eps=SU8)
+    sim.solve_global_smatrix()
+    return sim.S_parameters(orders=[0, 0], direction="forward", port="transmission", polarization="xx", ref_order=[0, 0])
+
+
+def config5_density(P, nx, ny, seed0=333):
+    """Blurred uniform noise in (0, 1), one per geometry, CPU generator for portability (Example6.ipynb:926-930 uses the
+    device RNG)."""
+    out = []
+    fx = torch.fft.fftfreq(nx, dtype=torch.float32)[:, None]
+    fy = torch.fft.fftfreq(ny, dtype=torch.float32)[None, :]
+    blur = torch.exp(-((fx * 40.0) ** 2 + (fy * 40.0) ** 2))
+    for b in range(P):
+        g = torch.Generator().manual_seed(seed0 + b)
+        r = torch.rand(nx, ny, generator=g, dtype=torch.float32)
+        r = 0.5 * (r + torch.flip(r, dims=[1]))
+        sm = torch.fft.ifft2(torch.fft.fft2(r) * blur).real
+        sm = (sm - sm.min()) / (sm.max() - sm.min())
+        out.append(0.1 + 0.8 * sm)
+    return torch.stack(out)
+
+
+def step_config5(rho_dev, order, device):
+    """Example6's iteration (Example6.ipynb:67-82,938-945): density -> permittivity -> one 300 nm layer on glass ->
+    FoM = sum |t(1,0)|^2 over xx, yy, xy, yx -> backward; returns (FoM per geometry summed, gradient w.r.t. the densities)."""
+    import torcwa_b200
+    P = rho_dev.shape[0]
+    rho = rho_dev.clone().requires_grad_(True)
+    lam = torch.full((P,), 532.0, dtype=torch.float32, device=device)
+    sim = torcwa_b200.rcwa(freq=1.0 / lam, order=list(order), L=[700.0, 300.0], dtype=torch.complex64, device=device)
+    sim.add_input_layer(eps=1.46 ** 2)
+    sim.set_incident_angle(inc_ang=0.0, azi_ang=0.0)
+    eps = rho.to(torch.complex64) * complex(SI_EPS[532.0]) + (1.0 - rho)
+    sim.add_layer(thickness=300.0, eps=eps)
+    sim.solve_global_smatrix()
+    fom = 0.0
+    for pol in ("xx", "yy", "xy", "yx"):
+        t = sim.S_parameters(orders=[1, 0], direction="forward", port="transmission", polarization=pol, ref_order=[0, 0])
+        fom = fom + (t.abs() ** 2).sum()
+    fom.backward()
+    return fom.detach(), rho.grad
+
+
+def bench_config(args):
+    """--config 3 / 5: the same JSON schema as the headline config, with a simpler extra-metrics section."""
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    P = args.points
+    if args.config == 3:
+        order = args.order
+        masks, lams = config3_inputs(P)
+        masks_host, lams_host = masks.pin_memory(), lams.pin_memory()
+        masks_res, lams_res = masks.to(device), lams.to(device)
+
+        def chunk(s):
+            return (torch.arange(P) + (s * world + rank) * P) % N_SWEEP
+
+        def step_res(s):
+            return step_config3(masks_res, lams_res[chunk(s).to(device)], order, device)
+
+        def step_e2e(s):
+            m = masks_host.to(device, non_blocking=True)
+            l = lams_host[chunk(s)].pin_memory().to(device, non_blocking=True)
+            return step_config3(m, l, order, device)
+        layers_per_point, h2d = 8, int(masks.numel() * 8 + P * 8)
+        n = 2 * (2 * order + 1) ** 2
+        metric = "layers/sec (order %dx%d, 8 stacked layers, c128)" % (order, order)
+        workload = ("BASELINE configs[2]: order %dx%d (n=%d), 8 layers per point (4 rotated a-Si:H bars in SU-8 + 4 homogeneous spacers, "
+                    "Example1-1 style), complex128, %d wavelengths per step per GPU" % (order, order, n, P))
+        dtype = "f64 (complex128 API: every stage on the fp64 pipes)"
+    else:
+        order = (args.order, args.order) if args.order_y is None else (args.order, args.order_y)
+        nx, ny = 700, 300
+        rho = config5_density(P * 4, nx, ny)
+        rho_host, rho_res = rho.pin_memory(), rho.to(device)
+
+        def chunk(s):
+            return (torch.arange(P) + (s * world + rank) * P) % rho.shape[0]
+
+        def step_res(s):
+            return step_config5(rho_res[chunk(s).to(device)], order, device)[0]
+
+        def step_e2e(s):
+            r = rho_host[chunk(s)].pin_memory().to(device, non_blocking=True)
+            f, g = step_config5(r, order, device)
+            return torch.stack([f, g.abs().sum()])
+        layers_per_point, h2d = 1, int(P * nx * ny * 4)
+        n = 2 * (2 * order[0] + 1) * (2 * order[1] + 1)
+        metric = "layers/sec forward+backward (order %dx%d, c64)" % order
+        workload = ("BASELINE configs[4]: order %dx%d (n=%d), topology-optimisation step (Example6): density -> layer -> FoM = sum |t(1,0)|^2 "
+                    "-> autograd backward to the 700 x 300 density, complex64 API, %d geometries per step per GPU" % (order[0], order[1], n, P))
+        dtype = "f64 internals behind the complex64 API (differentiable pipeline: autograd over the C-ABI primitives)"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, K, W, s0=0, fetch=False):
+        for s in range(W):
+            r = fn(s0 + s)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(K):
+            r = fn(s0 + W + s)
+            if fetch:
+                r = r.cpu()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+    K, W = args.steps, args.warmup
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms_res = timed(step_res, K, W)
+    clk = clocks.stop()
+    ms_e2e = timed(step_e2e, K, 1, s0=K + W, fetch=True)
+    if rank == 0:
+        launches, per_kernel = count_my_launches(lambda: step_res(0))
+        value = P * world * layers_per_point * K / (ms_res * 1e-3)
+        tot_k = max(sum(v[1] for v in per_kernel.values()), 1e-9) if launches else 1.0
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        mvk = per_kernel.get("hb_matvec") if launches else None
+        n_eigs = P * (4 if args.config == 3 else 1)
+        b_hess = 16.0 * n ** 3 / 3.0
+        roof = None if not mvk else {
+            "bound": "hbm", "kernel": "hb_matvec_kernel (streaming mat-vec of the blocked Hessenberg reduction) inside the step, CUPTI durations of all its launches",
+            "achieved": n_eigs * b_hess / mvk[1] / 1e3, "peak": hbm_peak, "unit": "GB/s", "frac": n_eigs * b_hess / mvk[1] / 1e3 / hbm_peak, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
+            "note": "algorithmic bytes 16 n^3 / 3 per eigen-decomposition; the whole-stage fraction is the headline config's roofline.frac"}
+        cpu = None
+        if args.cpu_baseline and world == 1:
+            cpu = cpu_baseline_config(args)
+        print(json.dumps({
+            "metric": metric, "value": value, "unit": "layers/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_res / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
+            "data": "synthetic (rotated bars with linear a-Si:H dispersion)" if args.config == 3 else "synthetic (seeded blurred-noise densities)",
+            "config": {"workload": workload, "points_per_step_per_gpu": P, "layers_per_point": layers_per_point,
+                       "l2": "working set per step >> 126 MB L2", "parallelism": "dp%d" % world},
+            "e2e": {"value": P * world * layers_per_point * K / (ms_e2e * 1e-3), "unit": "layers/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(P * 8 if args.config == 3 else 16), "ms_per_step": ms_e2e / K},
+            "gpu_launches": (launches * K) if launches else None, "gpu_launches_per_step": launches, "clocks": clk, "roofline": roof,
+            "kernel_time_share": {k: round(v[1] / tot_k, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])[:8]} if launches else per_kernel,
+            "cpu_baseline": cpu}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline_config(args):
+    """CPU leg of configs 3 / 5 (one layer of one design point, extrapolated)."""
+    torch.set_num_threads(ref_threads())
+    if args.config == 3:
+        dt, _, kind = cpu_point(args.order, torch.complex128, 650.0)
+        return {"value": 1.0 / dt, "unit": "layers/s", "cores": torch.get_num_threads(), "host_cores": os.cpu_count(), "kind": kind,
+                "sample": "ONE patterned layer of ONE design point at order %dx%d, complex128 (%.1f s), taken as the per-layer cost of the 8-layer stack "
+                          "(BASELINE.md 3.1 allows the extrapolation; the homogeneous layers cost the reference the same dense algebra)" % (args.order, args.order, dt)}
+    torcwa = reference_module()
+    if torcwa is None:
+        return {"unavailable": "baseline/_ref is missing (the oracle port has no autograd leg)"}
+    ox, oy = 15, 8                                                   # Example6's own order; order 25x25 takes > 15 min per forward on the host
+    rho = config5_density(1, 700, 300)[0].requires_grad_(True)
+    t0 = time.perf_counter()
+    sim = torcwa.rcwa(freq=1 / torch.tensor(532.0), order=[ox, oy], L=[700.0, 300.0], dtype=torch.complex64, device=torch.device("cpu"))
+    sim.add_input_layer(eps=1.46 ** 2)
+    sim.set_incident_angle(inc_ang=0.0, azi_ang=0.0)
+    sim.add_layer(thickness=300.0, eps=rho.to(torch.complex64) * complex(SI_EPS[532.0]) + (1.0 - rho))
+    sim.solve_global_smatrix()
+    fom = 0.0
+    for pol in ("xx", "yy", "xy", "yx"):
+        fom = fom + (sim.S_parameters(orders=[1, 0], direction="forward", port="transmission", polarization=pol, ref_order=[0, 0]).abs() ** 2).sum()
+    fom.backward()
+    dt = time.perf_counter() - t0
+    n_ref = 2 * (2 * ox + 1) * (2 * oy + 1)
+    oyy = args.order if args.order_y is None else args.order_y
+    n_here = 2 * (2 * args.order + 1) * (2 * oyy + 1)
+    scale = (n_here / n_ref) ** 3
+    return {"value": 1.0 / (dt * scale), "unit": "layers/s", "cores": torch.get_num_threads(), "host_cores": os.cpu_count(), "kind": "reference",
+            "sample": "ONE forward+backward of the unmodified reference at Example6's own order [15,8] (n=%d, complex64, %.1f s), scaled by (n/n_ref)^3 = %.1f "
+                      "to this order (n=%d): an EXTRAPOLATION (BASELINE.md 3.1), the full size takes > 15 min per forward on the host" % (n_ref, dt, scale, n_here)}
+
+
+def bench_reference_config(args):
+    c = cpu_baseline_config(args)
+    if "value" not in c:
+        print(json.dumps({"impl": "reference", "unavailable": c.get("unavailable", "?")}))
+        return
+    print(json.dumps({"impl": "reference", "metric": "layers/sec (config %d)" % args.config, "value": c["value"], "unit": "layers/s", "n_gpus": args.gpus,
+                      "steps": 1, "warmup": 0, "ms_per_step": 1e3 / c["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "c128" if args.config == 3 else "c64", "data": "synthetic", "config": {"workload": c["sample"]}, "cpu_baseline": c,
+                      "e2e": {"value": c["value"], "unit": "layers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def main():
@@ -458,14 +817,24 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--points", type=int, default=128, help="wavelengths per step per GPU (peak footprint ~0.7 GB each)")
-    ap.add_argument("--order", type=int, default=15)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5], help="BASELINE.json configs[config-1]: 2 = headline (order 15, c64 sweep), "
+                    "3 = order 21, 8 stacked layers, complex128, 5 = forward + autograd backward (Example6)")
+    ap.add_argument("--points", type=int, default=None, help="design points per step per GPU (default 128 / 16 / 4 for config 2 / 3 / 5)")
+    ap.add_argument("--order", type=int, default=None, help="Fourier order (default 15 / 21 / 25 for config 2 / 3 / 5)")
+    ap.add_argument("--order-y", type=int, default=None, help="config 5 only: second order (Example6 uses [15, 8])")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-cuda-baseline", dest="cuda_baseline", action="store_false", help="skip the reference's PyTorch-CUDA path (unmodified baseline/_ref on this GPU)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
     ap.add_argument("--ref-dtype", default="c128", choices=["c64", "c128"], help="arithmetic of the CPU reference legs (see REF_DTYPE_NOTE)")
     args = ap.parse_args()
+    if args.points is None:
+        args.points = {2: 128, 3: 16, 5: 4}[args.config]
+    if args.order is None:
+        args.order = {2: 15, 3: 21, 5: 25}[args.config]
     if args.impl == "reference":
         bench_reference(args)
+    elif args.config != 2:
+        bench_config(args)
     else:
         bench_b200(args)
 

@@ -94,8 +94,9 @@ int rcwa_tc_schedule(int slices, int levels, unsigned* ops, int* meta, unsigned*
  *   rotations, AED swaps, AED restore steps); 8: time budget of a serial QR slice in us (default 90);
  *   9: number of independently pipelined matrix groups of the QR phase (default 2); 10: skip the zero
  *   k groups of the banded window unitaries in the QR update GEMMs (default 0, measured no gain);
- *   11: Hessenberg phase as two staggered half batches (default 0, measured slower).  Call before
- *   enqueuing work; the numerical contract does not depend on them. */
+ *   11: Hessenberg phase as two staggered half batches (default 0, measured slower); 12: triangular solves of the
+ *   S-matrix stage on the tcgen05 engine too when gemm_slices >= 2 (default 0: measured slower at K = 512).  Call before
+ *   asking for workspace sizes and enqueuing work; the numerical contract does not depend on them. */
 int rcwa_zgemm_batched_cfg(int cfg, int opa, int opb, int M, int N, int K, double alpha_re, double alpha_im,
                            const void* A, int lda, long long stride_a, const void* B, int ldb, long long stride_b,
                            double beta_re, double beta_im, void* C, int ldc, long long stride_c,
@@ -134,6 +135,12 @@ int rcwa_pq_assemble(const void* eta, const void* E, const void* Mc, const void*
 size_t rcwa_eig_workspace_bytes(int n, int nb);
 int rcwa_eig(void* A, int n, int nb, void* w, void* V, void* ws, size_t ws_bytes, int* info,
              void* host_flag, void* stream);
+/* The same routine in two calls on the same arguments: phases = 1: Hessenberg reduction only (only enqueues; the reduced
+ * problem stays in A and ws), phases = 2: QR iteration and eigenvectors of a problem reduced by a phases = 1 call,
+ * phases = 3: both (= rcwa_eig).  Lets a host pipeline sub-batches: the HBM-bound reduction of one sub-batch runs under
+ * the latency-bound QR iteration of another (torcwa_b200/rcwa.py). */
+int rcwa_eig_phases(void* A, int n, int nb, void* w, void* V, void* ws, size_t ws_bytes, int* info,
+                    void* host_flag, int phases, void* stream);
 /* Diagnostics of the last rcwa_eig that used workspace `ws`: out[4*b..] = {QR sweeps, window passes,
  * AED windows, info} of matrix b (device int32 [nb,4]). */
 int rcwa_eig_stats(const void* ws, int n, int nb, int* out, void* stream);

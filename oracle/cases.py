@@ -11,7 +11,10 @@ import torch
 from .rcwa_oracle import rectangle_grid
 
 SI_EPS = {532.0: complex(12.011610263133004, 0.5259120147560001),
-          650.0: complex(10.362267239174999, 0.15362360819199997)}
+          650.0: complex(10.362267239174999, 0.15362360819199997),
+          400.0: complex(16.24464604339499, 3.9697033465479983),
+          550.0: complex(11.646077602684997, 0.41213333041199984),
+          700.0: complex(9.985966439994998, 0.11010441325199999)}
 SU8 = 1.6 ** 2
 
 PROBE_ORDERS = [[0, 0], [1, 0], [-1, 0], [0, 1], [0, -1], [1, 1]]
@@ -26,7 +29,7 @@ def _rect(d=300.0, Wx=180.0, Wy=100.0, theta=0.0, eps_in=SI_EPS[532.0], eps_bg=1
 
 def _base(**kw):
     c = dict(L=[300.0, 300.0], nxy=[300, 300], edge_sharpness=1000.0, lam=532.0, eps_in=1.46 ** 2,
-             eps_out=None, inc=0.0, azi=0.0, full=False, big=False)
+             eps_out=None, inc=0.0, azi=0.0, full=False, big=False, c128_only=False)
     c.update(kw)
     return c
 
@@ -36,6 +39,16 @@ def _stack():
     for k, th in enumerate([0.0, math.pi / 6, math.pi / 3, math.pi / 2]):
         out.append(_rect(d=200.0, theta=th, eps_in=SI_EPS[650.0], eps_bg=SU8))
         out.append(dict(kind="homogeneous", d=100.0, eps=SU8 if k != 1 else complex(2.0, 0.3)))
+    return out
+
+
+def _stack_config3():
+    """BASELINE.json configs[2] (Example1-1.ipynb:58-69,159-177): four a-Si:H bars in SU-8, rotated by 0 / 30 / 60 / 90
+    degrees, 200 nm each, separated by 100 nm homogeneous SU-8 spacers: 8 layers."""
+    out = []
+    for th in (0.0, math.pi / 6, math.pi / 3, math.pi / 2):
+        out.append(_rect(d=200.0, theta=th, eps_in=SI_EPS[650.0], eps_bg=SU8))
+        out.append(dict(kind="homogeneous", d=100.0, eps=SU8))
     return out
 
 
@@ -51,6 +64,13 @@ CASES = {
                         inc=0.2, azi=-0.7, nxy=[64, 48], full=True),
     # zero-layer Fresnel interface (Example0.ipynb:59-76)
     "fresnel_o2": _base(order=[2, 2], layers=[], eps_out=1.0, inc=0.5, full=True),
+    # BASELINE.json configs[3] (Example3.ipynb:85-101): corners and centre of the (Wx, Wy, lambda) sweep at order 15
+    "sweep_o15_a": _base(order=[15, 15], layers=[_rect(Wx=50.0, Wy=250.0, eps_in=SI_EPS[400.0])], lam=400.0, big=True),
+    "sweep_o15_b": _base(order=[15, 15], layers=[_rect(Wx=250.0, Wy=50.0, eps_in=SI_EPS[700.0])], lam=700.0, big=True),
+    "sweep_o15_c": _base(order=[15, 15], layers=[_rect(Wx=150.0, Wy=150.0, eps_in=SI_EPS[550.0])], lam=550.0, big=True),
+    # BASELINE.json configs[2]: order 21 x 21, 8 stacked layers, complex128 (the reference's complex64 run is skipped:
+    # its MKL cgetri slow path would take hours at 4N = 7396)
+    "stack_o21": _base(order=[21, 21], layers=_stack_config3(), lam=650.0, big=True, c128_only=True),
     # C4v-symmetric cell: exactly degenerate eigenpairs
     "square_o4": _base(order=[4, 4], layers=[_rect(Wx=150.0, Wy=150.0)]),
 }

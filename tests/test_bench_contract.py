@@ -18,7 +18,9 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "layers/s" and d["higher_is_better"] is True
     for k in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the unmodified reference (baseline/_ref) when it is installed, the oracle port otherwise
+    want = "reference" if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "torcwa")) else "port"
+    assert d["cpu_baseline"]["kind"] == want and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
 

@@ -161,8 +161,8 @@ def test_order15_batched_sweep_parity_and_batch_independence(golden_dir):
     lams = torch.linspace(500.0, 640.0, 24, dtype=torch.float64)
     lams[0] = 532.0
 
-    def solve(lam_vec):
-        sim = torcwa_b200.rcwa(freq=1 / lam_vec, order=case["order"], L=case["L"], dtype=cd, device=dev, store_intermediates=False)
+    def solve(lam_vec, pipeline=1):
+        sim = torcwa_b200.rcwa(freq=1 / lam_vec, order=case["order"], L=case["L"], dtype=cd, device=dev, store_intermediates=False, pipeline=pipeline)
         sim.add_input_layer(eps=case["eps_in"])
         sim.set_incident_angle(0.0, 0.0)
         sim.add_layer(thickness=float(d), eps=grid.to(dev))
@@ -183,6 +183,12 @@ def test_order15_batched_sweep_parity_and_batch_independence(golden_dir):
     sub = solve(lams[:5].clone())                                  # one group, other slice boundaries
     t_sub = sub.S_parameters(orders=[[0, 0], [1, 0], [0, -1]], polarization="xx")
     assert torch.equal(t_all[:5], t_sub)
+    del sim, sub
+    # the same sweep as two pipelined sub-batches (own streams, own host threads, staggered eigensolvers)
+    piped = solve(lams, pipeline=2)
+    assert piped._children is not None and len(piped._children) == 2
+    assert int(piped.eig_info[0].abs().max()) == 0
+    assert torch.equal(piped.S_parameters(orders=[[0, 0], [1, 0], [0, -1]], polarization="xx"), t_all)
 
 
 def test_order15_energy_conservation_lossless_cell():

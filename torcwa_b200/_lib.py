@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("RCWA_B200_LIB", "librcwa_b200.so"
 EXPORTS = [
     "rcwa_b200_abi_version", "rcwa_gemm_scratch_bytes", "rcwa_convmat_workspace_bytes", "rcwa_convmat",
     "rcwa_zgemm_batched", "rcwa_zgemm_batched_cfg", "rcwa_zgemm_tc_workspace_bytes", "rcwa_zgemm_tc_batched", "rcwa_tc_split", "rcwa_tc_schedule", "rcwa_set_tuning", "rcwa_get_tuning", "rcwa_lu_tinv_bytes", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
-    "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_eig_stats", "rcwa_eig_profile", "rcwa_hessenberg", "rcwa_hessenberg_matvec_probe", "rcwa_hessenberg_panel_width", "rcwa_kz_branch", "rcwa_eig_backward_workspace_bytes", "rcwa_eig_backward", "rcwa_layer_smatrix_workspace_bytes",
+    "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_eig_phases", "rcwa_eig_stats", "rcwa_eig_profile", "rcwa_hessenberg", "rcwa_hessenberg_matvec_probe", "rcwa_hessenberg_panel_width", "rcwa_kz_branch", "rcwa_eig_backward_workspace_bytes", "rcwa_eig_backward", "rcwa_layer_smatrix_workspace_bytes",
     "rcwa_layer_smatrix", "rcwa_redheffer_workspace_bytes", "rcwa_redheffer", "rcwa_redheffer_bdleft", "rcwa_blockdiag_dense",
 ]
 
@@ -39,6 +39,7 @@ _SIGS = {
     "rcwa_pq_assemble": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "rcwa_eig_workspace_bytes": (_sz, [_i, _i]),
     "rcwa_eig": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "rcwa_eig_phases": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp, _vp, _i, _vp]),
     "rcwa_eig_stats": (_i, [_vp, _i, _i, _vp, _vp]),
     "rcwa_eig_profile": (_i, [_vp, _i, _i, _vp, _vp]),
     "rcwa_hessenberg": (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp]),
@@ -303,8 +304,10 @@ _tls = threading.local()       # pinned polling flags of rcwa_eig: one buffer pe
 
 
 @_on_device
-def eig(A):
-    """A [nb,n,n] (destroyed) -> (w [nb,n], V [nb,n,n], info [nb])."""
+def eig(A, after_reduction=None):
+    """A [nb,n,n] (destroyed) -> (w [nb,n], V [nb,n,n], info [nb]).  after_reduction: optional callable invoked on the host
+    once the Hessenberg phase has been ENQUEUED on the current stream (the routine then runs as two calls, rcwa_eig_phases):
+    the hook a pipelining host uses to release the next sub-batch (torcwa_b200/rcwa.py)."""
     lib = load()
     _c128(A, "A")
     nb, n = A.shape[0], A.shape[1]
@@ -315,8 +318,15 @@ def eig(A):
     ws = _ws(nbytes, A.device)
     if getattr(_tls, "host_flag", None) is None:
         _tls.host_flag = torch.zeros(16, dtype=torch.int32).pin_memory()
-    _check(lib.rcwa_eig(_ptr(A), n, nb, _ptr(w), _ptr(V), _ptr(ws), nbytes, _ptr(info),
-                        ctypes.c_void_p(_tls.host_flag.data_ptr()), _stream()), "rcwa_eig")
+    hf = ctypes.c_void_p(_tls.host_flag.data_ptr())
+    if after_reduction is None:
+        _check(lib.rcwa_eig(_ptr(A), n, nb, _ptr(w), _ptr(V), _ptr(ws), nbytes, _ptr(info), hf, _stream()), "rcwa_eig")
+    else:
+        try:
+            _check(lib.rcwa_eig_phases(_ptr(A), n, nb, _ptr(w), _ptr(V), _ptr(ws), nbytes, _ptr(info), hf, 1, _stream()), "rcwa_eig_phases(1)")
+        finally:
+            after_reduction()
+        _check(lib.rcwa_eig_phases(_ptr(A), n, nb, _ptr(w), _ptr(V), _ptr(ws), nbytes, _ptr(info), hf, 2, _stream()), "rcwa_eig_phases(2)")
     global last_eig_stats
     stats = torch.empty((nb, 4), dtype=torch.int32, device=A.device)
     _check(lib.rcwa_eig_stats(_ptr(ws), n, nb, _ptr(stats), _stream()), "rcwa_eig_stats")

@@ -132,6 +132,10 @@ int rcwa_get_tuning(int key) { return gemm_get_tuning(key); }
 size_t rcwa_lu_tinv_bytes(int n, int nb) { return align256(lu_tinv_elems(n, nb > 0 ? nb : 1) * sizeof(cplx)); }
 static size_t tinv_bytes(int n, int nb, int slices) { return align256(lu_tinv_elems(n, nb > 0 ? nb : 1, slices) * sizeof(cplx)); }
 static int norm_slices(int s) { return (s >= 2 && s <= TC_MAXS) ? s : 0; }
+// Triangular solves on the tcgen05 engine (512-wide right-looking blocks): off by default -- measured on B200 (profiles/
+// r2g_stage_kernels_*.log) the K = 512 products are bound by the kernel's epilogue and the 512-wide block inverses cost
+// more than they save; tuning key 12 = 1 turns them on for experiments.
+static int solve_slices(int sl) { return gemm_get_tuning(12) ? sl : 0; }
 
 int rcwa_lu_factor(void* A, long long stride, int n, int lda, int nb, int* ipiv, int* perm, int* info, void* tinv, void* gs, void* stream) {
     if (!A) return -1;
@@ -181,6 +185,10 @@ int rcwa_pq_assemble(const void* eta, const void* E, const void* Mc, const void*
 size_t rcwa_eig_workspace_bytes(int n, int nb) { return eig_workspace_bytes(n, nb); }
 
 int rcwa_eig(void* A, int n, int nb, void* w, void* V, void* ws, size_t ws_bytes, int* info, void* host_flag, void* stream) {
+    return rcwa_eig_phases(A, n, nb, w, V, ws, ws_bytes, info, host_flag, 3, stream);
+}
+
+int rcwa_eig_phases(void* A, int n, int nb, void* w, void* V, void* ws, size_t ws_bytes, int* info, void* host_flag, int phases, void* stream) {
     if (!A) return -1;
     if (n <= 0) return -2;
     if (nb <= 0) return -3;
@@ -188,7 +196,8 @@ int rcwa_eig(void* A, int n, int nb, void* w, void* V, void* ws, size_t ws_bytes
     if (!V) return -5;
     if (!ws || ws_bytes < eig_workspace_bytes(n, nb)) return -6;
     if (!info) return -8;
-    return cu(eig((cplx*)A, n, nb, (cplx*)w, (cplx*)V, (char*)ws, ws_bytes, info, (volatile int*)host_flag, S(stream)));
+    if (phases < 1 || phases > 3) return -10;
+    return cu(eig((cplx*)A, n, nb, (cplx*)w, (cplx*)V, (char*)ws, ws_bytes, info, (volatile int*)host_flag, S(stream), phases));
 }
 
 int rcwa_eig_stats(const void* ws, int n, int nb, int* out, void* stream) {
@@ -279,7 +288,7 @@ int rcwa_eig_backward(const void* lam, const void* X, const void* glam, const vo
 size_t rcwa_layer_smatrix_workspace_bytes(int N, int nb, int gemm_slices) {
     const size_t n = 2 * (size_t)N, mat = align256(n * n * nb * sizeof(cplx));
     const int sl = norm_slices(gemm_slices);
-    return 6 * mat + 2 * align256(n * nb * sizeof(int)) + tinv_bytes((int)n, nb, sl) + rcwa_gemm_scratch_bytes(nb) + align256(tc_ctx_bytes((int)n, nb, sl));
+    return 6 * mat + 2 * align256(n * nb * sizeof(int)) + tinv_bytes((int)n, nb, solve_slices(sl)) + rcwa_gemm_scratch_bytes(nb) + align256(tc_ctx_bytes((int)n, nb, sl));
 }
 
 int rcwa_layer_smatrix(const void* W, const void* kz, const void* Q, const void* vfinv, const double* omega,
@@ -310,19 +319,20 @@ int rcwa_layer_smatrix(const void* W, const void* kz, const void* Q, const void*
     int* ipiv = (int*)p; p += align256((size_t)n * nb * sizeof(int));
     int* perm = (int*)p; p += align256((size_t)n * nb * sizeof(int));
     const int sl = norm_slices(gemm_slices);
-    cplx* tinv = (cplx*)p; p += tinv_bytes(n, nb, sl);
+    cplx* tinv = (cplx*)p; p += tinv_bytes(n, nb, solve_slices(sl));
     ZGemmProblem* gs = (ZGemmProblem*)p; p += rcwa_gemm_scratch_bytes(nb);
     TcCtx tc = {sl, p, tc_ctx_bytes(n, nb, sl)};
+    const int ssl = solve_slices(sl);
     // QW = Q * W
     CK(gemm_auto(&tc, OP_N, OP_N, n, n, n, 1.0, (const cplx*)Q, n, ms, (const cplx*)W, n, ms, C(0, 0), b0, n, ms, nb, gs, st));
     // M+ (b1), M- (b2), R+ (b3), R- (b4)
     CK(layer_form((const cplx*)W, b0, (const cplx*)kz, (const cplx*)vfinv, omega, thickness, nb, N, b1, b2, b3, b4, st));
     // T+ = R+ M+^-1  -> b0
-    CK(lu_factor(b1, ms, n, n, nb, ipiv, perm, info, tinv, gs, st, true, sl));
-    CK(lu_solve_right(b1, ms, n, n, perm, tinv, b3, ms, n, n, b0, ms, n, b5, nb, gs, st, &tc));
+    CK(lu_factor(b1, ms, n, n, nb, ipiv, perm, info, tinv, gs, st, true, ssl));
+    CK(lu_solve_right(b1, ms, n, n, perm, tinv, b3, ms, n, n, b0, ms, n, b5, nb, gs, st, ssl ? &tc : nullptr));
     // T- = R- M-^-1  -> b3   (info keeps the first failure: the second factorisation does not clear it)
-    CK(lu_factor(b2, ms, n, n, nb, ipiv, perm, info, tinv, gs, st, false, sl));
-    CK(lu_solve_right(b2, ms, n, n, perm, tinv, b4, ms, n, n, b3, ms, n, b5, nb, gs, st, &tc));
+    CK(lu_factor(b2, ms, n, n, nb, ipiv, perm, info, tinv, gs, st, false, ssl));
+    CK(lu_solve_right(b2, ms, n, n, perm, tinv, b4, ms, n, n, b3, ms, n, b5, nb, gs, st, ssl ? &tc : nullptr));
     CK(layer_finish(b0, b3, nb, n, (cplx*)S11, (cplx*)S21, st));
     return 0;
 }
@@ -330,7 +340,7 @@ int rcwa_layer_smatrix(const void* W, const void* kz, const void* Q, const void*
 size_t rcwa_redheffer_workspace_bytes(int n, int nb, int gemm_slices) {
     const size_t mat = align256((size_t)n * n * nb * sizeof(cplx));
     const int sl = norm_slices(gemm_slices);
-    return 5 * mat + 2 * align256((size_t)n * nb * sizeof(int)) + tinv_bytes(n, nb, sl) + rcwa_gemm_scratch_bytes(nb) + align256(tc_ctx_bytes(n, nb, sl));
+    return 5 * mat + 2 * align256((size_t)n * nb * sizeof(int)) + tinv_bytes(n, nb, solve_slices(sl)) + rcwa_gemm_scratch_bytes(nb) + align256(tc_ctx_bytes(n, nb, sl));
 }
 
 int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const out[4], int nb, int n, void* ws, int* info, int gemm_slices, void* stream) {
@@ -358,9 +368,10 @@ int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const
     int* ipiv = (int*)p; p += align256((size_t)n * nb * sizeof(int));
     int* perm = (int*)p; p += align256((size_t)n * nb * sizeof(int));
     const int sl = norm_slices(gemm_slices);
-    cplx* tinv = (cplx*)p; p += tinv_bytes(n, nb, sl);
+    cplx* tinv = (cplx*)p; p += tinv_bytes(n, nb, solve_slices(sl));
     ZGemmProblem* gs = (ZGemmProblem*)p; p += rcwa_gemm_scratch_bytes(nb);
     TcCtx tc = {sl, p, tc_ctx_bytes(n, nb, sl)};
+    const int ssl = solve_slices(sl);
     const cplx *Sm11 = (const cplx*)Sm[0], *Sm21 = (const cplx*)Sm[1], *Sm12 = (const cplx*)Sm[2], *Sm22 = (const cplx*)Sm[3];
     const cplx *Sn11 = (const cplx*)Sn[0], *Sn21 = (const cplx*)Sn[1], *Sn12 = (const cplx*)Sn[2], *Sn22 = (const cplx*)Sn[3];
     cplx *O11 = (cplx*)out[0], *O21 = (cplx*)out[1], *O12 = (cplx*)out[2], *O22 = (cplx*)out[3];
@@ -370,10 +381,10 @@ int rcwa_redheffer(const void* const Sm[4], const void* const Sn[4], void* const
     // D = I - Sm12 Sn21
     CK(set_identity(D, n, n, ms, nb, st));
     CK(gemm_auto(&tc, OP_N, OP_N, n, n, n, -1.0, Sm12, n, ms, Sn21, n, ms, one, D, n, ms, nb, gs, st));
-    CK(lu_factor(D, ms, n, n, nb, ipiv, perm, info, tinv, gs, st, true, sl));
+    CK(lu_factor(D, ms, n, n, nb, ipiv, perm, info, tinv, gs, st, true, ssl));
     // Y1 = Sn11 D^-1 ; Y2 = Sn21 D^-1     (T is free until later: it is the solves' work buffer)
-    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn11, ms, n, n, Y1, ms, n, T, nb, gs, st, &tc));
-    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn21, ms, n, n, Y2, ms, n, T, nb, gs, st, &tc));
+    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn11, ms, n, n, Y1, ms, n, T, nb, gs, st, ssl ? &tc : nullptr));
+    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn21, ms, n, n, Y2, ms, n, T, nb, gs, st, ssl ? &tc : nullptr));
     // G = Sm12 Sn22
     GEMM(Sm12, Sn22, zero, G);
     // S11 = Y1 Sm11
@@ -419,9 +430,10 @@ int rcwa_redheffer_bdleft(const void* const Sm_bd[4], const void* const Sn[4], v
     int* ipiv = (int*)p; p += align256((size_t)n * nb * sizeof(int));
     int* perm = (int*)p; p += align256((size_t)n * nb * sizeof(int));
     const int sl = norm_slices(gemm_slices);
-    cplx* tinv = (cplx*)p; p += tinv_bytes(n, nb, sl);
+    cplx* tinv = (cplx*)p; p += tinv_bytes(n, nb, solve_slices(sl));
     ZGemmProblem* gs = (ZGemmProblem*)p; p += rcwa_gemm_scratch_bytes(nb);
     TcCtx tc = {sl, p, tc_ctx_bytes(n, nb, sl)};
+    const int ssl = solve_slices(sl);
     const cplx *m11 = (const cplx*)Sm_bd[0], *m21 = (const cplx*)Sm_bd[1], *m12 = (const cplx*)Sm_bd[2], *m22 = (const cplx*)Sm_bd[3];
     const cplx *Sn11 = (const cplx*)Sn[0], *Sn21 = (const cplx*)Sn[1], *Sn12 = (const cplx*)Sn[2], *Sn22 = (const cplx*)Sn[3];
     cplx *O11 = (cplx*)out[0], *O21 = (cplx*)out[1], *O12 = (cplx*)out[2], *O22 = (cplx*)out[3];
@@ -430,9 +442,9 @@ int rcwa_redheffer_bdleft(const void* const Sm_bd[4], const void* const Sn[4], v
     // D = I - Sm12 Sn21          (Sm12 is four diagonals: an O(n^2) row combination, not a GEMM)
     CK(set_identity(D, n, n, ms, nb, st));
     CK(bd_left_mul(m12, Sn21, nb, N, n, mone, one, D, st));
-    CK(lu_factor(D, ms, n, n, nb, ipiv, perm, info, tinv, gs, st, true, sl));
-    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn11, ms, n, n, Y1, ms, n, T, nb, gs, st, &tc));      // Y1 = Sn11 D^-1 (T = work)
-    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn21, ms, n, n, Y2, ms, n, T, nb, gs, st, &tc));      // Y2 = Sn21 D^-1
+    CK(lu_factor(D, ms, n, n, nb, ipiv, perm, info, tinv, gs, st, true, ssl));
+    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn11, ms, n, n, Y1, ms, n, T, nb, gs, st, ssl ? &tc : nullptr));      // Y1 = Sn11 D^-1 (T = work)
+    CK(lu_solve_right(D, ms, n, n, perm, tinv, Sn21, ms, n, n, Y2, ms, n, T, nb, gs, st, ssl ? &tc : nullptr));      // Y2 = Sn21 D^-1
     CK(bd_left_mul(m12, Sn22, nb, N, n, one, zero, G, st));                             // G = Sm12 Sn22
     CK(bd_right_mul(m11, Y1, nb, N, n, one, zero, O11, st));                            // S11 = Y1 Sm11
     CK(cudaMemcpyAsync(O12, Sn12, bytes, cudaMemcpyDeviceToDevice, st));                // S12 = Sn12 + Y1 G

@@ -1305,15 +1305,18 @@ cudaError_t hessenberg(cplx* A, int n, int nb, cplx* Zout, char* wsb, size_t ws_
     return cudaMemcpyAsync(Zout, ws.Z, sizeof(cplx) * (size_t)n * n * nb, cudaMemcpyDeviceToDevice, st);
 }
 
-cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t ws_bytes, int* info, volatile int* host_flag, cudaStream_t st) {
+cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t ws_bytes, int* info, volatile int* host_flag, cudaStream_t st, int phases) {
     EigWs ws = carve(wsb, n, nb);
     if (ws_bytes < ws.total) return cudaErrorInvalidValue;
     const long long ms = (long long)n * n;
     const cplx one = C(1, 0), zero = C(0, 0);
 
     // ---------------- phase 1: keep a copy A0 of the input for the final T = Z^H A0 Z; Hessenberg, Z accumulated
-    EK(cudaMemcpyAsync(ws.X, A, sizeof(cplx) * (size_t)n * n * nb, cudaMemcpyDeviceToDevice, st));
-    EK(hessenberg_phase(A, n, nb, ws, st));
+    if (phases & 1) {
+        EK(cudaMemcpyAsync(ws.X, A, sizeof(cplx) * (size_t)n * n * nb, cudaMemcpyDeviceToDevice, st));
+        EK(hessenberg_phase(A, n, nb, ws, st));
+    }
+    if (!(phases & 2)) return cudaGetLastError();
 
     // ---------------- phase 2: QR passes (host enqueues, polls the pinned flag every `poll` passes)
     qr_init_kernel<<<(nb + 127) / 128, 128, 0, st>>>(ws.states, n, nb);

@@ -117,6 +117,7 @@ cudaError_t eig_stats(const char* ws, int n, int nb, int* out, cudaStream_t st);
 cudaError_t eig_profile(const char* ws, int n, int nb, long long* out, cudaStream_t st);
 cudaError_t hessenberg(cplx* A, int n, int nb, cplx* Zout, char* ws, size_t ws_bytes, cudaStream_t st);
 cudaError_t eig_matvec_probe(const cplx* A, int n, int nb, int j, char* ws, size_t ws_bytes, cudaStream_t st);
-cudaError_t eig(cplx* A, int n, int nb, cplx* w, cplx* V, char* ws, size_t ws_bytes, int* info, volatile int* host_flag, cudaStream_t st);
+// phases: 1 = Hessenberg reduction only (state stays in A / ws), 2 = QR iteration + eigenvectors of a reduced problem, 3 = both
+cudaError_t eig(cplx* A, int n, int nb, cplx* w, cplx* V, char* ws, size_t ws_bytes, int* info, volatile int* host_flag, cudaStream_t st, int phases = 3);
 
 }  // namespace rcwa

@@ -51,7 +51,8 @@ class rcwa:
                  avoid_Pinv_instability=False,
                  max_Pinv_instability=0.005,
                  store_intermediates=None,
-                 gemm_digits=None):
+                 gemm_digits=None,
+                 pipeline=None):
         """Same parameters as the reference (torcwa/rcwa.py:9-35).  ``store_intermediates``
         (new): keep per-layer P, Q, eigenvectors, convolution matrices as attributes
         (default: only for unbatched sims, where the reference keeps them).
@@ -60,7 +61,14 @@ class rcwa:
         that many 8-bit digits per number (include/rcwa_b200.h: rcwa_zgemm_tc_batched).  Default: 5 for
         complex64 simulations (2e-10-grade products, far inside the API's single precision), 0 for complex128;
         the environment variable RCWA_B200_GEMM_DIGITS overrides the complex64 default.  The eigensolver always
-        runs in fp64 (SURVEY.md finding 5)."""
+        runs in fp64 (SURVEY.md finding 5).
+        ``pipeline`` (new): number of sub-batches a batched simulation is run as (default 1 = off; environment
+        RCWA_B200_PIPELINE; needs >= 8 points per sub-batch).  Sub-batches run on their own CUDA streams, driven by
+        their own host threads, staggered so that the Hessenberg reduction and the S-matrix stage of one sub-batch run
+        under the QR iteration of another.  Measured on B200 (profiles/r2_pipeline.md): a LOSS at every batch size --
+        the QR phase is bound by the fp64 tensor pipe (its K = 64 update GEMMs), not idle, so two concurrent
+        eigensolvers only share it -- hence off by default.  Results do not depend on it: every design point's
+        arithmetic is independent of the batch it is solved in (tests/test_gpu_parity.py checks bit identity)."""
         if dtype != torch.complex64 and dtype != torch.complex128:
             warnings.warn('Invalid simulation data type. Set as torch.complex64.', UserWarning)
             dtype = torch.complex64
@@ -121,6 +129,74 @@ class rcwa:
         self._layers = []          # internal: per layer [S11, S21] complex128 [B,n,n]
         self.eig_info = []         # per patterned layer: int32 [B] status of the eigensolver
         self._status = []          # (what, int32 [B] device tensor) of every factorisation / eigensolve: checked lazily
+        self._gate = None          # (wait flag, wait event, signal flag, signal event): stagger of pipelined sub-batches
+
+        # ---- pipelined sub-batches (children); the parent keeps the O(N) per-order state and delegates the dense stages
+        self._children = None
+        if pipeline is None:
+            pipeline = int(os.environ.get('RCWA_B200_PIPELINE', '1'))
+        k = int(pipeline) if (self._batched and self._B >= 16 and not self._store and self._device.type == 'cuda') else 1
+        if k > 1:
+            k = min(k, self._B // 8)
+            bounds = [self._B * i // k for i in range(k + 1)]
+            self._slices = [slice(bounds[i], bounds[i + 1]) for i in range(k)]
+            fr = torch.as_tensor(freq).reshape(-1)
+            with torch.cuda.device(self._device):
+                self._streams = [torch.cuda.Stream(device=self._device) for _ in range(k)]
+            self._children = [rcwa(fr[sl], order, L, dtype=dtype, device=self._device, stable_eig_grad=stable_eig_grad,
+                                   avoid_Pinv_instability=avoid_Pinv_instability, max_Pinv_instability=max_Pinv_instability,
+                                   store_intermediates=False, gemm_digits=self._digits, pipeline=1) for sl in self._slices]
+
+    # ------------------------------------------------------------------ pipelined sub-batches
+    def _part(self, v, sl):
+        """the slice of a per-point argument that belongs to one sub-batch (anything else is passed through)"""
+        # per-point scalars are [B], per-point material grids [B,nx,ny]; a 2-D tensor is always a shared grid
+        if isinstance(v, torch.Tensor) and v.dim() in (1, 3) and v.shape[0] == self._B and v.numel() > 1:
+            return v[sl]
+        return v
+
+    def _fanout(self, method, args=(), kwargs=None, gates=None):
+        """Run `method` of every sub-batch simulation on its own stream from its own host thread (the C ABI calls release
+        the GIL; rcwa_eig polls its convergence flag from the host, so each sub-batch needs its own thread to keep its
+        queue fed).  Joined -- on the host and on the caller's stream -- before returning."""
+        import threading
+        kwargs = kwargs or {}
+        cur = torch.cuda.current_stream(self._device)
+        start = torch.cuda.Event()
+        start.record(cur)
+        results, errors = [None] * len(self._children), []
+
+        def work(i):
+            child, sl = self._children[i], self._slices[i]
+            child._gate = gates[i] if gates else None
+            try:
+                with torch.cuda.device(self._device), torch.cuda.stream(self._streams[i]):
+                    self._streams[i].wait_event(start)
+                    results[i] = getattr(child, method)(*[self._part(a, sl) for a in args],
+                                                        **{k: self._part(v, sl) for k, v in kwargs.items()})
+            except BaseException as e:      # re-raised in the caller's thread
+                errors.append(e)
+            finally:
+                if child._gate is not None and child._gate[2] is not None:
+                    child._gate[2].set()    # never leave the next sub-batch waiting
+                child._gate = None
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(len(self._children))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for st in self._streams:
+            cur.wait_stream(st)
+        if errors:
+            raise errors[0]
+        return results
+
+    def _gather(self, parts):
+        """per-sub-batch public tensors -> one tensor on the caller's stream"""
+        cur = torch.cuda.current_stream(self._device)
+        for p in parts:
+            p.record_stream(cur)
+        return torch.cat(parts, dim=0)
 
     # ------------------------------------------------------------------ helpers
     def _b(self, v):
@@ -144,11 +220,15 @@ class rcwa:
         self.eps_in = torch.as_tensor(eps, dtype=self._dtype, device=self._device)
         self.mu_in = torch.as_tensor(mu, dtype=self._dtype, device=self._device)
         self.Sin = []
+        if self._children:
+            self._fanout('add_input_layer', kwargs=dict(eps=eps, mu=mu))
 
     def add_output_layer(self, eps=1., mu=1.):
         self.eps_out = torch.as_tensor(eps, dtype=self._dtype, device=self._device)
         self.mu_out = torch.as_tensor(mu, dtype=self._dtype, device=self._device)
         self.Sout = []
+        if self._children:
+            self._fanout('add_output_layer', kwargs=dict(eps=eps, mu=mu))
 
     def set_incident_angle(self, inc_ang, azi_ang, angle_layer='input'):
         self.inc_ang = torch.as_tensor(inc_ang, dtype=self._dtype, device=self._device)
@@ -161,6 +241,8 @@ class rcwa:
             warnings.warn('Invalid angle layer. Set as input layer.', UserWarning)
             self.angle_layer = 'input'
         self._kvectors()
+        if self._children:
+            self._fanout('set_incident_angle', args=(inc_ang, azi_ang, self.angle_layer))
 
     def _kvectors(self):
         """Per-order wavevectors and half-space S-matrices (rcwa.py:1124-1181), O(N)."""
@@ -244,6 +326,8 @@ class rcwa:
 
     def add_layer(self, thickness, eps=1., mu=1.):
         he, hm = self._is_homogeneous(eps), self._is_homogeneous(mu)
+        if self._children:
+            return self._add_layer_pipelined(thickness, eps, mu, patterned=not (he and hm))
         B, N = self._B, self.order_N
         kx, ky = self._kx, self._ky
         thick = (thickness.to(device=self._device, dtype=torch.float64) if isinstance(thickness, torch.Tensor)
@@ -304,7 +388,7 @@ class rcwa:
                 self._pinv_metrics(P, Q)
             A = _lib.zgemm(P, Q)
             del P                                  # free early: a batch chunk is sized by its peak footprint
-            lam, W, info = _lib.eig(A)
+            lam, W, info = self._eig(A)
             del A
             self.eig_info.append(info)
             self._status.append(('eigendecomposition (layer %d): QR iteration did not converge' % self.layer_N, info))
@@ -323,6 +407,43 @@ class rcwa:
             s11, s21 = self._pub(S11), self._pub(S21)
             self.layer_S11.append(s11); self.layer_S21.append(s21)
             self.layer_S12.append(s21); self.layer_S22.append(s11)      # single-layer symmetry
+
+    def _eig(self, A):
+        """rcwa_eig; as a pipelined sub-batch, wait for the previous sub-batch's Hessenberg phase and announce our own."""
+        gate = self._gate
+        if gate is None:
+            return _lib.eig(A)
+        wait_flag, wait_event, signal_flag, signal_event = gate
+        if wait_flag is not None:
+            wait_flag.wait()
+            torch.cuda.current_stream().wait_event(wait_event)
+
+        def announce():
+            if signal_flag is not None:
+                signal_event.record(torch.cuda.current_stream())
+                signal_flag.set()
+        return _lib.eig(A, after_reduction=announce)
+
+    def _add_layer_pipelined(self, thickness, eps, mu, patterned):
+        import threading
+        k = len(self._children)
+        diff = any(isinstance(v, torch.Tensor) and v.requires_grad for v in (eps, mu, thickness))
+        gates = None
+        if patterned and not diff:
+            flags = [threading.Event() for _ in range(k)]
+            events = [torch.cuda.Event() for _ in range(k)]
+            gates = [(flags[i - 1] if i > 0 else None, events[i - 1] if i > 0 else None,
+                      flags[i] if i < k - 1 else None, events[i] if i < k - 1 else None) for i in range(k)]
+        self._fanout('add_layer', args=(thickness,), kwargs=dict(eps=eps, mu=mu), gates=gates)
+        self._diff = self._diff or any(c._diff for c in self._children)
+        self.kz_norm.append(self._gather([c.kz_norm[-1] for c in self._children]))
+        if patterned and not diff:
+            self.eig_info.append(self._gather([c.eig_info[-1] for c in self._children]))
+        if self.avoid_Pinv_instability and patterned and not diff:
+            self.Pinv_instability.append(self._gather([c.Pinv_instability[-1] for c in self._children]))
+            self.Qinv_instability.append(self._gather([c.Qinv_instability[-1] for c in self._children]))
+        self.layer_N += 1
+        self.thickness.append(thickness)
 
     def _pinv_metrics(self, P, Q):
         """`avoid_Pinv_instability=True` (rcwa.py:1249-1262): the reference measures how badly P (and Q) invert,
@@ -361,6 +482,12 @@ class rcwa:
     # ------------------------------------------------------------------ cascade (rcwa.py:173-211)
     def solve_global_smatrix(self):
         B, n = self._B, 2 * self.order_N
+        if self._children:
+            self._fanout('solve_global_smatrix')
+            self._S = _CatList(self, '_S')
+            self.S = _CatList(self, 'S')
+            self.C = [[], []]
+            return
         if self._diff:
             return self._solve_global_smatrix_differentiable()
         if self.layer_N > 0:
@@ -521,6 +648,16 @@ class rcwa:
 
     def S_parameters(self, orders, *, direction='forward', port='transmission', polarization='xx',
                      ref_order=[0, 0], power_norm=True, evanscent=1e-3):
+        if self._children:
+            cur = torch.cuda.current_stream(self._device)
+            parts = []
+            for c, st in zip(self._children, self._streams):
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    parts.append(c.S_parameters(orders, direction=direction, port=port, polarization=polarization,
+                                                ref_order=ref_order, power_norm=power_norm, evanscent=evanscent))
+                cur.wait_stream(st)
+            return self._gather(parts)
         orders = torch.as_tensor(orders, dtype=torch.int64, device=self._device).reshape([-1, 2])
         if direction in ['f', 'forward']:
             direction = 'forward'
@@ -607,6 +744,31 @@ class rcwa:
         # an evanescent reference order gives zeros (rcwa.py:447-449), here per design point
         out = torch.where(r_ev, torch.zeros_like(out), out)
         return self._pub(out)
+
+
+class _CatList:
+    """The four global S-matrix blocks of a pipelined simulation: concatenated from the sub-batches on first access
+    (a [B,n,n] copy per block -- the readout, S_parameters, never needs it)."""
+
+    def __init__(self, sim, attr):
+        self._sim, self._attr, self._val = weakref.ref(sim), attr, None
+
+    def _get(self):
+        if self._val is None:
+            sim = self._sim()
+            for st in sim._streams:
+                torch.cuda.current_stream(sim._device).wait_stream(st)
+            self._val = [torch.cat([getattr(c, self._attr)[k] for c in sim._children], dim=0) for k in range(4)]
+        return self._val
+
+    def __len__(self):
+        return 4
+
+    def __getitem__(self, k):
+        return self._get()[k]
+
+    def __iter__(self):
+        return iter(self._get())
 
 
 class _LazyDense:
