@@ -8,10 +8,17 @@
  * Conventions
  *   - every matrix pointer is a DEVICE pointer to row-major, interleaved (re,im) fp64 ("c128")
  *     data, 16-byte aligned; batched tensors are [nb, rows, cols] contiguous unless a stride is given;
- *   - the caller allocates everything (outputs, workspaces, info); the library keeps no state,
- *     never allocates or frees device memory, never synchronises; every call only enqueues work
- *     on `stream` (a cudaStream_t passed as void*), so sequences are CUDA-graph capturable
- *     (rcwa_eig polls a device flag through pinned host memory supplied by the caller -- see there);
+ *   - the caller allocates everything (outputs, workspaces, info); the library never allocates or frees device
+ *     memory.  Every entry point EXCEPT rcwa_eig / rcwa_eig_phases only enqueues work on `stream` (a cudaStream_t
+ *     passed as void*), never synchronises, and is CUDA-graph capturable;
+ *   - rcwa_eig is the exception, and says so: its QR phase forks onto internal streams (created once per host thread
+ *     and device on first use, reused by later calls, joined back into `stream` before it returns -- also on error
+ *     paths) and, to stop as soon as every matrix has converged, the HOST polls a counter through the caller's pinned
+ *     `host_flag` with cudaEventSynchronize.  It therefore blocks the calling host thread for the duration of the QR
+ *     phase and cannot be captured into a CUDA graph.  It is re-entrant: concurrent calls from different host threads
+ *     (on their own streams and workspaces) share nothing (tests/test_gpu_eig.py);
+ *   - process-wide state: the tuning table behind rcwa_set_tuning (defaults = the measured best; results do not
+ *     depend on it) and per-device "attribute already set" flags of the kernels.  Nothing else;
  *   - return value: 0 ok; -k = argument k invalid (LAPACK style); <= -1000 = CUDA runtime error
  *     (-1000 - cudaError_t);
  *   - numerical status is reported per batch entry in device int32 info[nb]

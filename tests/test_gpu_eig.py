@@ -161,3 +161,42 @@ def test_eig_autograd_gauge_invariant_loss_matches_native():
         assert Ar.grad.dtype == torch.float64 and not torch.is_complex(Ar.grad)
     finally:
         torcwa_b200.Eig.broadening_parameter = old
+
+
+def test_eig_is_reentrant_across_host_threads_and_bitwise_reproducible():
+    """Boundary contract (include/rcwa_b200.h): rcwa_eig may run concurrently from different host threads on their own
+    streams and workspaces (its internal streams are per thread), twice in a row from the same thread (the cached streams
+    are reused), and gives bit-identical results however the calls interleave.  rcwa_eig_phases(1) + (2) == rcwa_eig."""
+    import threading
+    from torcwa_b200 import _lib
+    n, nb = 150, 4
+    A0, A1 = rnd(nb, n, n, seed=7), rnd(nb, n, n, seed=8)
+    ref0 = _lib.eig(A0.clone())
+    ref1 = _lib.eig(A1.clone())
+    again = _lib.eig(A0.clone())                       # same thread, cached internal streams reused
+    torch.cuda.synchronize()
+    assert torch.equal(again[0], ref0[0]) and torch.equal(again[1], ref0[1])
+    out, errs = {}, []
+
+    def work(k, A):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(3):
+                    out[k] = _lib.eig(A.clone())
+            st.synchronize()
+        except BaseException as e:
+            errs.append(e)
+    ts = [threading.Thread(target=work, args=(0, A0)), threading.Thread(target=work, args=(1, A1))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for k, ref in ((0, ref0), (1, ref1)):
+        assert int(out[k][2].abs().max()) == 0
+        assert torch.equal(out[k][0], ref[0]) and torch.equal(out[k][1], ref[1])
+    hooks = []
+    two = _lib.eig(A0.clone(), after_reduction=lambda: hooks.append(1))
+    torch.cuda.synchronize()
+    assert hooks == [1] and torch.equal(two[0], ref0[0]) and torch.equal(two[1], ref0[1])

@@ -1237,6 +1237,37 @@ EigWs carve(char* base, int n, int nb) {
 
 }  // namespace
 
+// Streams / events of the QR phase: one set per host thread and device, created on first use, reused, never destroyed
+// (a few driver objects per thread; they die with the process).  Thread-local => re-entrant across host threads.
+struct EigStreams {
+    bool ready;
+    cudaStream_t sa[4], sb[4];
+    cudaEvent_t ev_fork, ev_join[4], ev_pass[4][2], ev_side[4][2], ev[4][2];
+};
+EigStreams* eig_streams() {
+    static thread_local EigStreams cache[16] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    EigStreams& r = cache[dev];
+    if (r.ready) return &r;
+    int prio_lo = 0, prio_hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) return nullptr;
+    bool ok = cudaEventCreateWithFlags(&r.ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int g = 0; g < 4 && ok; ++g) {
+        ok = ok && cudaStreamCreateWithPriority(&r.sa[g], cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&r.sb[g], cudaStreamNonBlocking, prio_lo) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&r.ev_join[g], cudaEventDisableTiming) == cudaSuccess;
+        for (int q = 0; q < 2 && ok; ++q) {
+            ok = ok && cudaEventCreateWithFlags(&r.ev_pass[g][q], cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&r.ev_side[g][q], cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&r.ev[g][q], cudaEventDisableTiming) == cudaSuccess;
+        }
+    }
+    if (!ok) return nullptr;
+    r.ready = true;
+    return &r;
+}
+
 namespace rcwa {
 
 size_t eig_workspace_bytes(int n, int nb) { return carve(nullptr, n, nb).total; }
@@ -1364,26 +1395,35 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
     int G = gemm_get_tuning(9) > 0 ? gemm_get_tuning(9) : 2;
     if (G > 4) G = 4;
     while (G > 1 && nb < 8 * G) --G;
-    int prio_lo = 0, prio_hi = 0;
-    EK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    cudaStream_t user_st = st, sa[4] = {nullptr, nullptr, nullptr, nullptr}, sb[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[4], ev_pass[4][2], ev_side[4][2], ev[4][2];
+    // Internal streams and events are created ONCE per host thread and device and reused by later calls (thread-local
+    // cache below): no per-call cudaStreamCreate / Destroy, nothing shared between host threads.  Whatever happens below,
+    // the Join guard makes the caller's stream wait for everything that was forked before this function returns.
+    EigStreams* res = eig_streams();
+    if (!res) return cudaErrorMemoryAllocation;
+    cudaStream_t user_st = st;
+    cudaStream_t* sa = res->sa; cudaStream_t* sb = res->sb;
+    cudaEvent_t ev_fork = res->ev_fork;
+    cudaEvent_t (*ev_pass)[2] = res->ev_pass; cudaEvent_t (*ev_side)[2] = res->ev_side; cudaEvent_t (*ev)[2] = res->ev;
     int gb0[5];
     for (int g = 0; g <= G; ++g) gb0[g] = (int)((long long)nb * g / G);
-    EK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     EK(cudaEventRecord(ev_fork, user_st));
     int* hf = const_cast<int*>(host_flag);
-    for (int g = 0; g < G; ++g) {
-        EK(cudaStreamCreateWithPriority(&sa[g], cudaStreamNonBlocking, prio_hi));
-        EK(cudaStreamCreateWithPriority(&sb[g], cudaStreamNonBlocking, prio_lo));
-        EK(cudaStreamWaitEvent(sa[g], ev_fork, 0));
-        EK(cudaEventCreateWithFlags(&ev_join[g], cudaEventDisableTiming));
-        for (int q = 0; q < 2; ++q) {
-            EK(cudaEventCreateWithFlags(&ev_pass[g][q], cudaEventDisableTiming));
-            EK(cudaEventCreateWithFlags(&ev_side[g][q], cudaEventDisableTiming));
-            EK(cudaEventCreateWithFlags(&ev[g][q], cudaEventDisableTiming));
-            if (hf) hf[g * 2 + q] = gb0[g + 1] - gb0[g];
+    struct Join {
+        EigStreams* r; cudaStream_t user; int G; bool side_used[4][2];
+        void run() {
+            for (int g = 0; g < G; ++g) {
+                for (int q = 0; q < 2; ++q) if (side_used[g][q]) cudaStreamWaitEvent(r->sa[g], r->ev_side[g][q], 0);
+                cudaEventRecord(r->ev_join[g], r->sa[g]);
+                cudaStreamWaitEvent(user, r->ev_join[g], 0);
+            }
+            G = 0;
         }
+        ~Join() { run(); }      // also on every early error return: never leave forked work un-joined behind the caller's stream
+    } join_guard = {res, user_st, G, {{false, false}, {false, false}, {false, false}, {false, false}}};
+    for (int g = 0; g < G; ++g) {
+        EK(cudaStreamWaitEvent(sa[g], ev_fork, 0));
+        for (int q = 0; q < 2; ++q)
+            if (hf) hf[g * 2 + q] = gb0[g + 1] - gb0[g];
     }
     long long group = 0;
     bool fin[4] = {false, false, false, false};
@@ -1412,6 +1452,7 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
             EK(cudaStreamWaitEvent(ss, ev_pass[g][buf], 0));
             EK(zgemm_grouped(cfg_cz_b, OP_N, OP_N, pcz, 2 * nbg, max_tiles_cz, one, zero, ss));
             EK(cudaEventRecord(ev_side[g][buf], ss));
+            join_guard.side_used[g][buf] = true;
         }
         if (hf && (it % poll) == poll - 1) {
             const int slot = (int)(group & 1);
@@ -1430,19 +1471,7 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
     }
     // join all internal streams back into the caller's stream before anything reads H or Z
     st = user_st;
-    for (int g = 0; g < G; ++g) {
-        EK(cudaStreamWaitEvent(sa[g], ev_side[g][0], 0));
-        EK(cudaStreamWaitEvent(sa[g], ev_side[g][1], 0));
-        EK(cudaEventRecord(ev_join[g], sa[g]));
-        EK(cudaStreamWaitEvent(st, ev_join[g], 0));
-    }
-    cudaEventDestroy(ev_fork);
-    for (int g = 0; g < G; ++g) {
-        cudaEventDestroy(ev_join[g]);
-        for (int q = 0; q < 2; ++q) { cudaEventDestroy(ev_pass[g][q]); cudaEventDestroy(ev_side[g][q]); cudaEventDestroy(ev[g][q]); }
-        cudaStreamDestroy(sa[g]);
-        cudaStreamDestroy(sb[g]);
-    }
+    join_guard.run();
     qr_finish_kernel<<<(nb + 127) / 128, 128, 0, st>>>(ws.states, nb, info);
 
     // ---------------- phase 3: Schur form T = Z^H A0 Z (upper triangle; the strictly lower part is round-off
