@@ -88,6 +88,9 @@ int rcwa_zgemm_tc_batched(int slices, int opa, int opb, int M, int N, int K, dou
 int rcwa_tc_split(const void* X, int ld, long long stride, int rows_contiguous, int R, int Kc, int slices, int conj,
                   void* planes, int* ex, int nb, void* stream);
 int rcwa_tc_schedule(int slices, int levels, unsigned* ops, int* meta, unsigned* loads, unsigned* mmas);
+/* (host only) the issue-table entry (16 words, layout in csrc/kernels.h: tc_issue_entry) the kernel's MMA issuer reads for
+ * step `step` of level group `group` when the iteration's first load sits in ring slot `ring_pos`. */
+int rcwa_tc_issue_entry(int slices, int levels, int group, int ring_pos, int step, unsigned* entry, int* nsteps);
 
 /* Tuning / profiling entry points (not needed by a binding; used by bench.py and tools/).
  * rcwa_zgemm_batched_cfg: the same product on an explicit kernel configuration:

@@ -200,3 +200,27 @@ def test_eig_is_reentrant_across_host_threads_and_bitwise_reproducible():
     two = _lib.eig(A0.clone(), after_reduction=lambda: hooks.append(1))
     torch.cuda.synchronize()
     assert hooks == [1] and torch.equal(two[0], ref0[0]) and torch.equal(two[1], ref0[1])
+
+
+@pytest.mark.parametrize("n", [1054, 1922])
+def test_eig_backward_at_path_size(n):
+    """Eig.backward at the sizes of the path (n = 1054: Example6's order [15,8]; n = 1922: order 15x15): rcwa_eig_backward on
+    our own eigen-decomposition against the reference's formula (torch_eig.py:25-40) evaluated with torch fp64 ops on the GPU:
+    grad = X^-H (diag(g_lambda) + conj(F) o (X^H g_X)) X^H,  F_ij = conj(s) / (|s|^2 + delta), s = lambda_j - lambda_i."""
+    from torcwa_b200 import _lib
+    A = rnd(1, n, n, seed=5) / np.sqrt(n) + torch.diag(torch.linspace(-3.0, 1.0, n, dtype=torch.float64)).to(dev())[None]
+    w, V, info = _lib.eig(A.clone())
+    assert int(info.abs().max()) == 0
+    gw, gV = rnd(1, n, seed=6), rnd(1, n, n, seed=7) / np.sqrt(n)
+    delta = 1e-10
+    grad, info = _lib.eig_backward(w, V, gw, gV, delta)
+    assert int(info.abs().max()) == 0
+    s = w[0][None, :] - w[0][:, None]
+    F = s.conj() / (s.abs() ** 2 + delta)
+    F.fill_diagonal_(0.0)
+    Xh = V[0].conj().T
+    inner = torch.diag(gw[0]) + F.conj() * (Xh @ gV[0])
+    ref = torch.linalg.solve(Xh, inner @ Xh)
+    err = rel(grad[0], ref)
+    print("n = %d: eig backward vs torch fp64 formula %.2e" % (n, err))
+    assert err < 1e-9

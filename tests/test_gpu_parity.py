@@ -15,6 +15,9 @@ pytestmark = pytest.mark.gpu
 from oracle import cases as C  # noqa: E402
 
 SMALL = ["ex1_o3", "ex1_o5", "stack_o3", "stack_o4x2", "fresnel_o2", "square_o4"]
+# BASELINE configs at their real sizes: corners / C4v-symmetric centre of config 4's (Wx, Wy, lambda) sweep at order 15, and
+# config 3's 8-layer stack at order 21 (complex128 only)
+SWEEP = ["sweep_o15_a", "sweep_o15_b", "sweep_o15_c"]
 
 
 def b200_factory(freq, order, L, dtype):
@@ -36,7 +39,7 @@ def relfro(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
-@pytest.mark.parametrize("name", SMALL)
+@pytest.mark.parametrize("name", SMALL + SWEEP + ["stack_o21"])
 def test_parity_c128(name, golden_dir):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     sim = run(name, torch.complex128)
@@ -66,7 +69,7 @@ def test_parity_c128(name, golden_dir):
             assert np.abs(mine - g["kz2_sorted"][l]).max() <= 1e-9 * np.abs(mine).max()
 
 
-@pytest.mark.parametrize("name", SMALL + ["ex1_o15"])
+@pytest.mark.parametrize("name", SMALL + ["ex1_o15"] + SWEEP)
 def test_parity_c64_api(name, golden_dir):
     """complex64 API (fp64 eigensolver, S-matrix stage on the tcgen05 5-digit GEMM where the matrices are large enough
     -- at order 15 every dense product and triangular-solve update of the stage) against the reference's complex128 run."""
@@ -98,6 +101,32 @@ def test_order15_parity_vs_digits_of_the_tcgen05_engine(digits, gate, golden_dir
     err = np.abs(sp - g["sparams_c128"]).max() / np.abs(g["sparams_c128"]).max()
     print("order 15, %d digits: S-parameter max err / max|S| = %.2e" % (digits, err))
     assert err <= gate
+
+
+def test_pinv_metrics_and_dispersion_table_on_the_gpu(tmp_path):
+    """Scope rows f3 / f2 on the device: avoid_Pinv_instability=True reports one round-off-level metric per patterned layer
+    without changing the result (rcwa.py:1249-1262), and NKTable evaluates a sweep of wavelengths on the GPU exactly as
+    scipy's cubic interpolant does on the host (example/Materials.py:5-50)."""
+    import torcwa_b200
+    from scipy.interpolate import interp1d
+    from torcwa_b200.materials import NKTable
+    case = C.CASES["ex1_o5"]
+    mk = lambda **kw: (lambda freq, order, L, dtype: torcwa_b200.rcwa(freq=freq, order=order, L=L, dtype=dtype, device=torch.device("cuda:0"), **kw))
+    a = C.run_case(mk(avoid_Pinv_instability=True), case, torch.complex128)
+    b = C.run_case(mk(), case, torch.complex128)
+    assert len(a.Pinv_instability) == 1 and len(a.Qinv_instability) == 1
+    assert 0.0 <= float(a.Pinv_instability[0]) < 1e-8 and 0.0 <= float(a.Qinv_instability[0]) < 1e-8
+    assert b.Pinv_instability is None
+    assert np.abs(C.probe(a) - C.probe(b)).max() == 0.0
+    rng = np.random.default_rng(5)
+    lam = np.sort(rng.uniform(300.0, 900.0, 60))
+    n, k = 3.5 + 0.8 * np.sin(lam / 90.0), 0.3 * np.exp(-(lam - 300.0) / 150.0)
+    tab = NKTable(lam, n, k, device="cuda:0")
+    q = torch.linspace(float(lam[0]), float(lam[-1]), 512, dtype=torch.float64, device="cuda:0")
+    got = tab.apply(q)
+    assert got.is_cuda
+    ref = interp1d(lam, n, kind="cubic")(q.cpu().numpy()) + 1j * interp1d(lam, k, kind="cubic")(q.cpu().numpy())
+    assert np.abs(got.cpu().numpy() - ref).max() <= 1e-12
 
 
 def test_batched_equals_unbatched():

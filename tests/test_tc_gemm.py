@@ -39,6 +39,44 @@ def test_schedule_covers_all_pairs_and_ring_is_deadlock_free(s, nl):
         assert sorted(firsts) == list(range(g["nl"]))
 
 
+@pytest.mark.parametrize("s", [2, 4, 5, 7, 8])
+def test_issue_table_entries_cover_every_pair_once(s):
+    """The issue table the kernel's MMA issuer reads (tc_issue_entry, shared host/device code): for every level group and
+    every ring position, the MMA groups of a step -- single planes (N = 128) and doubles (two digit planes in adjacent ring
+    slots, one N = 256 MMA over two adjacent accumulator levels) -- cover exactly the (A digit, B digit) pairs of the
+    schedule, each into the accumulator column of its level."""
+    from torcwa_b200 import _lib
+    RING = 12
+    ops, groups = _lib.tc_schedule(s, 4)
+    n_double = 0
+    for gi, g in enumerate(groups):
+        nl = g["nl"]
+        for bs in range(RING):
+            entries = _lib.tc_issue_entries(s, gi, bs)
+            # expected pairs per step from the compact MMA table: consecutive ops sharing their A load
+            steps, cur = [], None
+            for w in g["mmas"]:
+                ia, ib, lvl, first = w & 31, (w >> 5) & 31, (w >> 10) & 3, (w >> 12) & 1
+                if cur is None or cur[0] != ia:
+                    cur = (ia, [])
+                    steps.append(cur)
+                cur[1].append((ib, lvl, first))
+            assert len(entries) == len(steps)
+            for e, (ia, pairs) in zip(entries, steps):
+                assert e["a_slot"] == (bs + ia) % RING
+                got = []
+                for grp in e["groups"]:
+                    lvl = nl - 1 - grp["col"] // 128
+                    got.append((grp["b_slot"], lvl, grp["first"]))
+                    if grp["double"]:
+                        n_double += 1
+                        assert grp["b_slot"] + 1 < RING and lvl >= 1
+                        got.append((grp["b_slot"] + 1, lvl - 1, grp["first"]))       # second plane: next slot, next column
+                want = [((bs + ib) % RING, lvl, first) for (ib, lvl, first) in pairs]
+                assert got == want
+    assert n_double > 0 or s < 3
+
+
 @pytest.mark.parametrize("s,tol", [(4, 2e-6), (5, 1e-8), (6, 3e-11), (7, 2e-13), (8, 2e-15)])
 def test_model_accuracy(s, tol):
     A = _rnd((37, 150), 1, spread=1.0)

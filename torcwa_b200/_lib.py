@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("RCWA_B200_LIB", "librcwa_b200.so"
 
 EXPORTS = [
     "rcwa_b200_abi_version", "rcwa_gemm_scratch_bytes", "rcwa_convmat_workspace_bytes", "rcwa_convmat",
-    "rcwa_zgemm_batched", "rcwa_zgemm_batched_cfg", "rcwa_zgemm_tc_workspace_bytes", "rcwa_zgemm_tc_batched", "rcwa_tc_split", "rcwa_tc_schedule", "rcwa_set_tuning", "rcwa_get_tuning", "rcwa_lu_tinv_bytes", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
+    "rcwa_zgemm_batched", "rcwa_zgemm_batched_cfg", "rcwa_zgemm_tc_workspace_bytes", "rcwa_zgemm_tc_batched", "rcwa_tc_split", "rcwa_tc_schedule", "rcwa_tc_issue_entry", "rcwa_set_tuning", "rcwa_get_tuning", "rcwa_lu_tinv_bytes", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
     "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_eig_phases", "rcwa_eig_stats", "rcwa_eig_profile", "rcwa_hessenberg", "rcwa_hessenberg_matvec_probe", "rcwa_hessenberg_panel_width", "rcwa_kz_branch", "rcwa_eig_backward_workspace_bytes", "rcwa_eig_backward", "rcwa_layer_smatrix_workspace_bytes",
     "rcwa_layer_smatrix", "rcwa_redheffer_workspace_bytes", "rcwa_redheffer", "rcwa_redheffer_bdleft", "rcwa_blockdiag_dense",
 ]
@@ -31,6 +31,7 @@ _SIGS = {
     "rcwa_zgemm_tc_batched": (_i, [_i, _i, _i, _i, _i, _i, _d, _vp, _i, _ll, _vp, _i, _ll, _d, _d, _vp, _i, _ll, _i, _vp, _sz, _vp]),
     "rcwa_tc_split": (_i, [_vp, _i, _ll, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "rcwa_tc_schedule": (_i, [_i, _i, _vp, _vp, _vp, _vp]),
+    "rcwa_tc_issue_entry": (_i, [_i, _i, _i, _i, _i, _vp, _vp]),
     "rcwa_set_tuning": (_i, [_i, _i]),
     "rcwa_get_tuning": (_i, [_i]),
     "rcwa_lu_tinv_bytes": (_sz, [_i, _i]),
@@ -242,6 +243,26 @@ def tc_schedule(slices, levels=4):
         d["mmas"] = list(mmas)[32 * g:32 * g + d["nmma"]]
         groups.append(d)
     return list(ops)[:meta[1]], groups
+
+
+def tc_issue_entries(slices, group, ring_pos, levels=4):
+    """Host-only: the decoded issue-table entries of every step of one level group at one ring position."""
+    lib = load()
+    out = []
+    ns = ctypes.c_int(0)
+    e = (ctypes.c_uint * 16)()
+    step = 0
+    while True:
+        rc = lib.rcwa_tc_issue_entry(int(slices), int(levels), int(group), int(ring_pos), step, e, ctypes.byref(ns))
+        if rc == -5:
+            break
+        _check(rc, "rcwa_tc_issue_entry")
+        ng = e[1] & 15
+        out.append(dict(a_slot=e[0], nacq=(e[1] >> 4) & 15, rel_b=((e[1] >> 17) & 255) if (e[1] >> 16) & 1 else None,
+                        groups=[dict(b_slot=e[2 + 2 * j], col=e[3 + 2 * j] & 511, first=(e[3 + 2 * j] >> 9) & 1, double=(e[3 + 2 * j] >> 10) & 1)
+                                for j in range(ng)]))
+        step += 1
+    return out
 
 
 @_on_device

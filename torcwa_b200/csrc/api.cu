@@ -122,6 +122,22 @@ int rcwa_tc_schedule(int slices, int levels, unsigned* ops, int* meta, unsigned*
     return 0;
 }
 
+int rcwa_tc_issue_entry(int slices, int levels, int group, int ring_pos, int step, unsigned* entry, int* nsteps) {
+    if (slices < 2 || slices > TC_MAXS) return -1;
+    if (levels < 1 || levels > 4) return -2;
+    if (!entry) return -6;
+    TcSchedule sch;
+    tc_build_schedule(slices, levels, &sch);
+    TcTables tab;
+    tc_compact_schedule(&sch, &tab);
+    if (group < 0 || group >= tab.ngroups) return -3;
+    if (ring_pos < 0 || ring_pos >= TC_RING) return -4;
+    if (nsteps) *nsteps = tab.nsteps[group];
+    if (step < 0 || step >= tab.nsteps[group]) return -5;
+    tc_issue_entry(tab, group, ring_pos, step, entry);
+    return 0;
+}
+
 int rcwa_set_tuning(int key, int value) {
     if (key < 0 || key > 15) return -1;
     gemm_set_tuning(key, value);

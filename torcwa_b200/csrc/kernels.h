@@ -53,6 +53,40 @@ struct TcSchedule { int s, ngroups, nops, pad; TcGroup g[TC_MAXS]; unsigned ops[
 struct TcTables { int s, ngroups; int d0[TC_MAXS], nl[TC_MAXS], nloads[TC_MAXS], nmma[TC_MAXS], nsteps[TC_MAXS];
                   unsigned loads[TC_MAXS * TC_MAXLOADS]; unsigned mmas[TC_MAXS * TC_MAXMMAS]; unsigned steps[TC_MAXS * TC_MAXS * 2]; };
 void tc_compact_schedule(const TcSchedule* sch, TcTables* tab);
+#define TC_RING 12           // ring slots of 16 KB (one digit plane tile: 128 rows x 128 bytes of K)
+// Issue-table entry of one step for a given ring position `bs` of the iteration's first load (16 words, what the issuer
+// thread reads): [0] ring slot of the A plane, [1] MMA groups | loads to acquire << 4 | A slot << 8 | (B released ? 1 : 0) << 16
+// | its slot << 17; per MMA group j (<= 4): [2+2j] ring slot of its (first) B plane, [3+2j] accumulator column | first << 9 |
+// double << 10.  A "double" multiplies the A plane with TWO B planes that sit in adjacent ring slots (digits q and q-1)
+// in one N = 256 MMA: the accumulator columns of level l and l-1 are adjacent in TMEM (level l of a group of nl levels
+// lives at column (nl-1-l)*128).  Host and device share this function (tests/test_tc_gemm.py checks it on the CPU).
+inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+void tc_issue_entry(const TcTables& t, int g, int bs, int st, unsigned* e) {
+    const unsigned w0 = t.steps[(g * TC_MAXS + st) * 2], w1 = t.steps[(g * TC_MAXS + st) * 2 + 1];
+    const unsigned sa = (bs + (w0 & 31u)) % TC_RING, np = (w0 >> 5) & 7u, relb = (w0 >> 12) & 31u;
+    const unsigned nl = (unsigned)t.nl[g];
+    unsigned ng = 0;
+    for (unsigned j = 0; j < 8; ++j) e[2 + j] = 0;
+    for (unsigned j = 0; j < np;) {
+        const unsigned pj = (w1 >> (8 * j)) & 255u;
+        const unsigned sb = (bs + (pj & 31u)) % TC_RING, lvl = (pj >> 5) & 3u, first = (pj >> 7) & 1u;
+        unsigned dbl = 0;
+        if (j + 1 < np) {
+            const unsigned pk = (w1 >> (8 * (j + 1))) & 255u;
+            const unsigned sb2 = (bs + (pk & 31u)) % TC_RING, lvl2 = (pk >> 5) & 3u, first2 = (pk >> 7) & 1u;
+            if (sb + 1 < TC_RING && sb2 == sb + 1 && lvl >= 1 && lvl2 == lvl - 1 && first2 == first) dbl = 1;
+        }
+        e[2 + 2 * ng] = sb;
+        e[3 + 2 * ng] = ((nl - 1 - lvl) * 128u) | (first << 9) | (dbl << 10);
+        ++ng;
+        j += 1 + dbl;
+    }
+    e[0] = sa;
+    e[1] = ng | (((w0 >> 8) & 15u) << 4) | (sa << 8) | (relb ? (1u << 16) | (((bs + relb - 1u) % TC_RING) << 17) : 0u);
+}
 void tc_build_schedule(int s, int nl, TcSchedule* sch);
 size_t tc_workspace_bytes(int M, int N, int K, int nb, int s);      // split storage for the whole batch
 size_t tc_workspace_min_bytes(int M, int N, int K, int s);          // ... for one matrix (the routine then runs in chunks)

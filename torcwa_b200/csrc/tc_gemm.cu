@@ -39,11 +39,12 @@ void tc_build_schedule(int s, int nl, TcSchedule* sch) {
         int loaded_b[TC_MAXS]; bool first[4] = {true, true, true, true};
         for (int q = 0; q < TC_MAXS; ++q) loaded_b[q] = -1;
         const int pmax = d1;                                   // d1 <= s - 1
+        // every B plane of the group first, most significant digit last (q = d1 .. 0), into CONSECUTIVE ring slots: planes
+        // q and q-1 then sit in adjacent slots, and one N = 256 MMA can multiply an A plane with both (see tc_issue_entry)
+        for (int q = d1; q >= 0; --q) { sch->ops[sch->nops++] = TC_OP_LOAD_B | (q << 2); loaded_b[q] = g.nloads++; }
         for (int p = 0; p <= pmax; ++p) {
             const int qlo = (d0 - p > 0) ? d0 - p : 0, qhi = (d1 - p < s - 1) ? d1 - p : s - 1;
             if (qlo > qhi) continue;
-            for (int q = qhi; q >= qlo; --q)
-                if (loaded_b[q] < 0) { sch->ops[sch->nops++] = TC_OP_LOAD_B | (q << 2); loaded_b[q] = g.nloads++; }
             sch->ops[sch->nops++] = TC_OP_LOAD_A | (p << 2);
             const int ia = g.nloads++;
             for (int q = qhi; q >= qlo; --q) {
@@ -113,7 +114,6 @@ using namespace rcwa;
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 128;          // tile rows / columns, K bytes per ring slot
 constexpr int TC_SLOT = TC_BM * TC_BK;                          // 16 KB
-constexpr int TC_RING = 12;
 constexpr int TC_THREADS = 384;                                  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
 constexpr int TC_TAB_GROUPS = 2;                                 // level groups the kernel supports (s <= 8 at 4 levels per group)
 constexpr int TC_TAB_BYTES = TC_TAB_GROUPS * TC_RING * TC_MAXS * 64;
@@ -204,26 +204,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = sch.s;
     // Issue table: for every (level group, ring position of the iteration's first load, step) the ready-made operands of
-    // the issue, 64 bytes: [0] A descriptor low word, [1] pairs | loads to acquire << 4 | empty-barrier offset of A << 8 |
-    // (B released ? 1 : 0) << 16 | its barrier offset << 17, then per pair j: [2+2j] B descriptor low word,
-    // [3+2j] accumulator column | first << 9 -- the issuer's per-step work is three 16-byte shared loads, the waits and
-    // the tcgen05 instructions themselves.
+    // the issue (tc_issue_entry, kernels.h, with ring slots turned into descriptor low words / barrier offsets here):
+    // the issuer's per-step work is three 16-byte shared loads, the waits and the tcgen05 instructions themselves.
     const uint32_t tab = bars + 512;
     {
         const uint32_t lo0 = (sbase & 0x3FFFFu) >> 4;
         uint32_t* T = reinterpret_cast<uint32_t*>(smem_raw + (tab - smem_u32(smem_raw)));
         for (int idx = threadIdx.x; idx < sch.ngroups * TC_RING * TC_MAXS; idx += blockDim.x) {
             const int g = idx / (TC_RING * TC_MAXS), bs = (idx / TC_MAXS) % TC_RING, st = idx % TC_MAXS;
-            const uint32_t w0 = sch.steps[(g * TC_MAXS + st) * 2], w1 = sch.steps[(g * TC_MAXS + st) * 2 + 1];
-            const uint32_t sa = (bs + (w0 & 31u)) % TC_RING, np = (w0 >> 5) & 7u, relb = (w0 >> 12) & 31u;
-            uint32_t* e = T + (size_t)idx * 16;
-            e[0] = lo0 + sa * (TC_SLOT >> 4);
-            e[1] = np | (((w0 >> 8) & 15u) << 4) | ((8u * sa) << 8) | (relb ? (1u << 16) | ((8u * ((bs + relb - 1u) % TC_RING)) << 17) : 0u);
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t pj = (w1 >> (8 * j)) & 255u;
-                e[2 + 2 * j] = lo0 + ((bs + (pj & 31u)) % TC_RING) * (TC_SLOT >> 4);
-                e[3 + 2 * j] = (((pj >> 5) & 3u) * TC_BN) | (((pj >> 7) & 1u) << 9);
-            }
+            unsigned e[16];
+            tc_issue_entry(sch, g, bs, st, e);
+            uint32_t* o = T + (size_t)idx * 16;
+            o[0] = lo0 + e[0] * (TC_SLOT >> 4);
+            o[1] = (e[1] & 0xFFu) | (((e[1] >> 8) & 255u) * 8u) << 8 | (e[1] & (1u << 16)) | (((e[1] >> 17) & 255u) * 8u) << 17;
+            for (int j = 0; j < 4; ++j) { o[2 + 2 * j] = lo0 + e[2 + 2 * j] * (TC_SLOT >> 4); o[3 + 2 * j] = e[3 + 2 * j]; }
         }
     }
     if (threadIdx.x == 0) {
@@ -287,6 +281,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int n0 = (rem % prm.nt) * TC_BN;
             int ncols = prm.N - n0; if (ncols > TC_BN) ncols = TC_BN;
             const uint32_t idesc = tc_idesc((ncols + 15) & ~15);
+            const uint32_t idesc2 = tc_idesc(TC_BN + ((ncols + 15) & ~15));   // two planes at once: 128 rows of the first + the live rows of the second
             for (int t = 0; t < 3; ++t) {
                 for (int g = 0; g < sch.ngroups; ++g, ++grp) {
                     mbar_wait(bar_tempty, (grp & 1u) ^ 1u);          // the epilogue has drained the previous group's accumulators
@@ -307,12 +302,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             }
                             tc_fence_after();
                             if (elect_one()) {
-                                const uint32_t np = e0.y & 15u;
+                                const uint32_t ng = e0.y & 15u;
                                 const uint64_t da = ((uint64_t)desc_hi << 32) | e0.x;
-                                tc_issue_pair(tmem_base + (e0.w & 511u), da, ((uint64_t)desc_hi << 32) | e0.z, idesc, (e0.w & fresh_mask) ? 0u : 1u, nk);
-                                if (np > 1) tc_issue_pair(tmem_base + (e1.y & 511u), da, ((uint64_t)desc_hi << 32) | e1.x, idesc, (e1.y & fresh_mask) ? 0u : 1u, nk);
-                                if (np > 2) tc_issue_pair(tmem_base + (e1.w & 511u), da, ((uint64_t)desc_hi << 32) | e1.z, idesc, (e1.w & fresh_mask) ? 0u : 1u, nk);
-                                if (np > 3) tc_issue_pair(tmem_base + (e2.y & 511u), da, ((uint64_t)desc_hi << 32) | e2.x, idesc, (e2.y & fresh_mask) ? 0u : 1u, nk);
+                                tc_issue_pair(tmem_base + (e0.w & 511u), da, ((uint64_t)desc_hi << 32) | e0.z, (e0.w & 1024u) ? idesc2 : idesc, (e0.w & fresh_mask) ? 0u : 1u, nk);
+                                if (ng > 1) tc_issue_pair(tmem_base + (e1.y & 511u), da, ((uint64_t)desc_hi << 32) | e1.x, (e1.y & 1024u) ? idesc2 : idesc, (e1.y & fresh_mask) ? 0u : 1u, nk);
+                                if (ng > 2) tc_issue_pair(tmem_base + (e1.w & 511u), da, ((uint64_t)desc_hi << 32) | e1.z, (e1.w & 1024u) ? idesc2 : idesc, (e1.w & fresh_mask) ? 0u : 1u, nk);
+                                if (ng > 3) tc_issue_pair(tmem_base + (e2.y & 511u), da, ((uint64_t)desc_hi << 32) | e2.x, (e2.y & 1024u) ? idesc2 : idesc, (e2.y & fresh_mask) ? 0u : 1u, nk);
                                 tc_commit(bar_empty + ((e0.y >> 8) & 255u));                           // A plane: its last use is this step
                                 if (e0.y & (1u << 16)) tc_commit(bar_empty + ((e0.y >> 17) & 255u));    // the B plane that is done
                             }
@@ -356,10 +351,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                     for (int cc = 0; cc < 8; ++cc) {
                         int r0[8], r1[8], r2[8], r3[8];
-                        tmem_ld8(tlane + cc * 8, r0);
-                        if (nl > 1) tmem_ld8(tlane + TC_BN + cc * 8, r1);
-                        if (nl > 2) tmem_ld8(tlane + 2 * TC_BN + cc * 8, r2);
-                        if (nl > 3) tmem_ld8(tlane + 3 * TC_BN + cc * 8, r3);
+                        // level l of the group lives at column (nl-1-l)*128 (adjacent levels side by side for the N = 256 MMAs)
+                        tmem_ld8(tlane + (nl - 1) * TC_BN + cc * 8, r0);
+                        if (nl > 1) tmem_ld8(tlane + (nl - 2) * TC_BN + cc * 8, r1);
+                        if (nl > 2) tmem_ld8(tlane + (nl - 3) * TC_BN + cc * 8, r2);
+                        if (nl > 3) tmem_ld8(tlane + (nl - 4) * TC_BN + cc * 8, r3);
                         tmem_ld_wait();
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
