@@ -214,7 +214,7 @@ def _well_conditioned(nb, n, seed):
 
 
 @pytest.mark.parametrize("N,nb", [(169, 3), (961, 2)])
-@pytest.mark.parametrize("slices,tol", [(5, 2e-7), (8, 1e-12)])
+@pytest.mark.parametrize("slices,tol", [(5, 2e-7), (8, 2e-11)])
 def test_layer_smatrix_and_redheffer_tc_vs_dmma(N, nb, slices, tol):
     """The S-matrix stage with its dense products on the tcgen05 int8-digit GEMM (gemm_slices = 5 / 8: products, and the
     512-wide right-looking triangular solves) against the same stage on the fp64 DMMA kernels (gemm_slices = 0)."""

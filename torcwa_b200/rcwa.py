@@ -58,8 +58,11 @@ class rcwa:
         (default: only for unbatched sims, where the reference keeps them).
         ``gemm_digits`` (new): engine of the dense products of the S-matrix stage (layer S-matrix, star
         products, their triangular solves): 0 = fp64 tensor pipe (DMMA), 2..8 = tcgen05 int8-digit GEMM with
-        that many 8-bit digits per number (include/rcwa_b200.h: rcwa_zgemm_tc_batched).  Default: 5 for
-        complex64 simulations (2e-10-grade products, far inside the API's single precision), 0 for complex128;
+        that many 8-bit digits per number (include/rcwa_b200.h: rcwa_zgemm_tc_batched).  Default: 7 for
+        complex64 simulations, 0 for complex128.  Why 7 and not fewer: the stage amplifies a product's error by up
+        to ~1e6 into the far-evanescent entries of the S blocks (measured on config 4's sweep corners at order 15:
+        5 digits -> 2e-4 on a block column, 6 -> 1e-6, 7 and 8 -> the float32 input noise 8e-8), so 7 keeps the
+        complex64 gate of 1e-4 with four orders of margin at 1.9x the fp64 kernel's speed (5 digits: 2.6x);
         the environment variable RCWA_B200_GEMM_DIGITS overrides the complex64 default.  The eigensolver always
         runs in fp64 (SURVEY.md finding 5).
         ``pipeline`` (new): number of sub-batches a batched simulation is run as (default 1 = off; environment
@@ -78,7 +81,7 @@ class rcwa:
             device = torch.device('cuda')
         self._device = torch.device(device)
         if gemm_digits is None:
-            gemm_digits = int(os.environ.get('RCWA_B200_GEMM_DIGITS', '5')) if dtype == torch.complex64 else 0
+            gemm_digits = int(os.environ.get('RCWA_B200_GEMM_DIGITS', '7')) if dtype == torch.complex64 else 0
         self._digits = int(gemm_digits) if 2 <= int(gemm_digits) <= 8 else 0
         if self._device.type != 'cuda' and not _TEST_ALLOW_NON_CUDA:
             raise RuntimeError('torcwa_b200 runs on CUDA devices only (no CPU path); got device=%s' % device)
