@@ -281,7 +281,7 @@ def bench_b200(args):
         sim_stage, A_eig = stage_times(case, grids_res[sl0][:Ps].contiguous(), freq_res[sl0][:Ps].contiguous(), device)
         torch.cuda.empty_cache()
         mv = matvec_roofline(A_eig)
-        tz = tensor_roofline(A_eig, digits=int(os.environ.get('RCWA_B200_GEMM_DIGITS', '5')))
+        tz = tensor_roofline(A_eig, digits=int(os.environ.get('RCWA_B200_GEMM_DIGITS', '7')))
         del A_eig
         torch.cuda.empty_cache()
         b_eig = 16.0 * (n ** 3 / 3.0 + 2.0 * n * n)                      # SURVEY.md 8d, s = 16 (fp64 internals)
@@ -325,7 +325,7 @@ def bench_b200(args):
         out = {
             "metric": "layers/sec (order %dx%d, c64)" % (args.order, args.order), "value": value, "unit": "layers/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64 (complex128 internals behind the complex64 API; results rounded to c64)",
+            "vs_baseline": None, "dtype": "f64 eigensolver and solves; the S-matrix stage's dense products on tcgen05 int8 digits (7 x 8 bit, fp64-grade) behind the complex64 API; results rounded to c64",
             "data": "synthetic (Example1 cell, linear a-Si:H dispersion, 512 wavelengths 400-700 nm)",
             "config": {"workload": "BASELINE configs[1]: order %dx%d (n=%d), 1 patterned layer + SiO2 half space, 512-wavelength sweep, complex64 API"
                                    % (args.order, args.order, n), "points_per_step_per_gpu": P, "layers_per_point": 1,
@@ -429,7 +429,7 @@ def matvec_roofline(A):
     return {"gbs": byts / (ms * 1e-3) / 1e9, "launches": len(cols), "bytes_per_launch": byts / len(cols), "us_per_launch": 1e3 * ms / len(cols)}
 
 
-def tensor_roofline(A, digits=5):
+def tensor_roofline(A, digits=7):
     """Tensor pipes, measured in this run with CUDA events on batched n x n x n complex products:
       * fp64 (DMMA, mma.sync): our kernel, against the fp64 tensor peak MEASURED here as a sustained cuBLAS dgemm (8192^3,
         back to back for ~1 s) -- MEASURED_PEAKS.json has no fp64 entry;

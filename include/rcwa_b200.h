@@ -189,8 +189,9 @@ int rcwa_eig_backward(const void* lam, const void* X, const void* glam, const vo
  * rcwa._solve_layer_smatrix, rcwa.py:1244-1281 (dense inv of the 4N x 4N coupling matrix).
  * gemm_slices (here and in the star products): 0 = every dense product on the fp64 tensor pipe (DMMA; the complex128
  * contract); 2..8 = the n x n x n products and the K = 512 block updates of the triangular solves run on the tcgen05
- * int8-digit GEMM with that many digits (see rcwa_zgemm_tc_batched; 5 keeps the complex64 API's 1e-4 gate with three
- * orders of margin).  The workspace size depends on it. */
+ * int8-digit GEMM with that many digits (see rcwa_zgemm_tc_batched; the Python host uses 7 for complex64 simulations:
+ * the stage amplifies a product's error by up to ~1e6 into the far-evanescent S-block entries).  The
+ * workspace size depends on it. */
 size_t rcwa_layer_smatrix_workspace_bytes(int N, int nb, int gemm_slices);
 int rcwa_layer_smatrix(const void* W, const void* kz, const void* Q, const void* vfinv,
                        const double* omega, const double* thickness, int nb, int N,
