@@ -88,6 +88,10 @@ class rcwa:
         _lib.load()   # fail loudly, now, if the CUDA library is missing
 
         self.stable_eig_grad = True if stable_eig_grad else False
+        if not stable_eig_grad:
+            # accepted for drop-in compatibility; the broadened backward (torch_eig.py:28-33) is the only one implemented
+            warnings.warn('torcwa_b200: stable_eig_grad=False is not honoured -- gradients of the eigendecomposition always use '
+                          'the Lorentzian-broadened formula (torcwa.Eig.broadening_parameter)', UserWarning)
         if avoid_Pinv_instability is True:
             self.avoid_Pinv_instability = True
             self.max_Pinv_instability = max_Pinv_instability
@@ -133,6 +137,7 @@ class rcwa:
         self.eig_info = []         # per patterned layer: int32 [B] status of the eigensolver
         self._status = []          # (what, int32 [B] device tensor) of every factorisation / eigensolve: checked lazily
         self._gate = None          # (wait flag, wait event, signal flag, signal event): stagger of pipelined sub-batches
+        self._kz_min = []          # per patterned layer: min |kz| / max |kz| over the batch (device scalar), read with the status words
 
         # ---- pipelined sub-batches (children); the parent keeps the O(N) per-order state and delegates the dense stages
         self._children = None
@@ -396,6 +401,9 @@ class rcwa:
             self.eig_info.append(info)
             self._status.append(('eigendecomposition (layer %d): QR iteration did not converge' % self.layer_N, info))
             kz = _lib.kz_branch(lam)
+            ka = kz.abs()
+            self._kz_min.append((ka.amin(dim=1) / ka.amax(dim=1)).min())
+            del ka
             S11, S21, info_s = _lib.layer_smatrix(W, kz, Q, self._Vf_inv, omega, thick, slices=self._digits)
             self._status.append(('layer S-matrix (layer %d): singular coupling matrix' % self.layer_N, info_s))
             if self._store:
@@ -522,6 +530,16 @@ class rcwa:
         and the host looks at it once, when the global S-matrix is complete)."""
         if not self._status:
             return
+        # Wood-anomaly guard (scope row f3).  The layer kernel forms the H modes as V = Q W Kz^-1 (the reference's fallback
+        # branch, rcwa.py:1260); the reference's DEFAULT, P^-1 W Kz (:1264), stays finite when a mode's kz vanishes, this
+        # form does not -- say so instead of returning a silently degraded S-matrix.
+        if self._kz_min:
+            ratio = float(torch.stack(self._kz_min).min())
+            if ratio < 1e-9:
+                warnings.warn('torcwa_b200: a layer mode has |kz| / max|kz| = %.1e (Wood anomaly / cut-off): the H modes are '
+                              'formed as Q W Kz^-1 and lose accuracy there; the reference\'s default P^-1 W Kz stays finite' % ratio,
+                              UserWarning)
+            self._kz_min = []
         worst = torch.stack([i.to(self._device).abs().max() for _, i in self._status])
         if int(worst.max()) != 0:
             k = int(torch.nonzero(worst)[0])
