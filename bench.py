@@ -159,9 +159,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- B200 arm
-def run_step(grids_dev, freq_dev, case, device):
+def run_step(grids_dev, freq_dev, case, device, symmetry=None):
+    """symmetry: None = the package default (auto-detected symmetry reduction on), False = the general path."""
     import torcwa_b200
-    sim = torcwa_b200.rcwa(freq=freq_dev, order=case["order"], L=case["L"], dtype=torch.complex64, device=device)
+    sim = torcwa_b200.rcwa(freq=freq_dev, order=case["order"], L=case["L"], dtype=torch.complex64, device=device, symmetry_reduction=symmetry)
     sim.add_input_layer(eps=case["eps_in"])
     sim.set_incident_angle(inc_ang=0.0, azi_ang=0.0)
     sim.add_layer(thickness=300.0, eps=grids_dev)
@@ -222,9 +223,9 @@ def bench_b200(args):
         c = s * world + rank
         return (torch.arange(P) + c * P) % N_SWEEP
 
-    def step_resident(s):
+    def step_resident(s, symmetry=None):
         sl = chunk(s).to(device)
-        return run_step(grids_res[sl], freq_res[sl], case, device)
+        return run_step(grids_res[sl], freq_res[sl], case, device, symmetry)
 
     def step_e2e(s):
         sl = chunk(s)
@@ -265,6 +266,14 @@ def bench_b200(args):
     ms_res = timed(step_resident, K, W)
     clk = clocks.stop()
     ms_e2e = timed(step_e2e, K, 1, s0=K + W)
+    # the same sweep with the symmetry reduction switched off: every design point as one dense n x n problem
+    Pg = min(P, args.general_points)
+    ms_gen = None
+    if args.general_path:
+        def step_general(s):
+            sl = (chunk(s)[:Pg]).to(device)
+            return run_step(grids_res[sl], freq_res[sl], case, device, False)
+        ms_gen = timed(step_general, K, W, s0=2 * (K + W))
     layers_per_step = P * world                                           # one patterned layer per design point
     value = layers_per_step * K / (ms_res * 1e-3)
     e2e_value = layers_per_step * K / (ms_e2e * 1e-3)
@@ -275,6 +284,18 @@ def bench_b200(args):
         # ---- stage split and roofline of the eigen stage (untimed extra step on rank 0)
         from torcwa_b200 import _lib
         launches, per_kernel = count_my_launches(lambda: step_resident(0))
+        sym_probe = None
+        try:            # which symmetry the package found for this workload (one untimed small solve)
+            import torcwa_b200
+            sl0_ = chunk(0)[:8].to(device)
+            sim_ = torcwa_b200.rcwa(freq=freq_res[sl0_], order=case["order"], L=case["L"], dtype=torch.complex64, device=device)
+            sim_.add_input_layer(eps=case["eps_in"]); sim_.set_incident_angle(inc_ang=0.0, azi_ang=0.0)
+            sim_.add_layer(thickness=300.0, eps=grids_res[sl0_])
+            if sim_._sym not in (None, False):
+                sym_probe = {"mirrors": list(sim_._sym.gens), "block_sizes": [sim_._sym.sizes[c] for c in sim_._sym.chars]}
+            del sim_
+        except Exception as ex:
+            sym_probe = {"error": str(ex)[:200]}
         torch.cuda.empty_cache()
         sl0 = chunk(0).to(device)
         Ps = P
@@ -329,6 +350,7 @@ def bench_b200(args):
             "data": "synthetic (Example1 cell, linear a-Si:H dispersion, 512 wavelengths 400-700 nm)",
             "config": {"workload": "BASELINE configs[1]: order %dx%d (n=%d), 1 patterned layer + SiO2 half space, 512-wavelength sweep, complex64 API"
                                    % (args.order, args.order, n), "points_per_step_per_gpu": P, "layers_per_point": 1,
+                       "symmetry_reduction": sym_probe if sym_probe else "none found: general path",
                        "l2": "working set per step >> 126 MB L2; every step takes new wavelengths", "parallelism": "dp%d (sweep sharded, final all_gather)" % world},
             "e2e": {"value": e2e_value, "unit": "layers/s", "h2d_bytes_per_step": int(P * (300 * 300 * 8 + 4)), "d2h_bytes_per_step": int(P * world * 8),
                     "ms_per_step": ms_e2e / K},
@@ -343,6 +365,10 @@ def bench_b200(args):
                                   sorted(per_kernel.items(), key=lambda kv: -kv[1][1])[:8]} if launches else per_kernel,
             "kernel_launches_and_avg_us": {k: [v[0], round(v[1] / max(v[0], 1), 1)] for k, v in
                                            sorted(per_kernel.items(), key=lambda kv: -kv[1][1])[:8]} if launches else None,
+            "general_path": None if ms_gen is None else {
+                "value": Pg * world * K / (ms_gen * 1e-3), "unit": "layers/s", "ms_per_step": ms_gen / K, "points_per_step_per_gpu": Pg,
+                "note": "the same sweep with symmetry_reduction=False: each design point one dense n x n problem (the path the roofline, stage split and "
+                        "kernel shares below describe)"},
             "cpu_baseline": cpu,
             "cuda_baseline": cuda_ref,
             "vs_reference_cuda": None if not cuda_ref or "c64" not in cuda_ref or "layers_per_s" not in cuda_ref["c64"] else {
@@ -823,6 +849,8 @@ def main():
     ap.add_argument("--order", type=int, default=None, help="Fourier order (default 15 / 21 / 25 for config 2 / 3 / 5)")
     ap.add_argument("--order-y", type=int, default=None, help="config 5 only: second order (Example6 uses [15, 8])")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-general-path", dest="general_path", action="store_false", help="skip the extra timing of the sweep with the symmetry reduction off")
+    ap.add_argument("--general-points", type=int, default=128, help="design points per step of the general-path leg (its footprint is ~0.7 GB per point)")
     ap.add_argument("--no-cuda-baseline", dest="cuda_baseline", action="store_false", help="skip the reference's PyTorch-CUDA path (unmodified baseline/_ref on this GPU)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
     ap.add_argument("--ref-dtype", default="c128", choices=["c64", "c128"], help="arithmetic of the CPU reference legs (see REF_DTYPE_NOTE)")

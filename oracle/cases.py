@@ -71,6 +71,14 @@ CASES = {
     # BASELINE.json configs[2]: order 21 x 21, 8 stacked layers, complex128 (the reference's complex64 run is skipped:
     # its MKL cgetri slow path would take hours at 4N = 7396)
     "stack_o21": _base(order=[21, 21], layers=_stack_config3(), lam=650.0, big=True, c128_only=True),
+    # symmetry-reduction cases (torcwa_b200/symmetry.py): inversion centre only (rotated bars + spacer + output half space);
+    # one mirror only (incidence in the x-z plane keeps the y mirror); off-centre mirror planes
+    "c2_o3": _base(order=[3, 3], layers=[_rect(theta=math.pi / 6, eps_in=SI_EPS[650.0], eps_bg=SU8, d=200.0),
+                                         dict(kind="homogeneous", d=100.0, eps=SU8),
+                                         _rect(theta=math.pi / 3, eps_in=SI_EPS[650.0], eps_bg=SU8, d=150.0)], lam=650.0, eps_out=2.1, full=True),
+    "ymirror_o3": _base(order=[3, 2], layers=[_rect()], inc=0.35, azi=0.0, nxy=[96, 80], full=True),
+    "offcentre_o3": _base(order=[3, 3], layers=[dict(kind="rect", d=250.0, Wx=140.0, Wy=90.0, Cx=101.0, Cy=187.5, theta=0.0,
+                                                     eps_in=SI_EPS[532.0], eps_bg=1.0)], full=True),
     # C4v-symmetric cell: exactly degenerate eigenpairs
     "square_o4": _base(order=[4, 4], layers=[_rect(Wx=150.0, Wy=150.0)]),
 }

@@ -14,41 +14,51 @@ pytestmark = pytest.mark.gpu
 
 from oracle import cases as C  # noqa: E402
 
-SMALL = ["ex1_o3", "ex1_o5", "stack_o3", "stack_o4x2", "fresnel_o2", "square_o4"]
+SMALL = ["ex1_o3", "ex1_o5", "stack_o3", "stack_o4x2", "fresnel_o2", "square_o4", "c2_o3", "ymirror_o3", "offcentre_o3"]
 # BASELINE configs at their real sizes: corners / C4v-symmetric centre of config 4's (Wx, Wy, lambda) sweep at order 15, and
 # config 3's 8-layer stack at order 21 (complex128 only)
 SWEEP = ["sweep_o15_a", "sweep_o15_b", "sweep_o15_c"]
 
 
-def b200_factory(freq, order, L, dtype):
+def b200_factory(freq, order, L, dtype, **kw):
     import torcwa_b200
-    return torcwa_b200.rcwa(freq=freq, order=order, L=L, dtype=dtype, device=torch.device("cuda:0"))
+    return torcwa_b200.rcwa(freq=freq, order=order, L=L, dtype=dtype, device=torch.device("cuda:0"), **kw)
 
 
 def to_dev(case, cdtype):
     return case
 
 
-def run(name, cdtype):
+def run(name, cdtype, **kw):
     case = C.CASES[name]
     # same driver as the golden generator, tensors moved to the GPU by the solver
-    return C.run_case(b200_factory, case, cdtype)
+    return C.run_case(lambda freq, order, L, dtype: b200_factory(freq, order, L, dtype, **kw), case, cdtype)
+
+
+# cases whose cell + incidence have a symmetry the reduction (torcwa_b200/symmetry.py) finds: they run on BOTH paths
+SYMMETRIC = {"ex1_o3", "ex1_o5", "square_o4", "c2_o3", "ymirror_o3", "offcentre_o3", "ex1_o15", "sweep_o15_a", "sweep_o15_b", "sweep_o15_c", "stack_o21"}
+
+
+def paths(names):
+    return [(n, s) for n in names for s in ((True, False) if n in SYMMETRIC else (False,))]
 
 
 def relfro(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
-@pytest.mark.parametrize("name", SMALL + SWEEP + ["stack_o21"])
-def test_parity_c128(name, golden_dir):
+@pytest.mark.parametrize("name,sym", paths(SMALL + SWEEP + ["stack_o21"]))
+def test_parity_c128(name, sym, golden_dir):
+    """sym = True: the symmetry-reduced block path (2 or 4 blocks); False: the general path."""
     g = np.load(os.path.join(golden_dir, name + ".npz"))
-    sim = run(name, torch.complex128)
+    sim = run(name, torch.complex128, symmetry_reduction=sym)
+    assert (sim._sym not in (None, False)) == sym
     for info in sim.eig_info:
         assert int(info.abs().max()) == 0
     sp = C.probe(sim)
     scale = np.abs(g["sparams_c128"]).max()
     err = np.abs(sp - g["sparams_c128"]).max() / scale
-    print(name, "S-parameter max err / max|S|:", err)
+    print(name, "sym=%s" % sym, "S-parameter max err / max|S|:", err)
     assert err <= 1e-10
     cols = g["S_cols_idx"]
     for k in range(4):
@@ -69,20 +79,20 @@ def test_parity_c128(name, golden_dir):
             assert np.abs(mine - g["kz2_sorted"][l]).max() <= 1e-9 * np.abs(mine).max()
 
 
-@pytest.mark.parametrize("name", SMALL + ["ex1_o15"] + SWEEP)
-def test_parity_c64_api(name, golden_dir):
+@pytest.mark.parametrize("name,sym", paths(SMALL + ["ex1_o15"] + SWEEP))
+def test_parity_c64_api(name, sym, golden_dir):
     """complex64 API (fp64 eigensolver, S-matrix stage on the tcgen05 7-digit GEMM where the matrices are large enough
     -- at order 15 every dense product and triangular-solve update of the stage) against the reference's complex128 run."""
     g = np.load(os.path.join(golden_dir, name + ".npz"))
-    sim = run(name, torch.complex64)
-    assert sim._digits == 7
+    sim = run(name, torch.complex64, symmetry_reduction=sym)
+    assert sim._digits == 7 and (sim._sym not in (None, False)) == sym
     assert sim.S[0].dtype == torch.complex64
     sp = C.probe(sim)
     scale = np.abs(g["sparams_c128"]).max()
     new_vs_ref128 = np.abs(sp - g["sparams_c128"]).max() / scale
     ref64_vs_ref128 = np.abs(g["sparams_c64"] - g["sparams_c128"]).max() / scale
     new_vs_ref64 = np.abs(sp - g["sparams_c64"]).max() / scale
-    print(f"{name}: new-c64 vs ref-c128 {new_vs_ref128:.2e} | ref-c64 vs ref-c128 {ref64_vs_ref128:.2e} | new-c64 vs ref-c64 {new_vs_ref64:.2e}")
+    print(f"{name} sym={sym}: new-c64 vs ref-c128 {new_vs_ref128:.2e} | ref-c64 vs ref-c128 {ref64_vs_ref128:.2e} | new-c64 vs ref-c64 {new_vs_ref64:.2e}")
     assert new_vs_ref128 <= 1e-4
     for k in range(4):
         assert relfro(sim.S[k][:, g["S_cols_idx"]].cpu().numpy().astype(np.complex128), g["S_cols"][k]) <= 1e-4
@@ -96,7 +106,7 @@ def test_order15_parity_vs_digits_of_the_tcgen05_engine(digits, gate, golden_dir
     import torcwa_b200
     g = np.load(os.path.join(golden_dir, "ex1_o15.npz"))
     sim = C.run_case(lambda freq, order, L, dtype: torcwa_b200.rcwa(freq=freq, order=order, L=L, dtype=dtype, device=torch.device("cuda:0"),
-                                                                  gemm_digits=digits), C.CASES["ex1_o15"], torch.complex128)
+                                                                  gemm_digits=digits, symmetry_reduction=False), C.CASES["ex1_o15"], torch.complex128)
     sp = C.probe(sim)
     err = np.abs(sp - g["sparams_c128"]).max() / np.abs(g["sparams_c128"]).max()
     print("order 15, %d digits: S-parameter max err / max|S| = %.2e" % (digits, err))
@@ -175,7 +185,8 @@ def test_dtype_and_device_rules():
         torcwa_b200.rcwa(freq=1 / 532.0, order=[1, 1], L=[300.0, 300.0], dtype=torch.float32, device=torch.device("cuda:0"))
 
 
-def test_order15_batched_sweep_parity_and_batch_independence(golden_dir):
+@pytest.mark.parametrize("sym", [False, True])
+def test_order15_batched_sweep_parity_and_batch_independence(sym, golden_dir):
     """BASELINE config 2 at its real size (order 15x15, n = 1922), batch 24: the QR phase runs as two pipelined
     matrix groups with time-sliced passes and side-stream updates.  (a) the 532 nm point matches the reference's
     complex128 run to 1e-10; (b) every point is BIT-IDENTICAL to what a different batch composition gives -- the
@@ -191,7 +202,8 @@ def test_order15_batched_sweep_parity_and_batch_independence(golden_dir):
     lams[0] = 532.0
 
     def solve(lam_vec, pipeline=1):
-        sim = torcwa_b200.rcwa(freq=1 / lam_vec, order=case["order"], L=case["L"], dtype=cd, device=dev, store_intermediates=False, pipeline=pipeline)
+        sim = torcwa_b200.rcwa(freq=1 / lam_vec, order=case["order"], L=case["L"], dtype=cd, device=dev, store_intermediates=False, pipeline=pipeline,
+                               symmetry_reduction=sym)
         sim.add_input_layer(eps=case["eps_in"])
         sim.set_incident_angle(0.0, 0.0)
         sim.add_layer(thickness=float(d), eps=grid.to(dev))
@@ -202,7 +214,7 @@ def test_order15_batched_sweep_parity_and_batch_independence(golden_dir):
     sim = solve(lams)
     one = torcwa_b200.rcwa(freq=1 / lams[0], order=case["order"], L=case["L"], dtype=cd, device=dev)
     one.add_input_layer(eps=case["eps_in"]); one.set_incident_angle(0.0, 0.0)
-    one._S = [s[0:1] for s in sim._S]
+    one._S = [s[0:1].clone() for s in sim._S]
     sp = C.probe(one)
     scale = np.abs(g["sparams_c128"]).max()
     err = np.abs(sp - g["sparams_c128"]).max() / scale

@@ -10,7 +10,10 @@ from fake_lib import cpu_double  # noqa: F401  (fixture)
 from oracle import cases as C
 from oracle.rcwa_oracle import OracleSim
 
-SMALL = ["ex1_o3", "ex1_o5", "stack_o3", "stack_o4x2", "fresnel_o2", "square_o4"]
+SMALL = ["ex1_o3", "ex1_o5", "stack_o3", "stack_o4x2", "fresnel_o2", "square_o4", "c2_o3", "ymirror_o3", "offcentre_o3"]
+# which symmetry the reduction (torcwa_b200/symmetry.py) must find in each case (None: general path)
+SYMMETRY = {"ex1_o3": ("x", "y"), "ex1_o5": ("x", "y"), "square_o4": ("x", "y"), "offcentre_o3": ("x", "y"), "c2_o3": ("c2",),
+            "ymirror_o3": ("y",), "stack_o3": None, "stack_o4x2": None, "fresnel_o2": None}
 CPU = torch.device("cpu")
 
 
@@ -29,6 +32,68 @@ def test_host_path_matches_reference_c128(cpu_double, name, golden_dir):
     if "S" in g:
         for k in range(4):
             assert relfro(sim.S[k].numpy(), g["S"][k]) <= 1e-10
+    found = sim._sym.gens if sim._sym not in (None, False) else None
+    assert found == SYMMETRY[name]
+
+
+@pytest.mark.parametrize("name", [k for k, v in SYMMETRY.items() if v])
+def test_symmetry_reduced_path_equals_general_path(cpu_double, name, golden_dir):
+    """The block path (2 or 4 blocks in the symmetry-adapted basis) and the general path give the same global S-matrix,
+    layer S-matrices, kz multiset and fields-relevant attributes; both match the reference's stored output."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    mk = lambda sym: C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, symmetry_reduction=sym, **kw), C.CASES[name], torch.complex128)
+    a, b = mk(True), mk(False)
+    assert a._sym not in (None, False) and b._sym is None
+    for k in range(4):
+        assert relfro(a.S[k].numpy(), b.S[k].numpy()) <= 1e-11
+        if "S" in g:
+            assert relfro(a.S[k].numpy(), g["S"][k]) <= 1e-10
+        assert relfro(a.S[k][:, g["S_cols_idx"]].numpy(), g["S_cols"][k]) <= 1e-10
+    for li in range(a.layer_N):
+        assert relfro(a.layer_S11[li].numpy(), b.layer_S11[li].numpy()) <= 1e-11
+        assert relfro(a.layer_S21[li].numpy(), b.layer_S21[li].numpy()) <= 1e-11
+        ka, kb = np.sort_complex(a.kz_norm[li].numpy() ** 2), np.sort_complex(b.kz_norm[li].numpy() ** 2)
+        assert np.abs(ka - kb).max() <= 1e-10 * np.abs(kb).max()
+    # the eigenvectors returned to the original basis still diagonalise P Q
+    li = 0
+    W, kz = a.E_eigvec[li], a.kz_norm[li]
+    A = a.P[li] @ a.Q[li]
+    assert relfro((A @ W).numpy(), (W * (kz ** 2)[None, :]).numpy()) <= 1e-10
+
+
+def test_symmetry_is_dropped_when_a_later_layer_breaks_it(cpu_double):
+    """First layer symmetric (solved in blocks), second layer an off-axis rotated bar without the mirrors: the stack is
+    cascaded in the original basis, and equals the general path."""
+    case = dict(C.CASES["ex1_o3"])
+    case["layers"] = [C._rect(), dict(C._rect(theta=0.4, d=120.0), Cx=140.0)]
+
+    def run(sym):
+        return C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, symmetry_reduction=sym, **kw), case, torch.complex128)
+    a, b = run(True), run(False)
+    assert a._sym is False
+    for k in range(4):
+        assert relfro(a.S[k].numpy(), b.S[k].numpy()) <= 1e-11
+
+
+def test_symmetry_reduced_batched_sweep(cpu_double):
+    """Batched (no stored intermediates): per-point results of the block path == the general path."""
+    case = C.CASES["ex1_o3"]
+    cd = torch.complex128
+    lams = torch.tensor([500.0, 532.0, 610.0], dtype=torch.float64)
+    d, grid = C.build_layers(case, cd)[0]
+    grids = torch.stack([grid, grid * 0.9 + 0.1, grid])
+    out = []
+    for sym in (True, False):
+        sim = cpu_double.rcwa(freq=1 / lams, order=case["order"], L=case["L"], dtype=cd, device=CPU, symmetry_reduction=sym)
+        sim.add_input_layer(eps=case["eps_in"])
+        sim.set_incident_angle(0.0, 0.0)
+        sim.add_layer(thickness=torch.tensor([300.0, 250.0, 300.0]), eps=grids)
+        sim.add_layer(thickness=50.0, eps=2.25)
+        sim.solve_global_smatrix()
+        out.append(torch.stack([sim.S_parameters(orders=[[0, 0], [1, 0], [-1, 1]], polarization=p, port=q)
+                                for p in ("xx", "yx", "pp") for q in ("transmission", "reflection")]))
+        assert (sim._sym not in (None, False)) == sym
+    assert float((out[0] - out[1]).abs().max()) <= 1e-12
 
 
 def test_half_space_blocks_match_oracle_dense(cpu_double):

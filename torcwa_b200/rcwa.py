@@ -24,6 +24,7 @@ import torch
 
 from . import _lib
 from . import autodiff
+from . import symmetry
 from ._bd import bd, bd_diag, bd_inv, bd_mul, sqrt_upper, v_matrix
 
 # The reference's pi is mistyped (torcwa/rcwa.py:5); omega = 2*pi*freq enters every layer phase, so
@@ -52,7 +53,8 @@ class rcwa:
                  max_Pinv_instability=0.005,
                  store_intermediates=None,
                  gemm_digits=None,
-                 pipeline=None):
+                 pipeline=None,
+                 symmetry_reduction=None):
         """Same parameters as the reference (torcwa/rcwa.py:9-35).  ``store_intermediates``
         (new): keep per-layer P, Q, eigenvectors, convolution matrices as attributes
         (default: only for unbatched sims, where the reference keeps them).
@@ -65,6 +67,12 @@ class rcwa:
         complex64 gate of 1e-4 with four orders of margin at 1.9x the fp64 kernel's speed (5 digits: 2.6x);
         the environment variable RCWA_B200_GEMM_DIGITS overrides the complex64 default.  The eigensolver always
         runs in fp64 (SURVEY.md finding 5).
+        ``symmetry_reduction`` (new): True / False / None (= environment RCWA_B200_SYMMETRY, default on).  When a
+        patterned layer's cell has a mirror plane in x and / or y, or an inversion centre, and the incidence respects
+        it (kx0 = 0 and / or ky0 = 0), the layer eigenproblem and the S-matrix cascade are solved in the
+        symmetry-adapted basis as 2 or 4 independent blocks of ~n/2 or ~n/4 (torcwa_b200/symmetry.py): the same
+        numbers to round-off at 1/4 ... 1/16 of the dense work.  Detected from the convolution matrix itself
+        (tolerance 1e-11); any layer without the symmetry sends the whole stack through the general path.
         ``pipeline`` (new): number of sub-batches a batched simulation is run as (default 1 = off; environment
         RCWA_B200_PIPELINE; needs >= 8 points per sub-batch).  Sub-batches run on their own CUDA streams, driven by
         their own host threads, staggered so that the Hessenberg reduction and the S-matrix stage of one sub-batch run
@@ -137,6 +145,11 @@ class rcwa:
         self.eig_info = []         # per patterned layer: int32 [B] status of the eigensolver
         self._status = []          # (what, int32 [B] device tensor) of every factorisation / eigensolve: checked lazily
         self._gate = None          # (wait flag, wait event, signal flag, signal event): stagger of pipelined sub-batches
+        if symmetry_reduction is None:
+            symmetry_reduction = os.environ.get('RCWA_B200_SYMMETRY', '1') != '0'
+        self._sym_on = bool(symmetry_reduction)
+        self._sym = None           # symmetry.Basis shared by the block layers of this stack
+        self._sym_G = None         # per block: Vf^-1 in adapted coordinates
         self._kz_min = []          # per patterned layer: min |kz| / max |kz| over the batch (device scalar), read with the status words
 
         # ---- pipelined sub-batches (children); the parent keeps the O(N) per-order state and delegates the dense stages
@@ -153,7 +166,8 @@ class rcwa:
                 self._streams = [torch.cuda.Stream(device=self._device) for _ in range(k)]
             self._children = [rcwa(fr[sl], order, L, dtype=dtype, device=self._device, stable_eig_grad=stable_eig_grad,
                                    avoid_Pinv_instability=avoid_Pinv_instability, max_Pinv_instability=max_Pinv_instability,
-                                   store_intermediates=False, gemm_digits=self._digits, pipeline=1) for sl in self._slices]
+                                   store_intermediates=False, gemm_digits=self._digits, pipeline=1,
+                                   symmetry_reduction=self._sym_on) for sl in self._slices]
 
     # ------------------------------------------------------------------ pipelined sub-batches
     def _part(self, v, sl):
@@ -266,6 +280,7 @@ class rcwa:
         kx = kxl[:, :, None].expand(B, len(self.order_x), len(self.order_y)).reshape(B, N).contiguous()
         ky = kyl[:, None, :].expand(B, len(self.order_x), len(self.order_y)).reshape(B, N).contiguous()
         self._kx, self._ky = kx, ky
+        self._k0_zero = (bool((kx0.abs() < 1e-14).all()), bool((ky0.abs() < 1e-14).all()))
         self.kx0_norm, self.ky0_norm = self._pub(kx0), self._pub(ky0)
         self.kx_norm, self.ky_norm = self._pub(kxl), self._pub(kyl)
         self.Kx_norm_dn, self.Ky_norm_dn = self._pub(kx), self._pub(ky)
@@ -346,6 +361,7 @@ class rcwa:
         diff = any(isinstance(v, torch.Tensor) and v.requires_grad for v in (eps, mu, thickness))
         if diff:
             self._diff = True
+        blocks = None
         if he and hm:
             S11, S21, kz, Qbd = self._homogeneous_layer(self._b(eps), self._b(mu), omega, thick, diff)
             if self._store:
@@ -375,6 +391,7 @@ class rcwa:
         else:
             E = self._b(eps)[:, None, None] * torch.eye(N, dtype=_C, device=self._device) if he else self._conv(eps)
             E = E.contiguous()
+            basis = self._symmetry_of(E) if (hm and not he) else None
             eta, info_e = _lib.inverse(E)
             self._status.append(('inverse of the permittivity convolution matrix (layer %d)' % self.layer_N, info_e))
             if hm:
@@ -394,18 +411,23 @@ class rcwa:
             del E, M
             if self.avoid_Pinv_instability:
                 self._pinv_metrics(P, Q)
-            A = _lib.zgemm(P, Q)
-            del P                                  # free early: a batch chunk is sized by its peak footprint
-            lam, W, info = self._eig(A)
-            del A
-            self.eig_info.append(info)
-            self._status.append(('eigendecomposition (layer %d): QR iteration did not converge' % self.layer_N, info))
-            kz = _lib.kz_branch(lam)
-            ka = kz.abs()
-            self._kz_min.append((ka.amin(dim=1) / ka.amax(dim=1)).min())
-            del ka
-            S11, S21, info_s = _lib.layer_smatrix(W, kz, Q, self._Vf_inv, omega, thick, slices=self._digits)
-            self._status.append(('layer S-matrix (layer %d): singular coupling matrix' % self.layer_N, info_s))
+            if basis is not None:
+                blocks, kz, W, S11, S21 = self._patterned_layer_blocks(basis, P, Q, omega, thick)
+                del P
+            else:
+                blocks = None
+                A = _lib.zgemm(P, Q)
+                del P                                  # free early: a batch chunk is sized by its peak footprint
+                lam, W, info = self._eig(A)
+                del A
+                self.eig_info.append(info)
+                self._status.append(('eigendecomposition (layer %d): QR iteration did not converge' % self.layer_N, info))
+                kz = _lib.kz_branch(lam)
+                ka = kz.abs()
+                self._kz_min.append((ka.amin(dim=1) / ka.amax(dim=1)).min())
+                del ka
+                S11, S21, info_s = _lib.layer_smatrix(W, kz, Q, self._Vf_inv, omega, thick, slices=self._digits)
+                self._status.append(('layer S-matrix (layer %d): singular coupling matrix' % self.layer_N, info_s))
             if self._store:
                 self.E_eigvec.append(self._pub(W))
                 self._modes_src.append(dict(W=W, Q=Q, kz=kz, E=E_keep, M=M_keep, thick=thick, omega=omega))
@@ -413,11 +435,93 @@ class rcwa:
         self.kz_norm.append(self._pub(kz))
         self.layer_N += 1
         self.thickness.append(thickness)
-        self._layers.append([S11, S21])
+        self._layers.append(_BlockLayer(blocks, self._sym) if blocks is not None else [S11, S21])
         if self._store:
             s11, s21 = self._pub(S11), self._pub(S21)
             self.layer_S11.append(s11); self.layer_S21.append(s21)
             self.layer_S12.append(s21); self.layer_S22.append(s11)      # single-layer symmetry
+
+    # ------------------------------------------------------------------ symmetry-reduced layers (torcwa_b200/symmetry.py)
+    def _symmetry_of(self, E):
+        """Basis of the symmetry this layer shares with the stack so far (None: general path)."""
+        if not self._sym_on or not hasattr(self, '_k0_zero') or self._sym is False:
+            return None
+        found = symmetry.detect(E, int(self.order[0]), int(self.order[1]), self._k0_zero[0], self._k0_zero[1])
+        if found is None:
+            self._sym = False                     # one layer without it: the whole stack runs the general path
+            return None
+        gens, thx, thy = found
+        if self._sym is None:
+            self._sym = symmetry.Basis(int(self.order[0]), int(self.order[1]), gens, thx, thy, self._device)
+            Vfi = _lib.blockdiag_dense(self._Vf_inv.contiguous())
+            self._sym_G = {chi: self._sym.project(Vfi, chi, 'E', 'H') for chi in self._sym.chars}
+            return self._sym
+        cand = symmetry.Basis.__new__(symmetry.Basis)
+        cand.gens, cand.thx, cand.thy, cand.ox, cand.oy = tuple(gens), thx, thy, int(self.order[0]), int(self.order[1])
+        if self._sym.same_as(cand):
+            return self._sym
+        self._sym = False
+        return None
+
+    def _patterned_layer_blocks(self, basis, P, Q, omega, thick):
+        """One patterned layer solved block by block in the symmetry-adapted basis: the algebra of rcwa_layer_smatrix
+        (V = Q W Kz^-1, T+- = R+- M+-^-1, S11 = T+ + T-, S21 = T+ - T- - I) on matrices of ~n/2 or ~n/4.
+        Blocks of equal size are stacked along the batch dimension so that each C-ABI call sees one larger batch."""
+        B = self._B
+        out, kzs, Ws, infos = {}, {}, {}, []
+        by_size = {}
+        for chi in basis.chars:
+            by_size.setdefault(basis.sizes[chi], []).append(chi)
+        for nk, chars in by_size.items():
+            Pk = torch.cat([basis.project(P, chi, 'E', 'H') for chi in chars], dim=0)
+            Qk = torch.cat([basis.project(Q, chi, 'H', 'E') for chi in chars], dim=0)
+            Gk = torch.cat([self._sym_G[chi] for chi in chars], dim=0)
+            om, th = omega.repeat(len(chars)), thick.repeat(len(chars))
+            A = _lib.zgemm(Pk, Qk)
+            del Pk
+            lam, W, info = self._eig(A)
+            del A
+            infos.append(info)
+            kz = _lib.kz_branch(lam)
+            ka = kz.abs()
+            self._kz_min.append((ka.amin(dim=1) / ka.amax(dim=1)).min())
+            V = _lib.zgemm(Qk, W) / kz[:, None, :]
+            del Qk
+            Bm = _lib.zgemm(Gk, V)
+            del V, Gk
+            X = torch.exp(1j * (om * th)[:, None] * kz)[:, None, :]
+            Rp, Rm = W * (1 + X), W * (X - 1)
+            Mp, Mm = Rp + Bm * (1 - X), W * (1 - X) + Bm * (1 + X)
+            del Bm
+            Tp, i1 = _lib.right_solve(Rp, Mp)
+            del Rp, Mp
+            Tm, i2 = _lib.right_solve(Rm, Mm)
+            del Rm, Mm
+            infos += [i1, i2]
+            eye = torch.eye(nk, dtype=_C, device=self._device)
+            S11, S21 = Tp + Tm, Tp - Tm - eye
+            del Tp, Tm
+            for j, chi in enumerate(chars):
+                sl = slice(j * B, (j + 1) * B)
+                out[chi] = [S11[sl].contiguous(), S21[sl].contiguous()]
+                kzs[chi], Ws[chi] = kz[sl], W[sl]
+        info_all = torch.stack([i.reshape(len(i) // B, B).abs().amax(dim=0) for i in infos]).amax(dim=0).to(torch.int32)
+        self.eig_info.append(info_all)
+        self._status.append(('symmetry-reduced layer %d: eigendecomposition or coupling-matrix factorisation failed' % self.layer_N, info_all))
+        kz_full = torch.cat([kzs[chi] for chi in basis.chars], dim=1)
+        W_full = S11_full = S21_full = None
+        if self._store:
+            # drop-in attributes in the original basis: eigenvectors W = [T_chi W_chi], dense layer S blocks
+            W_full = torch.zeros((B, basis.n, basis.n), dtype=_C, device=self._device)
+            c0 = 0
+            for chi in basis.chars:
+                idx, cf = basis.E[chi]
+                for t in range(idx.shape[0]):
+                    W_full[:, :, c0:c0 + basis.sizes[chi]].index_add_(1, idx[t], Ws[chi] * cf[t][None, :, None])
+                c0 += basis.sizes[chi]
+            S11_full = basis.unproject({chi: v[0] for chi, v in out.items()})
+            S21_full = basis.unproject({chi: v[1] for chi, v in out.items()})
+        return out, kz_full, W_full, S11_full, S21_full
 
     def _eig(self, A):
         """rcwa_eig; as a pipelined sub-batch, wait for the previous sub-batch's Hessenberg phase and announce our own."""
@@ -501,6 +605,13 @@ class rcwa:
             return
         if self._diff:
             return self._solve_global_smatrix_differentiable()
+        if any(isinstance(l, _BlockLayer) for l in self._layers):
+            if self._sym not in (None, False):
+                return self._solve_global_smatrix_blocks()
+            # a later layer broke the symmetry: bring the block layers back to the original basis
+            basis = self._sym_basis_of_blocks
+            self._layers = [[basis.unproject({c: v[0] for c, v in l.blocks.items()}), basis.unproject({c: v[1] for c, v in l.blocks.items()})]
+                            if isinstance(l, _BlockLayer) else l for l in self._layers]
         if self.layer_N > 0:
             s11, s21 = self._layers[0]
             S = [s11, s21, s21, s11]
@@ -523,6 +634,44 @@ class rcwa:
         self.S = [self._pub(s) for s in S]
         self.C = [[], []]      # filled on demand (fields.ensure_modes): the fused cascade does not carry mode coefficients
         self._modes_ready = False
+
+    def _solve_global_smatrix_blocks(self):
+        """The left fold of solve_global_smatrix (rcwa.py:173-211) block by block in the symmetry-adapted basis; layers and
+        half spaces that were built in the original basis (homogeneous layers: four diagonals) are projected first.  The
+        global S-matrix is returned to the original basis at the end (O(n^2))."""
+        basis = self._sym
+        dense_of = lambda bd4: _lib.blockdiag_dense(bd4.contiguous())
+        Sblocks = {}
+        for chi in basis.chars:
+            def part(layer):
+                if isinstance(layer, _BlockLayer):
+                    a, b = layer.blocks[chi]
+                else:
+                    a, b = basis.project(layer[0], chi), basis.project(layer[1], chi)
+                return [a, b, b, a]
+            S = part(self._layers[0])
+            for i in range(1, self.layer_N):
+                S, info_r = _lib.redheffer(S, part(self._layers[i]), slices=self._digits)
+                self._status.append(('star product with layer %d (block %s)' % (i, chi), info_r))
+            if hasattr(self, 'Sin'):
+                S, info_r = _lib.redheffer([basis.project(dense_of(s), chi) for s in self._Sin], S, slices=self._digits)
+                self._status.append(('star product with the input half space (block %s)' % (chi,), info_r))
+            if hasattr(self, 'Sout'):
+                S, info_r = _lib.redheffer(S, [basis.project(dense_of(s), chi) for s in self._Sout], slices=self._digits)
+                self._status.append(('star product with the output half space (block %s)' % (chi,), info_r))
+            Sblocks[chi] = S
+        self._check_status()
+        self._S = [basis.unproject({chi: Sblocks[chi][k] for chi in basis.chars}) for k in range(4)]
+        self.S = [self._pub(s) for s in self._S]
+        self.C = [[], []]
+        self._modes_ready = False
+
+    @property
+    def _sym_basis_of_blocks(self):
+        for l in self._layers:
+            if isinstance(l, _BlockLayer):
+                return l.basis
+        return None
 
     def _check_status(self):
         """Numerical status of everything enqueued so far: ONE device-to-host read of the per-matrix info words
@@ -765,6 +914,13 @@ class rcwa:
         # an evanescent reference order gives zeros (rcwa.py:447-449), here per design point
         out = torch.where(r_ev, torch.zeros_like(out), out)
         return self._pub(out)
+
+
+class _BlockLayer:
+    """Layer S-matrix held as blocks in a symmetry-adapted basis: {character: [S11, S21]} (torcwa_b200/symmetry.py)."""
+
+    def __init__(self, blocks, basis=None):
+        self.blocks, self.basis = blocks, basis
 
 
 class _CatList:
