@@ -215,6 +215,14 @@ int rcwa_redheffer_bdleft(const void* const Sm_bd[4], const void* const Sn[4], v
  * homogeneous-layer blocks (rcwa.py:1157-1181, :1206-1222). */
 int rcwa_blockdiag_dense(const void* d4, int nb, int N, void* D, void* stream);
 
+/* Symmetry-adapted block of a dense operator: out [nb,nkl,nkr] = T_L^H X T_R for X [nb,n,n], where column k of T_L is
+ * sum_{t<G} cl[t][k] e_{il[t][k]} (il, cl: [G,nkl] row-major, int32 / complex128; likewise ir, cr [G,nkr]; G <= 4; unused
+ * slots carry a zero coefficient and any valid index).  The bases are the joint eigenvectors of the mirror / C2 operators
+ * that commute with P and Q of a symmetric cell (torcwa_b200/symmetry.py); the reference has no counterpart -- it always
+ * solves the full n x n problem (rcwa.py:1224-1247). */
+int rcwa_sym_project(const void* X, int nb, int n, const int* il, const void* cl, const int* ir, const void* cr,
+                     int G, int nkl, int nkr, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,12 @@ def kz_branch(lam):
     return torch.where(r.imag < 0, -r, r)
 
 
+def sym_project(X, il, cl, ir, cr):
+    """T_L^H X T_R from the (index, coefficient) tables, in plain torch (what rcwa_sym_project computes in one pass)."""
+    Y = sum(X.index_select(1, il[t].long()) * cl[t].conj()[None, :, None] for t in range(il.shape[0]))
+    return sum(Y.index_select(2, ir[t].long()) * cr[t][None, None, :] for t in range(ir.shape[0])).contiguous()
+
+
 def blockdiag_dense(d4):
     a, b, c, d = (torch.diag_embed(d4[:, k]) for k in range(4))
     return torch.cat((torch.cat((a, b), 2), torch.cat((c, d), 2)), 1)

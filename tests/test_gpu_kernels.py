@@ -213,6 +213,29 @@ def _well_conditioned(nb, n, seed):
     return (A + 2.0 * torch.eye(n, dtype=torch.complex128, device=dev())).contiguous()
 
 
+@pytest.mark.parametrize("order,gens", [((3, 3), ("x", "y")), ((4, 2), ("x",)), ((2, 5), ("y",)), ((3, 4), ("c2",)), ((15, 15), ("x", "y"))])
+def test_sym_project_kernel_vs_index_arithmetic(order, gens):
+    """rcwa_sym_project (one gather pass) == T_L^H X T_R by torch index_select / multiply / add (symmetry.Basis.project);
+    the blocks of a random matrix carry no structure, so every gathered term matters.  Also the round trip through
+    unproject for an operator that commutes with the group (built by symmetrising)."""
+    from torcwa_b200 import _lib, symmetry
+    basis = symmetry.Basis(order[0], order[1], gens, 0.3, -1.1, dev())
+    nb = 2 if order[0] > 10 else 3
+    X = rnd(nb, basis.n, basis.n, seed=5)
+    for chi in basis.chars:
+        for left, right in (("E", "E"), ("E", "H"), ("H", "E")):
+            got = _lib.sym_project(X, *basis.tables(chi, left, right))
+            want = basis.project(X, chi, left, right)
+            assert got.shape == want.shape
+            assert rel(got, want) <= 1e-14
+    # symmetrised operator: sum_chi T S_chi T^H gives it back
+    Xs = basis.unproject({chi: _lib.sym_project(X, *basis.tables(chi)) for chi in basis.chars})
+    back = {chi: _lib.sym_project(Xs, *basis.tables(chi)) for chi in basis.chars}
+    assert rel(basis.unproject(back), Xs) <= 1e-13
+    a = torch.arange(basis.n, device=dev())
+    assert rel(basis.entries(back, a[:, None], a[None, :]), Xs) <= 1e-13
+
+
 @pytest.mark.parametrize("N,nb", [(169, 3), (961, 2)])
 @pytest.mark.parametrize("slices,tol", [(5, 2e-7), (8, 2e-11)])
 def test_layer_smatrix_and_redheffer_tc_vs_dmma(N, nb, slices, tol):

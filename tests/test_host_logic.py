@@ -75,6 +75,52 @@ def test_symmetry_is_dropped_when_a_later_layer_breaks_it(cpu_double):
         assert relfro(a.S[k].numpy(), b.S[k].numpy()) <= 1e-11
 
 
+@pytest.mark.parametrize("thetas,expect", [((0.0, 0.5), ("c2",)), ((0.5, 0.0), ("c2",)), ((0.0, 0.5, 0.0), ("c2",))])
+def test_stack_moves_to_the_common_subgroup(cpu_double, thetas, expect):
+    """Mirror-symmetric bars and rotated bars about the same centre share C2 only: the stack is solved in the C2 blocks,
+    the earlier layers re-expressed in that basis, and equals the general path."""
+    case = dict(C.CASES["ex1_o3"])
+    case["layers"] = [C._rect(theta=t, d=100.0 + 40.0 * i) for i, t in enumerate(thetas)]
+
+    def run(sym):
+        return C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, symmetry_reduction=sym, **kw), case, torch.complex128)
+    a, b = run(True), run(False)
+    assert a._sym.gens == expect and set(a._S.blocks) == set(a._sym.chars)
+    for k in range(4):
+        assert relfro(a.S[k].numpy(), b.S[k].numpy()) <= 1e-11
+    for li in range(a.layer_N):
+        assert relfro(a.layer_S11[li].numpy(), b.layer_S11[li].numpy()) <= 1e-11
+
+
+def test_mirror_subgroup_when_only_one_centre_agrees(cpu_double):
+    """Two centred bars, the second shifted in y: the x mirror survives, the y mirror and C2 do not."""
+    case = dict(C.CASES["ex1_o3"])
+    case["layers"] = [C._rect(), dict(C._rect(d=120.0), Cy=110.0)]
+
+    def run(sym):
+        return C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, symmetry_reduction=sym, **kw), case, torch.complex128)
+    a, b = run(True), run(False)
+    assert a._sym.gens == ("x",)
+    for k in range(4):
+        assert relfro(a.S[k].numpy(), b.S[k].numpy()) <= 1e-11
+
+
+def test_block_s_entries_and_lazy_dense(cpu_double):
+    """S_parameters reads its entries off the symmetry blocks; the dense blocks appear only when asked for."""
+    sim = C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, **kw), C.CASES["ex1_o3"], torch.complex128)
+    assert sim._S._cache == {}
+    sp = C.probe(sim)
+    assert sim._S._cache == {}                       # the readout did not densify anything
+    n = 2 * sim.order_N
+    a = torch.arange(n)[:, None]
+    b = torch.arange(n)[None, :]
+    for k in range(4):
+        assert float((sim._S.entries(k, a, b)[0] - sim.S[k]).abs().max()) <= 1e-15
+    assert len(sim.S) == 4 and len(list(sim.S)) == 4 and sim.S[-1].shape == (n, n) and set(sim._S._cache) == {0, 1, 2, 3}
+    gen = C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, symmetry_reduction=False, **kw), C.CASES["ex1_o3"], torch.complex128)
+    assert np.abs(sp - C.probe(gen)).max() <= 1e-12
+
+
 def test_symmetry_reduced_batched_sweep(cpu_double):
     """Batched (no stored intermediates): per-point results of the block path == the general path."""
     case = C.CASES["ex1_o3"]

@@ -16,7 +16,7 @@ EXPORTS = [
     "rcwa_b200_abi_version", "rcwa_gemm_scratch_bytes", "rcwa_convmat_workspace_bytes", "rcwa_convmat",
     "rcwa_zgemm_batched", "rcwa_zgemm_batched_cfg", "rcwa_zgemm_tc_workspace_bytes", "rcwa_zgemm_tc_batched", "rcwa_tc_split", "rcwa_tc_schedule", "rcwa_tc_issue_entry", "rcwa_set_tuning", "rcwa_get_tuning", "rcwa_lu_tinv_bytes", "rcwa_lu_factor", "rcwa_lu_solve_right", "rcwa_pq_assemble",
     "rcwa_eig_workspace_bytes", "rcwa_eig", "rcwa_eig_phases", "rcwa_eig_stats", "rcwa_eig_profile", "rcwa_hessenberg", "rcwa_hessenberg_matvec_probe", "rcwa_hessenberg_panel_width", "rcwa_kz_branch", "rcwa_eig_backward_workspace_bytes", "rcwa_eig_backward", "rcwa_layer_smatrix_workspace_bytes",
-    "rcwa_layer_smatrix", "rcwa_redheffer_workspace_bytes", "rcwa_redheffer", "rcwa_redheffer_bdleft", "rcwa_blockdiag_dense",
+    "rcwa_layer_smatrix", "rcwa_redheffer_workspace_bytes", "rcwa_redheffer", "rcwa_redheffer_bdleft", "rcwa_blockdiag_dense", "rcwa_sym_project",
 ]
 
 _vp, _i, _ll, _d, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_size_t
@@ -55,6 +55,7 @@ _SIGS = {
     "rcwa_redheffer": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "rcwa_redheffer_bdleft": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "rcwa_blockdiag_dense": (_i, [_vp, _i, _i, _vp, _vp]),
+    "rcwa_sym_project": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
 }
 
 _lib = None
@@ -460,6 +461,21 @@ def redheffer_bdleft(Sm_bd, Sn, slices=0):
     a_o = arr(*[t.data_ptr() for t in out])
     _check(lib.rcwa_redheffer_bdleft(a_m, a_n, a_o, nb, n // 2, _ptr(ws), _ptr(info), int(slices), _stream()), "rcwa_redheffer_bdleft")
     return out, info
+
+
+@_on_device
+def sym_project(X, il, cl, ir, cr):
+    """T_L^H X T_R for symmetry-adapted bases given as (index int32 [G,nk], coefficient complex128 [G,nk]) tables."""
+    lib = load()
+    nb, n = X.shape[0], X.shape[1]
+    G, nkl, nkr = il.shape[0], il.shape[1], ir.shape[1]
+    for t in (il, ir):
+        if t.dtype != torch.int32 or not t.is_contiguous():
+            raise ValueError("sym_project: index tables must be contiguous int32")
+    out = torch.empty((nb, nkl, nkr), dtype=torch.complex128, device=X.device)
+    _check(lib.rcwa_sym_project(_ptr(_c128(X, "X")), nb, n, _ptr(il), _ptr(_c128(cl, "cl")), _ptr(ir), _ptr(_c128(cr, "cr")),
+                                G, nkl, nkr, _ptr(out), _stream()), "rcwa_sym_project")
+    return out
 
 
 @_on_device

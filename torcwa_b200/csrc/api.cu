@@ -482,4 +482,18 @@ int rcwa_blockdiag_dense(const void* d4, int nb, int N, void* D, void* stream) {
     return cu(blockdiag_dense((const cplx*)d4, nb, N, (cplx*)D, S(stream)));
 }
 
+int rcwa_sym_project(const void* X, int nb, int n, const int* il, const void* cl, const int* ir, const void* cr,
+                     int G, int nkl, int nkr, void* out, void* stream) {
+    if (!X) return -1;
+    if (nb <= 0) return -2;
+    if (n <= 0) return -3;
+    if (!il || !cl) return -4;
+    if (!ir || !cr) return -6;
+    if (G < 1 || G > 4) return -8;
+    if (nkl <= 0 || nkl > 65535) return -9;
+    if (nkr <= 0) return -10;
+    if (!out) return -11;
+    return cu(sym_project((const cplx*)X, nb, n, il, (const cplx*)cl, ir, (const cplx*)cr, G, nkl, nkr, (cplx*)out, S(stream)));
+}
+
 }  // extern "C"

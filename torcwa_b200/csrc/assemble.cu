@@ -222,6 +222,38 @@ cudaError_t kz_branch(const cplx* lam, cplx* kz, size_t total, cudaStream_t st) 
     kz_branch_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lam, kz, total);
     return cudaGetLastError();
 }
+// ---- symmetry-adapted blocks (torcwa_b200/symmetry.py): out = T_L^H X T_R for bases whose columns are combinations of at most
+// G <= 4 unit vectors: column k of T_L is sum_t cl[t][k] e_{il[t][k]} (padding entries carry a zero coefficient).  One
+// pass over the G*G gathered entries per output element; rows il[t][k] are read along l, so the loads coalesce wherever the
+// orbit representatives ir[u][l] run contiguously (they do within one kx order).
+__global__ void sym_project_kernel(const cplx* __restrict__ X, int n, const int* __restrict__ il, const cplx* __restrict__ cl,
+                                   const int* __restrict__ ir, const cplx* __restrict__ cr, int G, int nkl, int nkr,
+                                   cplx* __restrict__ out) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    const long long b = blockIdx.z;
+    if (l >= nkr) return;
+    const cplx* Xb = X + b * (long long)n * n;
+    int jr[4];
+    cplx wr[4];
+    for (int u = 0; u < G; ++u) { jr[u] = ir[u * nkr + l]; wr[u] = cr[u * nkr + l]; }
+    double sr = 0.0, si = 0.0;
+    for (int t = 0; t < G; ++t) {
+        const cplx w = cl[t * nkl + k];
+        if (w.x == 0.0 && w.y == 0.0) continue;
+        const cplx* row = Xb + (long long)il[t * nkl + k] * n;
+        double ar = 0.0, ai = 0.0;
+        for (int u = 0; u < G; ++u) {
+            if (wr[u].x == 0.0 && wr[u].y == 0.0) continue;
+            const cplx x = row[jr[u]];
+            ar += x.x * wr[u].x - x.y * wr[u].y;
+            ai += x.x * wr[u].y + x.y * wr[u].x;
+        }
+        sr += w.x * ar + w.y * ai;          // conj(w) * a
+        si += w.x * ai - w.y * ar;
+    }
+    out[(b * nkl + k) * nkr + l] = make_double2(sr, si);
+}
+
 cudaError_t layer_form(const cplx* W, const cplx* QW, const cplx* kz, const cplx* vfinv, const double* omega,
                        const double* thick, int nb, int N, cplx* Mp, cplx* Mm, cplx* Rp, cplx* Rm, cudaStream_t st) {
     layer_form_kernel<<<dim3((2 * N + 255) / 256, N, nb), 256, 0, st>>>(W, QW, kz, vfinv, omega, thick, N, Mp, Mm, Rp, Rm);
@@ -245,6 +277,11 @@ cudaError_t bd_right_mul(const cplx* d4, const cplx* X, int nb, int N, int nrows
 }
 cudaError_t bd_add(const cplx* d4, int nb, int N, cplx alpha, cplx* D, cudaStream_t st) {
     bd_add_kernel<<<dim3((N + 255) / 256, 1, nb), 256, 0, st>>>(d4, N, alpha, D);
+    return cudaGetLastError();
+}
+cudaError_t sym_project(const cplx* X, int nb, int n, const int* il, const cplx* cl, const int* ir, const cplx* cr,
+                        int G, int nkl, int nkr, cplx* out, cudaStream_t st) {
+    sym_project_kernel<<<dim3((nkr + 127) / 128, nkl, nb), 128, 0, st>>>(X, n, il, cl, ir, cr, G, nkl, nkr, out);
     return cudaGetLastError();
 }
 cudaError_t set_identity(cplx* A, int n, int lda, long long stride, int nb, cudaStream_t st) {

@@ -122,6 +122,8 @@ cudaError_t layer_form(const cplx* W, const cplx* QW, const cplx* kz, const cplx
                        const double* thick, int nb, int N, cplx* Mp, cplx* Mm, cplx* Rp, cplx* Rm, cudaStream_t st);
 cudaError_t layer_finish(const cplx* Tp, const cplx* Tm, int nb, int n, cplx* S11, cplx* S21, cudaStream_t st);
 cudaError_t blockdiag_dense(const cplx* d4, int nb, int N, cplx* D, cudaStream_t st);
+cudaError_t sym_project(const cplx* X, int nb, int n, const int* il, const cplx* cl, const int* ir, const cplx* cr,
+                        int G, int nkl, int nkr, cplx* out, cudaStream_t st);
 cudaError_t bd_left_mul(const cplx* d4, const cplx* X, int nb, int N, int ncols, cplx alpha, cplx beta, cplx* Y, cudaStream_t st);
 cudaError_t bd_right_mul(const cplx* d4, const cplx* X, int nb, int N, int nrows, cplx alpha, cplx beta, cplx* Y, cudaStream_t st);
 cudaError_t bd_add(const cplx* d4, int nb, int N, cplx alpha, cplx* D, cudaStream_t st);

@@ -442,26 +442,44 @@ class rcwa:
             self.layer_S12.append(s21); self.layer_S22.append(s11)      # single-layer symmetry
 
     # ------------------------------------------------------------------ symmetry-reduced layers (torcwa_b200/symmetry.py)
+    def _proj(self, basis, X, chi, left='E', right='E'):
+        return _lib.sym_project(X.contiguous(), *basis.tables(chi, left, right))
+
     def _symmetry_of(self, E):
-        """Basis of the symmetry this layer shares with the stack so far (None: general path)."""
+        """Basis of the symmetry this layer shares with the stack so far (None: general path).  A layer with less symmetry
+        than its predecessors (a C2 layer on top of a doubly mirror-symmetric one, ...) moves the whole stack to the common
+        subgroup: the earlier block layers are re-expressed in its basis (O(n^2) per layer); no common element at all
+        sends the stack to the general path."""
         if not self._sym_on or not hasattr(self, '_k0_zero') or self._sym is False:
             return None
-        found = symmetry.detect(E, int(self.order[0]), int(self.order[1]), self._k0_zero[0], self._k0_zero[1])
+        ox, oy = int(self.order[0]), int(self.order[1])
+        found = symmetry.detect(E, ox, oy, self._k0_zero[0], self._k0_zero[1])
         if found is None:
             self._sym = False                     # one layer without it: the whole stack runs the general path
             return None
         gens, thx, thy = found
         if self._sym is None:
-            self._sym = symmetry.Basis(int(self.order[0]), int(self.order[1]), gens, thx, thy, self._device)
-            Vfi = _lib.blockdiag_dense(self._Vf_inv.contiguous())
-            self._sym_G = {chi: self._sym.project(Vfi, chi, 'E', 'H') for chi in self._sym.chars}
+            self._set_basis(symmetry.Basis(ox, oy, gens, thx, thy, self._device))
             return self._sym
-        cand = symmetry.Basis.__new__(symmetry.Basis)
-        cand.gens, cand.thx, cand.thy, cand.ox, cand.oy = tuple(gens), thx, thy, int(self.order[0]), int(self.order[1])
-        if self._sym.same_as(cand):
-            return self._sym
-        self._sym = False
-        return None
+        common = symmetry.common_subgroup(self._sym.gens, (self._sym.thx, self._sym.thy), gens, (thx, thy))
+        if common is None:
+            self._sym = False
+            return None
+        if set(common) != set(self._sym.gens):
+            old = self._sym
+            self._set_basis(symmetry.Basis(ox, oy, common, old.thx, old.thy, self._device))
+            for layer in self._layers:
+                if isinstance(layer, _BlockLayer):
+                    dense = [old.unproject({c: v[k] for c, v in layer.blocks.items()}) for k in range(2)]
+                    layer.blocks = {chi: [self._proj(self._sym, d, chi) for d in dense] for chi in self._sym.chars}
+                    layer.basis = self._sym
+                    del dense
+        return self._sym
+
+    def _set_basis(self, basis):
+        self._sym = basis
+        Vfi = _lib.blockdiag_dense(self._Vf_inv.contiguous())
+        self._sym_G = {chi: self._proj(basis, Vfi, chi, 'E', 'H') for chi in basis.chars}
 
     def _patterned_layer_blocks(self, basis, P, Q, omega, thick):
         """One patterned layer solved block by block in the symmetry-adapted basis: the algebra of rcwa_layer_smatrix
@@ -473,8 +491,8 @@ class rcwa:
         for chi in basis.chars:
             by_size.setdefault(basis.sizes[chi], []).append(chi)
         for nk, chars in by_size.items():
-            Pk = torch.cat([basis.project(P, chi, 'E', 'H') for chi in chars], dim=0)
-            Qk = torch.cat([basis.project(Q, chi, 'H', 'E') for chi in chars], dim=0)
+            Pk = torch.cat([self._proj(basis, P, chi, 'E', 'H') for chi in chars], dim=0)
+            Qk = torch.cat([self._proj(basis, Q, chi, 'H', 'E') for chi in chars], dim=0)
             Gk = torch.cat([self._sym_G[chi] for chi in chars], dim=0)
             om, th = omega.repeat(len(chars)), thick.repeat(len(chars))
             A = _lib.zgemm(Pk, Qk)
@@ -640,29 +658,32 @@ class rcwa:
         half spaces that were built in the original basis (homogeneous layers: four diagonals) are projected first.  The
         global S-matrix is returned to the original basis at the end (O(n^2))."""
         basis = self._sym
-        dense_of = lambda bd4: _lib.blockdiag_dense(bd4.contiguous())
+        Sin_d = [_lib.blockdiag_dense(s.contiguous()) for s in self._Sin] if hasattr(self, 'Sin') else None
+        Sout_d = [_lib.blockdiag_dense(s.contiguous()) for s in self._Sout] if hasattr(self, 'Sout') else None
         Sblocks = {}
         for chi in basis.chars:
             def part(layer):
                 if isinstance(layer, _BlockLayer):
                     a, b = layer.blocks[chi]
                 else:
-                    a, b = basis.project(layer[0], chi), basis.project(layer[1], chi)
+                    a, b = self._proj(basis, layer[0], chi), self._proj(basis, layer[1], chi)
                 return [a, b, b, a]
             S = part(self._layers[0])
             for i in range(1, self.layer_N):
                 S, info_r = _lib.redheffer(S, part(self._layers[i]), slices=self._digits)
                 self._status.append(('star product with layer %d (block %s)' % (i, chi), info_r))
             if hasattr(self, 'Sin'):
-                S, info_r = _lib.redheffer([basis.project(dense_of(s), chi) for s in self._Sin], S, slices=self._digits)
+                S, info_r = _lib.redheffer([self._proj(basis, s, chi) for s in Sin_d], S, slices=self._digits)
                 self._status.append(('star product with the input half space (block %s)' % (chi,), info_r))
             if hasattr(self, 'Sout'):
-                S, info_r = _lib.redheffer(S, [basis.project(dense_of(s), chi) for s in self._Sout], slices=self._digits)
+                S, info_r = _lib.redheffer(S, [self._proj(basis, s, chi) for s in Sout_d], slices=self._digits)
                 self._status.append(('star product with the output half space (block %s)' % (chi,), info_r))
             Sblocks[chi] = S
+        del Sin_d, Sout_d
         self._check_status()
-        self._S = [basis.unproject({chi: Sblocks[chi][k] for chi in basis.chars}) for k in range(4)]
-        self.S = [self._pub(s) for s in self._S]
+        # the dense blocks in the original basis are formed on first access; S_parameters reads its entries off the blocks
+        self._S = _BlockS(basis, Sblocks)
+        self.S = self._S.view(self._pub)
         self.C = [[], []]
         self._modes_ready = False
 
@@ -852,14 +873,17 @@ class rcwa:
         N = self.order_N
         blk = {('forward', 'transmission'): 0, ('forward', 'reflection'): 1,
                ('backward', 'reflection'): 2, ('backward', 'transmission'): 3}[(direction, port)]
-        S = self._S[blk]
+        if isinstance(self._S, _BlockS):
+            entry = lambda a, b: self._S.entries(blk, a, b)
+        else:
+            entry = lambda a, b: self._S[blk][:, a, b]
         side = {0: ('out', 'in'), 1: ('in', 'in'), 2: ('out', 'out'), 3: ('in', 'out')}[blk]
         kx, ky = self._kx, self._ky
 
         if polarization in ['xx', 'yx', 'xy', 'yy']:
             oi2 = oi + N if polarization[0] == 'y' else oi
             ri2 = ri + N if polarization[1] == 'y' else ri
-            out = S[:, oi2, ri2]
+            out = entry(oi2, ri2)
             if power_norm:
                 kzs = {'in': self._kz_power(self.eps_in, self.mu_in, evanscent),
                        'out': self._kz_power(self.eps_out, self.mu_out, evanscent)}
@@ -890,7 +914,7 @@ class rcwa:
         r_inc, r_azi, r_ev = angles(ri, em[side[1]], rsign)
 
         def pick(a, b):
-            v = S[:, a, b]
+            v = entry(a, b)
             return torch.where(o_ev, torch.zeros_like(v), v)
 
         xx, xy = pick(oi, ri), pick(oi, ri + N)
@@ -921,6 +945,34 @@ class _BlockLayer:
 
     def __init__(self, blocks, basis=None):
         self.blocks, self.basis = blocks, basis
+
+
+class _BlockS:
+    """The four global S-matrix blocks held as symmetry blocks {character: [S11, S21, S12, S22]}; list-like over the dense
+    [B, n, n] matrices in the original basis, each formed on first access (S_parameters never needs them)."""
+
+    def __init__(self, basis, blocks, cache=None, pub=None):
+        self.basis, self.blocks, self._cache, self._pub = basis, blocks, ({} if cache is None else cache), pub
+
+    def view(self, pub):
+        return _BlockS(self.basis, self.blocks, self._cache, pub)
+
+    def entries(self, k, a, b):
+        return self.basis.entries({chi: v[k] for chi, v in self.blocks.items()}, a, b)
+
+    def __len__(self):
+        return 4
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(4)[k]]
+        k = range(4)[k]
+        if k not in self._cache:
+            self._cache[k] = self.basis.unproject({chi: v[k] for chi, v in self.blocks.items()})
+        return self._pub(self._cache[k]) if self._pub is not None else self._cache[k]
+
+    def __iter__(self):
+        return (self[k] for k in range(4))
 
 
 class _CatList:
