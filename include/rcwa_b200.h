@@ -102,10 +102,14 @@ int rcwa_tc_issue_entry(int slices, int levels, int group, int ring_pos, int ste
  *   1 / 2: tile of the QR row / column updates; 3: use the 128-thread tiles (default 1); 4: the QR pass
  *   kernel claims a whole SM per matrix (default 0); 5-7: count limits of the serial QR slices (Schur
  *   rotations, AED swaps, AED restore steps); 8: time budget of a serial QR slice in us (default 90);
- *   9: number of independently pipelined matrix groups of the QR phase (default 2); 10: skip the zero
+ *   9: number of independently pipelined matrix groups of the QR phase (default 2; one per 148 matrices, at most 4,
+ *   for batches above 296); 10: skip the zero
  *   k groups of the banded window unitaries in the QR update GEMMs (default 0, measured no gain);
  *   11: Hessenberg phase as two staggered half batches (default 0, measured slower); 12: triangular solves of the
- *   S-matrix stage on the tcgen05 engine too when gemm_slices >= 2 (default 0: measured slower at K = 512).  Call before
+ *   S-matrix stage on the tcgen05 engine too when gemm_slices >= 2 (default 0: measured slower at K = 512); 13: QR pass
+ *   as two launches per iteration -- bulge-chase windows, then the small dense solves at two CTAs per SM (0 = automatic:
+ *   batches above 296 matrices, 1 = never, 2 = always); 14 = 2: replay the QR loop from CUDA graphs of 8 iterations per
+ *   matrix group (default off: measured no gain at the default group count).  Call before
  *   asking for workspace sizes and enqueuing work; the numerical contract does not depend on them. */
 int rcwa_zgemm_batched_cfg(int cfg, int opa, int opb, int M, int N, int K, double alpha_re, double alpha_im,
                            const void* A, int lda, long long stride_a, const void* B, int ldb, long long stride_b,

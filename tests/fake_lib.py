@@ -67,9 +67,24 @@ def pq_assemble(eta, E, kx, ky, mu_scalar=None, Mc=None, nu=None):
     return P.contiguous(), Q.contiguous()
 
 
-def eig(A):
-    w, V = torch.linalg.eig(A)
-    return w, V, torch.zeros(A.shape[0], dtype=torch.int32)
+def eig(A, after_reduction=None):
+    """torch.linalg.eig per matrix, with one documented property of rcwa_eig that the host relies on: leading rows / columns
+    that are exactly decoupled (the extension of a symmetry block, rcwa._patterned_layer_blocks) stay in place -- their
+    eigenvalues come first, the eigenvector matrix is diag(I, W)."""
+    nb, n = A.shape[0], A.shape[1]
+    w = torch.zeros((nb, n), dtype=A.dtype)
+    V = torch.zeros_like(A)
+    for b in range(nb):
+        d = 0
+        while d < n - 1 and not bool(A[b, d, d + 1:].any()) and not bool(A[b, d + 1:, d].any()):
+            d += 1
+        wt, Vt = torch.linalg.eig(A[b, d:, d:])
+        w[b, :d], w[b, d:] = torch.diagonal(A[b])[:d], wt
+        V[b, range(d), range(d)] = 1.0
+        V[b, d:, d:] = Vt
+    if after_reduction is not None:
+        after_reduction()
+    return w, V, torch.zeros(nb, dtype=torch.int32)
 
 
 def kz_branch(lam):

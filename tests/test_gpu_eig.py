@@ -64,6 +64,30 @@ def test_eig_random(n):
         assert match_sorted(w[b].cpu().numpy(), ref[b].numpy()) < 1e-10 * float(ref[b].abs().max())
 
 
+@pytest.mark.parametrize("n,d", [(97, 1), (200, 2), (482, 1)])
+def test_eig_keeps_an_exactly_decoupled_leading_block_in_place(n, d):
+    """A = diag(1 ... 1, A1) with exact zeros in the couplings (how the host extends a symmetry block to the common batch
+    size, rcwa._patterned_layer_blocks): the first d eigenvalues are exactly 1, the eigenvector matrix is exactly
+    diag(I, W1), and (lam1, W1) solve A1 as well as a direct call does.  Mixed with unextended matrices in one batch."""
+    from torcwa_b200 import _lib
+    A1 = rnd(2, n - d, n - d, seed=n)
+    A = torch.zeros((3, n, n), dtype=torch.complex128, device=dev())
+    A[:2, d:, d:] = A1
+    A[:2, range(d), range(d)] = 1.0
+    A[2] = rnd(1, n, n, seed=n + 1)[0]
+    A0 = A.clone()
+    w, V, info = _lib.eig(A)
+    assert int(info.abs().max()) == 0
+    assert float((w[:2, :d] - 1).abs().max()) == 0.0
+    assert float(V[:2, :d, d:].abs().max()) == 0.0 and float(V[:2, d:, :d].abs().max()) == 0.0
+    assert float((V[:2, range(d), range(d)] - 1).abs().max()) == 0.0
+    R = A0 @ V - V * w[:, None, :]
+    assert float(R.abs().max() / A0.abs().max()) <= 1e-11 * n
+    w1, _, _ = _lib.eig(A1.clone())
+    for b in range(2):
+        assert match_sorted(w[b, d:].cpu().numpy(), w1[b].cpu().numpy()) <= 1e-9 * float(w1[b].abs().max())
+
+
 def test_eig_batch_entries_independent():
     """A batch of different sizes of difficulty must give the same answer as one at a time."""
     from torcwa_b200 import _lib
@@ -161,6 +185,31 @@ def test_eig_autograd_gauge_invariant_loss_matches_native():
         assert Ar.grad.dtype == torch.float64 and not torch.is_complex(Ar.grad)
     finally:
         torcwa_b200.Eig.broadening_parameter = old
+
+
+@pytest.mark.parametrize("keys", [{13: 2}, {13: 2, 14: 2}, {14: 2}, {13: 2, 9: 4}])
+def test_eig_launch_modes_give_identical_results(keys):
+    """Tuning keys 13 (QR pass as two launches per iteration: windows / small dense solves at two CTAs per SM), 14 (CUDA
+    graph replay of the QR loop) and 9 (matrix groups) only change how the same per-matrix work is scheduled: eigenvalues
+    and eigenvectors are bit-identical to the default mode, on matrices large enough for sweeps, AED and small blocks."""
+    from torcwa_b200 import _lib
+    lib = _lib.load()
+    A = rnd(24, 230, 230, seed=77)
+    A[3] = torch.diag(torch.arange(1.0, 231.0, dtype=torch.float64, device=dev()).to(torch.complex128))      # converged at once
+    try:
+        for k in (9, 13, 14):
+            lib.rcwa_set_tuning(k, 1 if k != 9 else 0)
+        w0, V0, i0 = _lib.eig(A.clone())
+        for k, v in keys.items():
+            lib.rcwa_set_tuning(k, v)
+        w1, V1, i1 = _lib.eig(A.clone())
+    finally:
+        for k in (9, 13, 14):
+            lib.rcwa_set_tuning(k, 0)
+    assert int(i0.abs().max()) == 0 and int(i1.abs().max()) == 0
+    assert torch.equal(w0, w1) and torch.equal(V0, V1)
+    R = A @ V1 - V1 * w1[:, None, :]
+    assert float(R.abs().max() / A.abs().max()) <= 1e-11 * 230
 
 
 def test_eig_is_reentrant_across_host_threads_and_bitwise_reproducible():

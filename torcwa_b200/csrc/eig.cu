@@ -66,6 +66,13 @@ DEV bool slice_expired(const Cta& c, long long deadline) {
     return e != 0;
 #endif
 }
+#define QR_MODE_ALL 0
+#define QR_MODE_WIN 1
+#define QR_MODE_SMALL 2
+#define QR_ROWS_SMALL ((QR_SMALL > QR_AED_W) ? QR_SMALL : QR_AED_W)     // rows of the window buffers a small dense solve needs
+#define QR_GRAPH_ITERS 8     // iterations of one group recorded into one CUDA graph (even: the window-unitary buffers alternate)
+#define QR_MAXG 8           // most independently pipelined groups of the QR phase (host_flag holds 2 ints per group)
+#define QR_SMS 148         // SMs of a B200 (the pass kernel runs one CTA per SM)
 #define QR_MAXSTALL 40     // sweeps without deflation before giving up on a matrix
 #define TV_NB 32           // eigenvector back-substitution block
 
@@ -409,8 +416,10 @@ struct QrScratch {
     cplx rot_s[QR_W];
 };
 
-HD size_t qr_pass_smem_bytes(int n) {
-    return 2 * (size_t)QR_W * QR_LD * sizeof(cplx) + sizeof(QrScratch) + (size_t)(QR_NS * (QR_NS + 1)) * sizeof(cplx) + (size_t)(n + 16) + 64;
+HD size_t qr_pass_smem_bytes(int n, int mode = QR_MODE_ALL) {
+    const size_t rows = (mode == QR_MODE_SMALL) ? QR_ROWS_SMALL : QR_W;
+    return 2 * rows * QR_LD * sizeof(cplx) + sizeof(QrScratch) + (size_t)(QR_NS * (QR_NS + 1)) * sizeof(cplx)
+           + ((mode == QR_MODE_SMALL) ? 0 : (size_t)(n + 16)) + 64;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -594,23 +603,31 @@ DEV void emit_window_gemms(cplx* H, int ldh, int n, cplx* Zm, int ldz, cplx* Ug,
 
 DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, QrState* stg,
                       cplx* Ug, cplx* Vg, cplx* Tg, ZGemmProblem* prob_rows, ZGemmProblem* prob_cols_main,
-                      ZGemmProblem* prob_cols, ZGemmProblem* prob_z, QrBudget bud) {
+                      ZGemmProblem* prob_cols, ZGemmProblem* prob_z, QrBudget bud, int mode = QR_MODE_ALL) {
+    // mode: QR_MODE_ALL -- one launch does whatever segment the matrix is in.  QR_MODE_WIN / QR_MODE_SMALL -- the same
+    // iteration as TWO launches: the first handles the sweep start and the bulge-chase windows (64-row window buffers,
+    // 512 threads, one CTA per SM), the second the time slices of the small dense solves (AED window, small active
+    // block: at most QR_ROWS_SMALL rows, mostly one warp at work), launched with less shared memory and fewer threads so
+    // that two of its CTAs share an SM.  A launch returns at once for matrices in a segment of the other kind.
     // Ug: this pass's window unitary (double-buffered by the host: its GEMMs may still run while the next
     //     pass works); Vg/Tg: persistent copies for the time-sliced AED / small-block solves.
     // prob_rows, prob_cols_main run on the main stream before the next pass; prob_cols, prob_z on the side
     // stream (they touch only rows above / columns of Z that later passes of a downward-moving chase never
     // read).  AED and small-block solves may be followed by a window that reaches upwards, so their column
     // update goes to the main stream.
+    const int rows = (mode == QR_MODE_SMALL) ? QR_ROWS_SMALL : QR_W;     // see qr_pass_smem_bytes()
     cplx* Hs = reinterpret_cast<cplx*>(c.smem);
-    cplx* Us = Hs + QR_W * QR_LD;
-    QrScratch* sc = reinterpret_cast<QrScratch*>(Us + QR_W * QR_LD);
+    cplx* Us = Hs + rows * QR_LD;
+    QrScratch* sc = reinterpret_cast<QrScratch*>(Us + rows * QR_LD);
     cplx* Ts = reinterpret_cast<cplx*>(sc + 1);                         // [QR_NS][QR_NS+1] shift block
-    unsigned char* negl = reinterpret_cast<unsigned char*>(Ts + QR_NS * (QR_NS + 1));   // [n] deflation flags
+    unsigned char* negl = reinterpret_cast<unsigned char*>(Ts + QR_NS * (QR_NS + 1));   // [n] deflation flags (not in QR_MODE_SMALL)
     QrState& st = sc->st;
 
-    if (c.tid == 0) { prob_rows->M = 0; prob_cols_main->M = 0; prob_cols->M = 0; prob_z->M = 0; st = *stg; }
+    // the second launch of an iteration must not clear what the first one emitted
+    if (c.tid == 0) { if (mode != QR_MODE_SMALL) { prob_rows->M = 0; prob_cols_main->M = 0; prob_cols->M = 0; prob_z->M = 0; } st = *stg; }
     CTA_SYNC();
     if (st.done) return;
+    if (mode != QR_MODE_ALL && (mode == QR_MODE_SMALL) != (st.phase == 2 || st.phase == 3)) return;
     long long tseg = QR_CLOCK();
     const long long deadline = (bud.cycles > 0) ? tseg + bud.cycles : 0;
     const bool ran0 = (st.phase == 0);
@@ -683,6 +700,10 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
     }
 
     if (ran0) QR_ACCOUNT(0);
+    if (mode == QR_MODE_WIN && (st.phase == 2 || st.phase == 3)) {        // the sweep start chose a small dense solve: next launch
+        if (c.tid == 0) *stg = st;
+        return;
+    }
 
     if (st.phase == 3) {
         // ---------------- AED: time slices of the window's Schur factorisation on a COPY (Tg, Ug), then
@@ -1103,13 +1124,13 @@ namespace {
 // ---------------------------------------------------------------- phase 2: QR passes
 __global__ void __launch_bounds__(512, 1)
 qr_pass_kernel(cplx* H, long long hstride, int ldh, int n, cplx* Z, long long zstride, int ldz, QrState* states,
-               cplx* U, cplx* Vg, cplx* Tg, ZGemmProblem* prows, ZGemmProblem* pcols_main, ZGemmProblem* pcolsz, QrBudget bud) {
+               cplx* U, cplx* Vg, cplx* Tg, ZGemmProblem* prows, ZGemmProblem* pcols_main, ZGemmProblem* pcolsz, QrBudget bud, int mode) {
     extern __shared__ __align__(16) char smem_raw[];
     const int b = blockIdx.x;
     Cta c = make_cta(b, smem_raw);
     qr_pass_body(c, H + (size_t)b * hstride, ldh, n, Z + (size_t)b * zstride, ldz, states + b,
                  U + (size_t)b * QR_W * QR_W, Vg + (size_t)b * QR_W * QR_W, Tg + (size_t)b * QR_W * QR_W,
-                 prows + b, pcols_main + b, pcolsz + 2 * b, pcolsz + 2 * b + 1, bud);
+                 prows + b, pcols_main + b, pcolsz + 2 * b, pcolsz + 2 * b + 1, bud, mode);
 }
 
 __global__ void qr_init_kernel(QrState* states, int n, int nb) {
@@ -1241,8 +1262,9 @@ EigWs carve(char* base, int n, int nb) {
 // (a few driver objects per thread; they die with the process).  Thread-local => re-entrant across host threads.
 struct EigStreams {
     bool ready;
-    cudaStream_t sa[4], sb[4];
-    cudaEvent_t ev_fork, ev_join[4], ev_pass[4][2], ev_side[4][2], ev[4][2];
+    cudaStream_t sa[QR_MAXG], sb[QR_MAXG];
+    cudaEvent_t ev_fork, ev_join[QR_MAXG], ev_pass[QR_MAXG][2], ev_side[QR_MAXG][2], ev[QR_MAXG][2];
+    cudaEvent_t cap_pass[QR_MAXG][2], cap_side[QR_MAXG][2];      // the same roles inside a stream capture (CUDA graph of the QR loop)
 };
 EigStreams* eig_streams() {
     static thread_local EigStreams cache[16] = {};
@@ -1253,7 +1275,7 @@ EigStreams* eig_streams() {
     int prio_lo = 0, prio_hi = 0;
     if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) return nullptr;
     bool ok = cudaEventCreateWithFlags(&r.ev_fork, cudaEventDisableTiming) == cudaSuccess;
-    for (int g = 0; g < 4 && ok; ++g) {
+    for (int g = 0; g < QR_MAXG && ok; ++g) {
         ok = ok && cudaStreamCreateWithPriority(&r.sa[g], cudaStreamNonBlocking, prio_hi) == cudaSuccess;
         ok = ok && cudaStreamCreateWithPriority(&r.sb[g], cudaStreamNonBlocking, prio_lo) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&r.ev_join[g], cudaEventDisableTiming) == cudaSuccess;
@@ -1261,6 +1283,8 @@ EigStreams* eig_streams() {
             ok = ok && cudaEventCreateWithFlags(&r.ev_pass[g][q], cudaEventDisableTiming) == cudaSuccess;
             ok = ok && cudaEventCreateWithFlags(&r.ev_side[g][q], cudaEventDisableTiming) == cudaSuccess;
             ok = ok && cudaEventCreateWithFlags(&r.ev[g][q], cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&r.cap_pass[g][q], cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&r.cap_side[g][q], cudaEventDisableTiming) == cudaSuccess;
         }
     }
     if (!ok) return nullptr;
@@ -1392,8 +1416,14 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
     // The batch is split into G groups with their own stream pairs: the chain of one group (pass -> row GEMM ->
     // next pass) leaves the tensor pipes idle while its pass kernel runs and most SMs idle while its row GEMM
     // runs; the other groups' chains fill those gaps.
-    int G = gemm_get_tuning(9) > 0 ? gemm_get_tuning(9) : 2;
-    if (G > 4) G = 4;
+    // Default: two groups; more when a group's pass launch (one CTA per matrix, one CTA per SM) would not fit in one wave.
+    // Many small matrices (the blocks of a symmetry-reduced layer: more matrices than two waves of SMs) make the QR phase
+    // bound by the SM time of the pass kernel, 2/3 of it in the one-warp small dense solves: run those as a second launch
+    // with two CTAs per SM (tuning key 13: 0 = automatic, 1 = one launch, 2 = two launches).
+    const size_t smem_small = qr_pass_smem_bytes(n, QR_MODE_SMALL);
+    const bool split = (gemm_get_tuning(13) == 2) || (gemm_get_tuning(13) == 0 && nb > 2 * QR_SMS);
+    int G = gemm_get_tuning(9) > 0 ? gemm_get_tuning(9) : ((nb > 2 * QR_SMS) ? (nb + QR_SMS - 1) / QR_SMS : 2);
+    if (G > QR_MAXG) G = QR_MAXG;
     while (G > 1 && nb < 8 * G) --G;
     // Internal streams and events are created ONCE per host thread and device and reused by later calls (thread-local
     // cache below): no per-call cudaStreamCreate / Destroy, nothing shared between host threads.  Whatever happens below,
@@ -1404,12 +1434,12 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
     cudaStream_t* sa = res->sa; cudaStream_t* sb = res->sb;
     cudaEvent_t ev_fork = res->ev_fork;
     cudaEvent_t (*ev_pass)[2] = res->ev_pass; cudaEvent_t (*ev_side)[2] = res->ev_side; cudaEvent_t (*ev)[2] = res->ev;
-    int gb0[5];
+    int gb0[QR_MAXG + 1];
     for (int g = 0; g <= G; ++g) gb0[g] = (int)((long long)nb * g / G);
     EK(cudaEventRecord(ev_fork, user_st));
     int* hf = const_cast<int*>(host_flag);
     struct Join {
-        EigStreams* r; cudaStream_t user; int G; bool side_used[4][2];
+        EigStreams* r; cudaStream_t user; int G; bool side_used[QR_MAXG][2];
         void run() {
             for (int g = 0; g < G; ++g) {
                 for (int q = 0; q < 2; ++q) if (side_used[g][q]) cudaStreamWaitEvent(r->sa[g], r->ev_side[g][q], 0);
@@ -1419,54 +1449,114 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
             G = 0;
         }
         ~Join() { run(); }      // also on every early error return: never leave forked work un-joined behind the caller's stream
-    } join_guard = {res, user_st, G, {{false, false}, {false, false}, {false, false}, {false, false}}};
+    } join_guard = {res, user_st, G, {}};
     for (int g = 0; g < G; ++g) {
         EK(cudaStreamWaitEvent(sa[g], ev_fork, 0));
         for (int q = 0; q < 2; ++q)
             if (hf) hf[g * 2 + q] = gb0[g + 1] - gb0[g];
     }
     long long group = 0;
-    bool fin[4] = {false, false, false, false};
+    bool fin[QR_MAXG] = {};
     int nfin = 0;
     const size_t ustride = (size_t)QR_W * QR_W * nb;
     const size_t w2 = (size_t)QR_W * QR_W;
-    for (long long it = 0; it < max_passes && nfin < G; ++it) {
-        const int buf = (int)(it & 1);
-        for (int g = 0; g < G; ++g) {
-            if (fin[g]) continue;
-            const int b0 = gb0[g], nbg = gb0[g + 1] - gb0[g];
-            cudaStream_t sm = sa[g], ss = sb[g];
-            ZGemmProblem* pcz = ws.pcolsz + (size_t)buf * 2 * nb + 2 * (size_t)b0;
-            if (it >= 2) EK(cudaStreamWaitEvent(sm, ev_side[g][buf], 0));          // U[buf] / descriptors[buf] are free again
+    // One iteration of group g: pass launch(es), the row-panel GEMM and the main-stream column GEMM on sm, the bulk column / Z
+    // GEMMs on ss.  wait2 / wait1: whether the side GEMMs of iterations it-2 / it-1 exist and must be waited for (evs = the
+    // side events, evp = the pass events: the cached pair of the group, or the capture pair when this is being recorded
+    // into a CUDA graph).
+    auto enqueue = [&](int g, int buf, bool wait2, bool wait1, cudaEvent_t* evp, cudaEvent_t* evs) -> cudaError_t {
+        const int b0 = gb0[g], nbg = gb0[g + 1] - gb0[g];
+        cudaStream_t sm = sa[g], ss = sb[g];
+        ZGemmProblem* pcz = ws.pcolsz + (size_t)buf * 2 * nb + 2 * (size_t)b0;
+        if (wait2) EK(cudaStreamWaitEvent(sm, evs[buf], 0));                   // U[buf] / descriptors[buf] are free again
+        if (!split) {
             qr_pass_kernel<<<nbg, 512, smem, sm>>>(A + (size_t)b0 * ms, ms, n, n, ws.Z + (size_t)b0 * ms, ms, n, ws.states + b0,
                                                    ws.U + buf * ustride + b0 * w2, ws.Vg + b0 * w2, ws.Tg + b0 * w2,
-                                                   ws.prows + b0, ws.pcols_main + b0, pcz, bud);
-            EK(cudaEventRecord(ev_pass[g][buf], sm));
-            EK(zgemm_grouped(cfg_rows_b, OP_H, OP_N, ws.prows + b0, nbg, max_tiles_rows, one, zero, sm));
-            // A main-stream column update (last window of a sweep, AED, small block) overlaps the columns of the
-            // previous window's side-stream column update and must be applied AFTER it: wait for the previous
-            // iteration's side GEMMs.  (Without this the order was only a matter of timing -- the low-priority side
-            // GEMM normally finishes long before -- and a second group's kernels delaying it corrupted results.)
-            if (it >= 1) EK(cudaStreamWaitEvent(sm, ev_side[g][buf ^ 1], 0));
-            EK(zgemm_grouped(cfg_cz_b, OP_N, OP_N, ws.pcols_main + b0, nbg, max_tiles_cz, one, zero, sm));
-            EK(cudaStreamWaitEvent(ss, ev_pass[g][buf], 0));
-            EK(zgemm_grouped(cfg_cz_b, OP_N, OP_N, pcz, 2 * nbg, max_tiles_cz, one, zero, ss));
-            EK(cudaEventRecord(ev_side[g][buf], ss));
-            join_guard.side_used[g][buf] = true;
+                                                   ws.prows + b0, ws.pcols_main + b0, pcz, bud, QR_MODE_ALL);
+        } else {
+            qr_pass_kernel<<<nbg, 512, smem, sm>>>(A + (size_t)b0 * ms, ms, n, n, ws.Z + (size_t)b0 * ms, ms, n, ws.states + b0,
+                                                   ws.U + buf * ustride + b0 * w2, ws.Vg + b0 * w2, ws.Tg + b0 * w2,
+                                                   ws.prows + b0, ws.pcols_main + b0, pcz, bud, QR_MODE_WIN);
+            qr_pass_kernel<<<nbg, 256, smem_small, sm>>>(A + (size_t)b0 * ms, ms, n, n, ws.Z + (size_t)b0 * ms, ms, n, ws.states + b0,
+                                                         ws.U + buf * ustride + b0 * w2, ws.Vg + b0 * w2, ws.Tg + b0 * w2,
+                                                         ws.prows + b0, ws.pcols_main + b0, pcz, bud, QR_MODE_SMALL);
         }
-        if (hf && (it % poll) == poll - 1) {
-            const int slot = (int)(group & 1);
+        EK(cudaEventRecord(evp[buf], sm));
+        EK(zgemm_grouped(cfg_rows_b, OP_H, OP_N, ws.prows + b0, nbg, max_tiles_rows, one, zero, sm));
+        // A main-stream column update (last window of a sweep, AED, small block) overlaps the columns of the
+        // previous window's side-stream column update and must be applied AFTER it: wait for the previous
+        // iteration's side GEMMs.  (Without this the order was only a matter of timing -- the low-priority side
+        // GEMM normally finishes long before -- and a second group's kernels delaying it corrupted results.)
+        if (wait1) EK(cudaStreamWaitEvent(sm, evs[buf ^ 1], 0));
+        EK(zgemm_grouped(cfg_cz_b, OP_N, OP_N, ws.pcols_main + b0, nbg, max_tiles_cz, one, zero, sm));
+        EK(cudaStreamWaitEvent(ss, evp[buf], 0));
+        EK(zgemm_grouped(cfg_cz_b, OP_N, OP_N, pcz, 2 * nbg, max_tiles_cz, one, zero, ss));
+        EK(cudaEventRecord(evs[buf], ss));
+        return cudaSuccess;
+    };
+    auto poll_groups = [&]() -> cudaError_t {
+        const int slot = (int)(group & 1);
+        for (int g = 0; g < G; ++g) {
+            if (fin[g]) continue;
+            if (group >= 1) {       // examine the previous poll's count (its copy was enqueued one poll period ago)
+                EK(cudaEventSynchronize(ev[g][slot ^ 1]));
+                if (hf[g * 2 + (slot ^ 1)] == 0) { fin[g] = true; ++nfin; continue; }
+            }
+            qr_count_kernel<<<1, 128, 0, sa[g]>>>(ws.states + gb0[g], gb0[g + 1] - gb0[g], ws.flag + g * 2 + slot);
+            EK(cudaMemcpyAsync(hf + g * 2 + slot, ws.flag + g * 2 + slot, sizeof(int), cudaMemcpyDeviceToHost, sa[g]));
+            EK(cudaEventRecord(ev[g][slot], sa[g]));
+        }
+        ++group;
+        return cudaSuccess;
+    };
+    // Optional (tuning key 14 = 2): record QR_GRAPH_ITERS iterations of a group ONCE as a CUDA graph (after two directly
+    // enqueued iterations, which also take care of one-time kernel attributes) and replay it.  Inside the graph the side
+    // GEMMs overlap the following passes exactly as in the direct loop; replays of one group serialise on its main stream.
+    // Measured on 512 matrices of n = 481 (profiles/r2_summary.md): the direct loop costs the host ~60 us of API time per
+    // group and iteration, so 6 or 8 groups are host-bound (988 / 1148 ms against 872 ms with 4); graphs remove that (885
+    // / 877 ms) -- and show that 4 directly enqueued groups already sit on the device-side bound (pass SM time + GEMM time,
+    // which cannot share an SM's shared memory).  Off by default.  Any failure while recording falls back to the direct loop.
+    long long it = 0;
+    bool graphs = hf && gemm_get_tuning(14) == 2;
+    cudaGraphExec_t gexec[QR_MAXG] = {};
+    struct GraphGuard { cudaGraphExec_t* e; ~GraphGuard() { for (int g = 0; g < QR_MAXG; ++g) if (e[g]) cudaGraphExecDestroy(e[g]); } } graph_guard = {gexec};
+    if (graphs) {
+        for (; it < 2; ++it)
+            for (int g = 0; g < G; ++g) {
+                EK(enqueue(g, (int)(it & 1), false, it >= 1, ev_pass[g], ev_side[g]));
+                join_guard.side_used[g][it & 1] = true;
+            }
+        for (int g = 0; g < G && graphs; ++g) {
+            EK(cudaStreamWaitEvent(sa[g], ev_side[g][0], 0));
+            EK(cudaStreamWaitEvent(sa[g], ev_side[g][1], 0));
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(sa[g], cudaStreamCaptureModeThreadLocal) != cudaSuccess) { graphs = false; break; }
+            cudaError_t ce = cudaSuccess;
+            for (int j = 0; j < QR_GRAPH_ITERS && ce == cudaSuccess; ++j)
+                ce = enqueue(g, j & 1, j >= 2, j >= 1, res->cap_pass[g], res->cap_side[g]);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sa[g], res->cap_side[g][0], 0);      // join the side stream
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sa[g], res->cap_side[g][1], 0);
+            const cudaError_t ee = cudaStreamEndCapture(sa[g], &graph);
+            if (ce == cudaSuccess && ee == cudaSuccess && graph) ce = cudaGraphInstantiate(&gexec[g], graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (ce != cudaSuccess || ee != cudaSuccess) { cudaGetLastError(); gexec[g] = nullptr; graphs = false; }
+        }
+    }
+    if (graphs) {
+        for (; it < max_passes && nfin < G; it += QR_GRAPH_ITERS) {
+            for (int g = 0; g < G; ++g)
+                if (!fin[g]) EK(cudaGraphLaunch(gexec[g], sa[g]));
+            if (((it - 2) / QR_GRAPH_ITERS) % (poll / QR_GRAPH_ITERS) == (poll / QR_GRAPH_ITERS) - 1) EK(poll_groups());
+        }
+    } else {
+        for (; it < max_passes && nfin < G; ++it) {
+            const int buf = (int)(it & 1);
             for (int g = 0; g < G; ++g) {
                 if (fin[g]) continue;
-                if (group >= 1) {       // examine the previous group's count (its copy was enqueued one poll period ago)
-                    EK(cudaEventSynchronize(ev[g][slot ^ 1]));
-                    if (hf[g * 2 + (slot ^ 1)] == 0) { fin[g] = true; ++nfin; continue; }
-                }
-                qr_count_kernel<<<1, 128, 0, sa[g]>>>(ws.states + gb0[g], gb0[g + 1] - gb0[g], ws.flag + g * 2 + slot);
-                EK(cudaMemcpyAsync(hf + g * 2 + slot, ws.flag + g * 2 + slot, sizeof(int), cudaMemcpyDeviceToHost, sa[g]));
-                EK(cudaEventRecord(ev[g][slot], sa[g]));
+                EK(enqueue(g, buf, it >= 2, it >= 1, ev_pass[g], ev_side[g]));
+                join_guard.side_used[g][buf] = true;
             }
-            ++group;
+            if (hf && (it % poll) == poll - 1) EK(poll_groups());
         }
     }
     // join all internal streams back into the caller's stream before anything reads H or Z

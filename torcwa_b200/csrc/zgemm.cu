@@ -352,11 +352,16 @@ static int g_tune[16] = {1, GEMM_TILE_64x64, GEMM_TILE_64x64, 1, 0, 0, 0, 0, 0, 
 //   4: the QR pass kernel claims a whole SM per matrix (no GEMM CTA co-resident)  (default 0)
 //   5 / 6 / 7: per-launch count limits of the QR pass: small-Schur rotations, AED swaps, AED restore steps (0 = default)
 //   8: time budget of a serial QR slice in microseconds (0 = default 90, < 0 = count limits only)
-//   9: number of independently pipelined matrix groups in the QR phase (0 = default 2)
+//   9: number of independently pipelined matrix groups in the QR phase (0 = default: 2, or one per wave of 148 matrices up to 4)
 //  10: skip the zero k groups of the banded window unitaries in the QR update GEMMs (default 0: measured no gain --
 //      34 % fewer MMAs, same time: those launches are bound by their load/store phases and by sharing SMs with the pass kernels)
 //  11: run the Hessenberg phase as two staggered half batches on two streams (default 0: measured 9 % SLOWER --
 //      the latency-bound per-column kernel does not shrink with the batch and the halves do not stay in anti-phase)
+//  12: triangular solves of the S-matrix stage on tcgen05 too (default 0: measured slower, profiles/r2_summary.md section 3)
+//  13: QR pass as two launches per iteration, bulge-chase windows / small dense solves (0 = automatic: when the batch
+//      exceeds two waves of SMs, 1 = never, 2 = always)
+//  14: 2 = replay the QR loop of a group from a CUDA graph of 8 iterations instead of enqueuing every launch (default off:
+//      measured no gain with the default group count, eig.cu)
 void gemm_set_tuning(int key, int value) { if (key >= 0 && key < 16) g_tune[key] = value; }
 int gemm_get_tuning(int key) { return (key >= 0 && key < 16) ? g_tune[key] : 0; }
 

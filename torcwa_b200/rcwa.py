@@ -150,6 +150,7 @@ class rcwa:
         self._sym_on = bool(symmetry_reduction)
         self._sym = None           # symmetry.Basis shared by the block layers of this stack
         self._sym_G = None         # per block: Vf^-1 in adapted coordinates
+        self._pad_err = []         # per extended block: max |coupling| to the decoupled extension entries; must be exactly 0
         self._kz_min = []          # per patterned layer: min |kz| / max |kz| over the batch (device scalar), read with the status words
 
         # ---- pipelined sub-batches (children); the parent keeps the O(N) per-order state and delegates the dense stages
@@ -484,45 +485,66 @@ class rcwa:
     def _patterned_layer_blocks(self, basis, P, Q, omega, thick):
         """One patterned layer solved block by block in the symmetry-adapted basis: the algebra of rcwa_layer_smatrix
         (V = Q W Kz^-1, T+- = R+- M+-^-1, S11 = T+ + T-, S21 = T+ - T- - I) on matrices of ~n/2 or ~n/4.
-        Blocks of equal size are stacked along the batch dimension so that each C-ABI call sees one larger batch."""
+        All blocks go through the C-ABI calls as ONE batch (the QR phase of rcwa_eig is a chain of short launches whose
+        latency hides only behind other matrices): a block one or two rows smaller than the largest is extended at the FRONT
+        by an exactly decoupled diagonal entry (P' = diag(1, P), Q' = diag(1, Q), Vf^-1' = diag(1, G)).  Row / column 0 is
+        then never touched by a Householder reflector of the Hessenberg reduction (its first column is already zero), the
+        QR iteration sees a split at the top, and every later operator stays diag(t, T) with exact zeros in the couplings
+        -- the block's results are the trailing sub-matrices, bit for bit what the unextended block would give up to the
+        order of floating-point summation."""
         B = self._B
         out, kzs, Ws, infos = {}, {}, {}, []
-        by_size = {}
-        for chi in basis.chars:
-            by_size.setdefault(basis.sizes[chi], []).append(chi)
-        for nk, chars in by_size.items():
-            Pk = torch.cat([self._proj(basis, P, chi, 'E', 'H') for chi in chars], dim=0)
-            Qk = torch.cat([self._proj(basis, Q, chi, 'H', 'E') for chi in chars], dim=0)
-            Gk = torch.cat([self._sym_G[chi] for chi in chars], dim=0)
-            om, th = omega.repeat(len(chars)), thick.repeat(len(chars))
-            A = _lib.zgemm(Pk, Qk)
-            del Pk
-            lam, W, info = self._eig(A)
-            del A
-            infos.append(info)
-            kz = _lib.kz_branch(lam)
-            ka = kz.abs()
-            self._kz_min.append((ka.amin(dim=1) / ka.amax(dim=1)).min())
-            V = _lib.zgemm(Qk, W) / kz[:, None, :]
-            del Qk
-            Bm = _lib.zgemm(Gk, V)
-            del V, Gk
-            X = torch.exp(1j * (om * th)[:, None] * kz)[:, None, :]
-            Rp, Rm = W * (1 + X), W * (X - 1)
-            Mp, Mm = Rp + Bm * (1 - X), W * (1 - X) + Bm * (1 + X)
-            del Bm
-            Tp, i1 = _lib.right_solve(Rp, Mp)
-            del Rp, Mp
-            Tm, i2 = _lib.right_solve(Rm, Mm)
-            del Rm, Mm
-            infos += [i1, i2]
-            eye = torch.eye(nk, dtype=_C, device=self._device)
-            S11, S21 = Tp + Tm, Tp - Tm - eye
-            del Tp, Tm
+        chars = basis.chars
+        nk = max(basis.sizes.values())
+        pad = {chi: nk - basis.sizes[chi] for chi in chars}
+
+        def stacked(fn, dummy):
+            """the blocks of all characters as ONE batch [len(chars) B, nk, nk]: a block smaller than the largest is
+            extended at the FRONT by decoupled diagonal entries `dummy` (see _patterned_layer_blocks.__doc__)"""
+            if not any(pad.values()):
+                return torch.cat([fn(chi) for chi in chars], dim=0)
+            X = torch.zeros((len(chars) * B, nk, nk), dtype=_C, device=self._device)
             for j, chi in enumerate(chars):
-                sl = slice(j * B, (j + 1) * B)
-                out[chi] = [S11[sl].contiguous(), S21[sl].contiguous()]
-                kzs[chi], Ws[chi] = kz[sl], W[sl]
+                d = pad[chi]
+                X[j * B:(j + 1) * B, d:, d:] = fn(chi)
+                if d:
+                    X[j * B:(j + 1) * B, range(d), range(d)] = dummy
+            return X
+        Pk = stacked(lambda chi: self._proj(basis, P, chi, 'E', 'H'), 1.0)
+        Qk = stacked(lambda chi: self._proj(basis, Q, chi, 'H', 'E'), 1.0)
+        Gk = stacked(lambda chi: self._sym_G[chi], 1.0)
+        om, th = omega.repeat(len(chars)), thick.repeat(len(chars))
+        A = _lib.zgemm(Pk, Qk)
+        del Pk
+        lam, W, info = self._eig(A)
+        del A
+        infos.append(info)
+        kz = _lib.kz_branch(lam)
+        ka = kz.abs()
+        self._kz_min.append((ka.amin(dim=1) / ka.amax(dim=1)).min())
+        V = _lib.zgemm(Qk, W) / kz[:, None, :]
+        del Qk
+        Bm = _lib.zgemm(Gk, V)
+        del V, Gk
+        X = torch.exp(1j * (om * th)[:, None] * kz)[:, None, :]
+        Rp, Rm = W * (1 + X), W * (X - 1)
+        Mp, Mm = Rp + Bm * (1 - X), W * (1 - X) + Bm * (1 + X)
+        del Bm
+        Tp, i1 = _lib.right_solve(Rp, Mp)
+        del Rp, Mp
+        Tm, i2 = _lib.right_solve(Rm, Mm)
+        del Rm, Mm
+        infos += [i1, i2]
+        eye = torch.eye(nk, dtype=_C, device=self._device)
+        S11, S21 = Tp + Tm, Tp - Tm - eye
+        del Tp, Tm
+        for j, chi in enumerate(chars):
+            sl, d = slice(j * B, (j + 1) * B), pad[chi]
+            out[chi] = [S11[sl, d:, d:].contiguous(), S21[sl, d:, d:].contiguous()]
+            kzs[chi], Ws[chi] = kz[sl, d:], W[sl, d:, d:]
+            if d:       # the extension must have stayed exactly decoupled (checked with the other status words, _check_status)
+                self._pad_err.append(torch.stack([W[sl, :d, d:].abs().amax(), W[sl, d:, :d].abs().amax(), (lam[sl, :d] - 1).abs().amax(),
+                                                  S11[sl, :d, d:].abs().amax(), S11[sl, d:, :d].abs().amax()]).amax())
         info_all = torch.stack([i.reshape(len(i) // B, B).abs().amax(dim=0) for i in infos]).amax(dim=0).to(torch.int32)
         self.eig_info.append(info_all)
         self._status.append(('symmetry-reduced layer %d: eigendecomposition or coupling-matrix factorisation failed' % self.layer_N, info_all))
@@ -683,7 +705,7 @@ class rcwa:
         self._check_status()
         # the dense blocks in the original basis are formed on first access; S_parameters reads its entries off the blocks
         self._S = _BlockS(basis, Sblocks)
-        self.S = self._S.view(self._pub)
+        self.S = self._S.view(self)
         self.C = [[], []]
         self._modes_ready = False
 
@@ -710,6 +732,11 @@ class rcwa:
                               'formed as Q W Kz^-1 and lose accuracy there; the reference\'s default P^-1 W Kz stays finite' % ratio,
                               UserWarning)
             self._kz_min = []
+        if self._pad_err:
+            leak = float(torch.stack(self._pad_err).max())
+            self._pad_err = []
+            if leak != 0.0:
+                raise RuntimeError('torcwa_b200 internal error: the decoupled extension of a symmetry block picked up a coupling of %.3e' % leak)
         worst = torch.stack([i.to(self._device).abs().max() for _, i in self._status])
         if int(worst.max()) != 0:
             k = int(torch.nonzero(worst)[0])
@@ -951,11 +978,15 @@ class _BlockS:
     """The four global S-matrix blocks held as symmetry blocks {character: [S11, S21, S12, S22]}; list-like over the dense
     [B, n, n] matrices in the original basis, each formed on first access (S_parameters never needs them)."""
 
-    def __init__(self, basis, blocks, cache=None, pub=None):
-        self.basis, self.blocks, self._cache, self._pub = basis, blocks, ({} if cache is None else cache), pub
+    def __init__(self, basis, blocks, cache=None, sim=None):
+        # `sim` (public view only): weak, like _LazyDense -- a strong reference would make sim <-> sim.S a cycle and keep a
+        # finished simulation's multi-GB blocks alive until the cyclic garbage collector happens to run
+        self.basis, self.blocks, self._cache = basis, blocks, ({} if cache is None else cache)
+        self._sim = weakref.ref(sim) if sim is not None else None
 
-    def view(self, pub):
-        return _BlockS(self.basis, self.blocks, self._cache, pub)
+    def view(self, sim):
+        """the public list `sim.S`: same blocks and cache, entries passed through sim._pub (dtype / batch squeeze)"""
+        return _BlockS(self.basis, self.blocks, self._cache, sim)
 
     def entries(self, k, a, b):
         return self.basis.entries({chi: v[k] for chi, v in self.blocks.items()}, a, b)
@@ -969,7 +1000,7 @@ class _BlockS:
         k = range(4)[k]
         if k not in self._cache:
             self._cache[k] = self.basis.unproject({chi: v[k] for chi, v in self.blocks.items()})
-        return self._pub(self._cache[k]) if self._pub is not None else self._cache[k]
+        return self._sim()._pub(self._cache[k]) if self._sim is not None else self._cache[k]
 
     def __iter__(self):
         return (self[k] for k in range(4))
