@@ -9,6 +9,7 @@ from torcwa_b200 import _lib
 ap = argparse.ArgumentParser()
 ap.add_argument("--points", type=int, default=128)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--max-chunks", type=int, default=4)
 ap.add_argument("--groups", type=int, default=0, help="QR groups per rcwa_eig call (tuning key 9; 0 = automatic)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -32,7 +33,7 @@ def step(s):
     sl = (torch.arange(a.points, device=dev) + s * a.points) % 512
     return bench.run_step(grids[sl], freq[sl], case, dev, None)
 step(0); torch.cuda.synchronize()
-nchunks = 512 // a.points
+nchunks = min(512 // a.points, a.max_chunks)
 for rep in range(a.reps):
     for s in range(nchunks):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
