@@ -141,6 +141,63 @@ def test_finished_simulation_is_freed_without_the_cycle_collector(cpu_double, sy
         gc.enable()
 
 
+@pytest.mark.parametrize("order,inc,azi,expect", [([4, 2], 0.0, 0.0, ("x", "y")), ([2, 3], 0.35, 0.0, ("y",)), ([3, 2], 0.35, np.pi / 2, ("x",)),
+                                                   ([3, 3], 0.35, 0.6, None)])
+def test_symmetry_follows_the_illumination_and_rectangular_truncations(cpu_double, order, inc, azi, expect):
+    """A doubly mirror-symmetric cell: normal incidence keeps both mirrors, incidence in the xz plane (ky0 = 0) only the
+    mirror in y, in the yz plane only the mirror in x, a skew azimuth none; rectangular truncations (ox != oy).  Whatever
+    is used, the result equals the general path."""
+    case = dict(C.CASES["ex1_o3"], order=order, inc=inc, azi=azi)
+    mk = lambda sym: C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, symmetry_reduction=sym, **kw), case, torch.complex128)
+    a, b = mk(None), mk(False)
+    found = a._sym.gens if a._sym not in (None, False) else None
+    assert found == expect
+    for k in range(4):
+        assert relfro(a.S[k].numpy(), b.S[k].numpy()) <= 1e-11
+    assert np.abs(C.probe(a) - C.probe(b)).max() <= 1e-12
+
+
+def test_unanalysed_layers_send_the_stack_to_the_general_path(cpu_double):
+    """A symmetric patterned layer (solved in blocks) followed by (a) a layer with patterned permeability, (b) a layer on the
+    differentiable pipeline: neither is analysed for symmetry, so the stack is cascaded in the original basis -- same
+    S-matrix as with the reduction switched off, and the gradient still flows."""
+    case = C.CASES["ex1_o3"]
+    cd = torch.complex128
+    d0, grid0 = C.build_layers(case, cd)[0]
+    g = torch.Generator().manual_seed(11)
+    mu_grid = torch.complex(1.0 + 0.4 * torch.rand(grid0.shape, generator=g, dtype=torch.float64), torch.zeros(grid0.shape, dtype=torch.float64))
+    rho0 = torch.rand(grid0.shape, generator=g, dtype=torch.float64)
+
+    def run(sym, kind):
+        sim = cpu_double.rcwa(freq=torch.tensor(1.0 / case["lam"], dtype=torch.float64), order=case["order"], L=case["L"], dtype=cd, device=CPU,
+                              symmetry_reduction=sym)
+        sim.add_input_layer(eps=case["eps_in"])
+        sim.set_incident_angle(0.0, 0.0)
+        sim.add_layer(thickness=d0, eps=grid0)
+        first_in_blocks = sim._sym not in (None, False)
+        rho = rho0.clone().requires_grad_(kind == "diff")
+        if kind == "mu":
+            sim.add_layer(thickness=80.0, eps=grid0 * 0.5 + 1.0, mu=mu_grid)
+        else:
+            sim.add_layer(thickness=80.0, eps=(1.0 + 3.0 * rho).to(cd))
+        sim.solve_global_smatrix()
+        t = torch.cat([sim.S_parameters(orders=[0, 0], polarization=p) for p in ("xx", "yy", "yx")])    # (1, 0) is evanescent here
+        grad = None
+        if kind == "diff":
+            (t.abs() ** 2).sum().backward()
+            grad = rho.grad.clone()
+        return sim, t.detach(), grad, first_in_blocks
+    for kind in ("mu", "diff"):
+        a, ta, ga, blocks_a = run(None, kind)
+        b, tb, gb, blocks_b = run(False, kind)
+        assert blocks_a and not blocks_b and a._sym is False
+        assert float((ta - tb).abs().max()) <= 1e-12
+        for k in range(4):
+            assert relfro(a.S[k].detach().numpy(), b.S[k].detach().numpy()) <= 1e-11
+        if kind == "diff":
+            assert float((ga - gb).abs().max()) <= 1e-10 * float(gb.abs().max())
+
+
 def test_symmetry_reduced_batched_sweep(cpu_double):
     """Batched (no stored intermediates): per-point results of the block path == the general path."""
     case = C.CASES["ex1_o3"]

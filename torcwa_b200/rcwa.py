@@ -362,6 +362,10 @@ class rcwa:
         diff = any(isinstance(v, torch.Tensor) and v.requires_grad for v in (eps, mu, thickness))
         if diff:
             self._diff = True
+        if (diff and not (he and hm)) or not hm:
+            # layers whose symmetry is not analysed (differentiable pipeline, patterned permeability): the stack is cascaded in
+            # the original basis; block layers added so far are returned to it in solve_global_smatrix
+            self._sym = False
         blocks = None
         if he and hm:
             S11, S21, kz, Qbd = self._homogeneous_layer(self._b(eps), self._b(mu), omega, thick, diff)
@@ -644,14 +648,12 @@ class rcwa:
             self.C = [[], []]
             return
         if self._diff:
+            self._dense_layers()
             return self._solve_global_smatrix_differentiable()
         if any(isinstance(l, _BlockLayer) for l in self._layers):
             if self._sym not in (None, False):
                 return self._solve_global_smatrix_blocks()
-            # a later layer broke the symmetry: bring the block layers back to the original basis
-            basis = self._sym_basis_of_blocks
-            self._layers = [[basis.unproject({c: v[0] for c, v in l.blocks.items()}), basis.unproject({c: v[1] for c, v in l.blocks.items()})]
-                            if isinstance(l, _BlockLayer) else l for l in self._layers]
+            self._dense_layers()            # a later layer broke the symmetry
         if self.layer_N > 0:
             s11, s21 = self._layers[0]
             S = [s11, s21, s21, s11]
@@ -709,12 +711,10 @@ class rcwa:
         self.C = [[], []]
         self._modes_ready = False
 
-    @property
-    def _sym_basis_of_blocks(self):
-        for l in self._layers:
-            if isinstance(l, _BlockLayer):
-                return l.basis
-        return None
+    def _dense_layers(self):
+        """bring layers held as symmetry blocks back to the original basis (the stack is not cascaded in blocks after all)"""
+        self._layers = [[l.basis.unproject({c: v[k] for c, v in l.blocks.items()}) for k in range(2)] if isinstance(l, _BlockLayer) else l
+                        for l in self._layers]
 
     def _check_status(self):
         """Numerical status of everything enqueued so far: ONE device-to-host read of the per-matrix info words
