@@ -147,7 +147,7 @@ def test_symmetry_follows_the_illumination_and_rectangular_truncations(cpu_doubl
     """A doubly mirror-symmetric cell: normal incidence keeps both mirrors, incidence in the xz plane (ky0 = 0) only the
     mirror in y, in the yz plane only the mirror in x, a skew azimuth none; rectangular truncations (ox != oy).  Whatever
     is used, the result equals the general path."""
-    case = dict(C.CASES["ex1_o3"], order=order, inc=inc, azi=azi)
+    case = dict(C.CASES["ex1_o3"], order=order, inc=inc, azi=azi, eps_out=2.1)          # with an output half space (Sout on the right)
     mk = lambda sym: C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, symmetry_reduction=sym, **kw), case, torch.complex128)
     a, b = mk(None), mk(False)
     found = a._sym.gens if a._sym not in (None, False) else None
@@ -155,6 +155,54 @@ def test_symmetry_follows_the_illumination_and_rectangular_truncations(cpu_doubl
     for k in range(4):
         assert relfro(a.S[k].numpy(), b.S[k].numpy()) <= 1e-11
     assert np.abs(C.probe(a) - C.probe(b)).max() <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["ex1_o3", "c2_o3", "ymirror_o3", "offcentre_o3", "square_o4"])
+def test_half_spaces_are_pair_sparse_in_the_adapted_basis(cpu_double, name, monkeypatch):
+    """Every half-space block, projected, is a diagonal plus one partner entry per row (also with an off-centre cell, where the
+    basis carries translation phases): the cheap star products are the ones that run, and PairSparse reproduces the block."""
+    from torcwa_b200 import symmetry
+    seen = []
+    real = symmetry.PairSparse.from_dense
+
+    def spy(M, tol=1e-12):
+        out = real(M, tol)
+        seen.append((M, out))
+        return out
+    monkeypatch.setattr(symmetry.PairSparse, "from_dense", staticmethod(spy))
+    sim = C.run_case(lambda **kw: cpu_double.rcwa(device=CPU, **kw), C.CASES[name], torch.complex128)
+    assert sim._sym not in (None, False) and len(seen) in (4 * len(sim._sym.chars), 8 * len(sim._sym.chars))      # Sin, or Sin and Sout
+    eye = None
+    for M, sp in seen:
+        assert sp is not None
+        eye = torch.eye(M.shape[1], dtype=M.dtype).expand(M.shape[0], -1, -1)
+        assert float((sp.left(eye) - M).abs().max()) <= 1e-12 * float(M.abs().max())
+        assert float((sp.right(eye) - M).abs().max()) <= 1e-12 * float(M.abs().max())
+        assert float((sp.add_to(torch.zeros_like(M)) - M).abs().max()) <= 1e-12 * float(M.abs().max())
+
+
+def test_pair_sparse_star_products_equal_the_dense_routine(cpu_double):
+    import fake_lib
+    from torcwa_b200 import symmetry
+    g = torch.Generator().manual_seed(3)
+    n, B = 14, 2
+    rnd = lambda *s: torch.complex(torch.randn(*s, generator=g, dtype=torch.float64), torch.randn(*s, generator=g, dtype=torch.float64))
+    p = torch.tensor([1, 0, 2, 5, 6, 3, 4, 7, 9, 8, 13, 12, 11, 10])          # an involution with fixed points 2 and 7
+
+    def sparse_dense():
+        M = torch.diag_embed(rnd(B, n))
+        o = rnd(B, n) * (p != torch.arange(n))
+        M[:, torch.arange(n), p] += o
+        return M
+    half = [0.3 * sparse_dense() for _ in range(4)]
+    S = [0.3 * rnd(B, n, n) for _ in range(4)]
+    sp = [symmetry.PairSparse.from_dense(h) for h in half]
+    assert all(x is not None for x in sp)
+    for got, want in ((symmetry.redheffer_sparse_left(fake_lib, sp, S)[0], fake_lib.redheffer(half, S)[0]),
+                      (symmetry.redheffer_sparse_right(fake_lib, S, sp)[0], fake_lib.redheffer(S, half)[0])):
+        for k in range(4):
+            assert relfro(got[k].numpy(), want[k].numpy()) <= 1e-13
+    assert symmetry.PairSparse.from_dense(S[0]) is None                         # a dense matrix is not mistaken for one
 
 
 def test_unanalysed_layers_send_the_stack_to_the_general_path(cpu_double):

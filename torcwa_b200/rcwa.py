@@ -697,10 +697,10 @@ class rcwa:
                 S, info_r = _lib.redheffer(S, part(self._layers[i]), slices=self._digits)
                 self._status.append(('star product with layer %d (block %s)' % (i, chi), info_r))
             if hasattr(self, 'Sin'):
-                S, info_r = _lib.redheffer([self._proj(basis, s, chi) for s in Sin_d], S, slices=self._digits)
+                S, info_r = self._half_space_product(basis, chi, Sin_d, S, left=True)
                 self._status.append(('star product with the input half space (block %s)' % (chi,), info_r))
             if hasattr(self, 'Sout'):
-                S, info_r = _lib.redheffer(S, [self._proj(basis, s, chi) for s in Sout_d], slices=self._digits)
+                S, info_r = self._half_space_product(basis, chi, Sout_d, S, left=False)
                 self._status.append(('star product with the output half space (block %s)' % (chi,), info_r))
             Sblocks[chi] = S
         del Sin_d, Sout_d
@@ -710,6 +710,19 @@ class rcwa:
         self.S = self._S.view(self)
         self.C = [[], []]
         self._modes_ready = False
+
+    def _half_space_product(self, basis, chi, half, S, left):
+        """half (x) S or S (x) half in block chi.  A half-space block is four diagonals, i.e. a diagonal plus one partner entry
+        per row in the adapted basis (symmetry.PairSparse): six (left) or four (right) of the eight dense products of the
+        star product become row / column combinations.  Falls back to the dense routine if the pattern is not found."""
+        blocks = [self._proj(basis, s, chi) for s in half]
+        sparse = [symmetry.PairSparse.from_dense(b) for b in blocks]
+        if any(x is None for x in sparse):
+            return _lib.redheffer(blocks, S, slices=self._digits) if left else _lib.redheffer(S, blocks, slices=self._digits)
+        del blocks
+        if left:
+            return symmetry.redheffer_sparse_left(_lib, sparse, S)
+        return symmetry.redheffer_sparse_right(_lib, S, sparse)
 
     def _dense_layers(self):
         """bring layers held as symmetry blocks back to the original basis (the stack is not cascaded in blocks after all)"""
