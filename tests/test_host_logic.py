@@ -174,7 +174,7 @@ def test_half_spaces_are_pair_sparse_in_the_adapted_basis(cpu_double, name, monk
     assert sim._sym not in (None, False) and len(seen) in (4 * len(sim._sym.chars), 8 * len(sim._sym.chars))      # Sin, or Sin and Sout
     eye = None
     for M, sp in seen:
-        assert sp is not None
+        assert bool(sp.ok)
         eye = torch.eye(M.shape[1], dtype=M.dtype).expand(M.shape[0], -1, -1)
         assert float((sp.left(eye) - M).abs().max()) <= 1e-12 * float(M.abs().max())
         assert float((sp.right(eye) - M).abs().max()) <= 1e-12 * float(M.abs().max())
@@ -197,12 +197,12 @@ def test_pair_sparse_star_products_equal_the_dense_routine(cpu_double):
     half = [0.3 * sparse_dense() for _ in range(4)]
     S = [0.3 * rnd(B, n, n) for _ in range(4)]
     sp = [symmetry.PairSparse.from_dense(h) for h in half]
-    assert all(x is not None for x in sp)
+    assert all(bool(x.ok) for x in sp)
     for got, want in ((symmetry.redheffer_sparse_left(fake_lib, sp, S)[0], fake_lib.redheffer(half, S)[0]),
                       (symmetry.redheffer_sparse_right(fake_lib, S, sp)[0], fake_lib.redheffer(S, half)[0])):
         for k in range(4):
             assert relfro(got[k].numpy(), want[k].numpy()) <= 1e-13
-    assert symmetry.PairSparse.from_dense(S[0]) is None                         # a dense matrix is not mistaken for one
+    assert not bool(symmetry.PairSparse.from_dense(S[0]).ok)                         # a dense matrix is not mistaken for one
 
 
 def test_unanalysed_layers_send_the_stack_to_the_general_path(cpu_double):

@@ -717,7 +717,7 @@ class rcwa:
         star product become row / column combinations.  Falls back to the dense routine if the pattern is not found."""
         blocks = [self._proj(basis, s, chi) for s in half]
         sparse = [symmetry.PairSparse.from_dense(b) for b in blocks]
-        if any(x is None for x in sparse):
+        if not bool(torch.stack([x.ok for x in sparse]).all()):            # one host read for the four blocks
             return _lib.redheffer(blocks, S, slices=self._digits) if left else _lib.redheffer(S, blocks, slices=self._digits)
         del blocks
         if left:
