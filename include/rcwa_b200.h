@@ -109,7 +109,8 @@ int rcwa_tc_issue_entry(int slices, int levels, int group, int ring_pos, int ste
  *   S-matrix stage on the tcgen05 engine too when gemm_slices >= 2 (default 0: measured slower at K = 512); 13: QR pass
  *   as two launches per iteration -- bulge-chase windows, then the small dense solves at two CTAs per SM (0 = automatic:
  *   batches above 296 matrices, 1 = never, 2 = always); 14 = 2: replay the QR loop from CUDA graphs of 8 iterations per
- *   matrix group (default off: measured no gain at the default group count).  Call before
+ *   matrix group (default off: measured no gain at the default group count); 15: aggressive-early-deflation window of the QR
+ *   phase (0 = automatic: 24 for n <= 1024, else 32).  Call before
  *   asking for workspace sizes and enqueuing work; the numerical contract does not depend on them. */
 int rcwa_zgemm_batched_cfg(int cfg, int opa, int opb, int M, int N, int K, double alpha_re, double alpha_im,
                            const void* A, int lda, long long stride_a, const void* B, int ldb, long long stride_b,

@@ -49,6 +49,7 @@ struct QrBudget {
     int swaps;      // eigenvalue swaps per launch during the AED deflation scan
     int restore;    // Householder steps per launch while folding the AED spike back to Hessenberg form
     long long cycles;   // SM-clock budget of a serial slice (0: count budgets only); the counts above are upper bounds
+    int aed_w;          // aggressive-early-deflation window of this call (<= QR_AED_W, the size the buffers are laid out for)
 };
 #define QR_BUDGET_SCHUR 4000
 #define QR_BUDGET_SWAPS 300
@@ -66,6 +67,9 @@ DEV bool slice_expired(const Cta& c, long long deadline) {
     return e != 0;
 #endif
 }
+#define QR_AED_W_SMALL 24   // AED window for matrices up to QR_AED_SMALL_N ...
+#define QR_AED_W_LARGE 32   // ... and above (the buffers are laid out for QR_AED_W = 48, the largest allowed)
+#define QR_AED_SMALL_N 1024
 #define QR_MODE_ALL 0
 #define QR_MODE_WIN 1
 #define QR_MODE_SMALL 2
@@ -666,7 +670,8 @@ DEV void qr_pass_body(const Cta& c, cplx* H, int ldh, int n, cplx* Zm, int ldz, 
                     st.phase = 2; st.p = lo; st.ss_i = hi - lo; st.ss_its = 0; st.ss_fresh = 1; st.small_solves++;
                 } else if (!st.aed_off) {
                     // aggressive early deflation on the trailing window before (or instead of) a sweep
-                    const int nw = (QR_AED_W < hi - lo) ? QR_AED_W : hi - lo;     // spike entry H[kw][kw-1] stays inside the block
+                    const int aw = (bud.aed_w > 0 && bud.aed_w < QR_AED_W) ? bud.aed_w : QR_AED_W;
+                    const int nw = (aw < hi - lo) ? aw : hi - lo;     // spike entry H[kw][kw-1] stays inside the block
                     st.phase = 3; st.aed_stage = 0; st.aed_nw = nw; st.aed_kw = hi - nw + 1; st.ss_i = nw - 1; st.ss_its = 0; st.ss_fresh = 1; st.aeds++;
                 } else {
                     st.ns = QR_NS; st.nintro = 0; st.nbulge = 0; st.p = lo; st.phase = 1; st.sweeps++; st.shifts_ready = 0;
@@ -1068,7 +1073,7 @@ extern "C" int emu_qr(cplx* H, cplx* Z, int n, int max_passes, int* stats) {
     ZGemmProblem pr, pcm, pc, pz;
     int it = 0;
     for (; it < max_passes && !st.done; ++it) {
-        QrBudget bud; bud.schur = 160; bud.swaps = 100; bud.restore = 12; bud.cycles = 0;     // count budgets exercise the slicing on the CPU
+        QrBudget bud; bud.schur = 160; bud.swaps = 100; bud.restore = 12; bud.cycles = 0; bud.aed_w = 0;     // count budgets exercise the slicing on the CPU
         qr_pass_body(c, H, n, n, Z, n, &st, U.data(), Vgbuf.data(), Tgbuf.data(), &pr, &pcm, &pc, &pz, bud);
         emu_gemm(pr, 2); emu_gemm(pcm, 0); emu_gemm(pc, 0); emu_gemm(pz, 0);
     }
@@ -1385,6 +1390,12 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
     bud.schur = gemm_get_tuning(5) > 0 ? gemm_get_tuning(5) : QR_BUDGET_SCHUR;
     bud.swaps = gemm_get_tuning(6) > 0 ? gemm_get_tuning(6) : QR_BUDGET_SWAPS;
     bud.restore = gemm_get_tuning(7) > 0 ? gemm_get_tuning(7) : QR_BUDGET_RESTORE;
+    // AED window: the Schur factorisation of the window costs O(w^3) serial work per AED, and on small matrices that is what
+    // the pass kernel spends its time on.  Measured (profiles/r2_summary.md): 512 matrices of n = 481 -- eig 872 ms at w = 48,
+    // 790 at 40, 700 at 32, 662 at 28, 651 at 24 (sweeps per matrix 26.6 -> 33.7); 64 matrices of n = 1922 -- step 4.14 s at 48,
+    // 4.00 at 40, 3.91 at 32.
+    bud.aed_w = gemm_get_tuning(15) > 0 ? gemm_get_tuning(15) : ((n <= QR_AED_SMALL_N) ? QR_AED_W_SMALL : QR_AED_W_LARGE);
+    if (bud.aed_w < 8) bud.aed_w = 8;
     {
         int dev = 0, khz = 0;
         cudaGetDevice(&dev);

@@ -362,6 +362,7 @@ static int g_tune[16] = {1, GEMM_TILE_64x64, GEMM_TILE_64x64, 1, 0, 0, 0, 0, 0, 
 //      exceeds two waves of SMs, 1 = never, 2 = always)
 //  14: 2 = replay the QR loop of a group from a CUDA graph of 8 iterations instead of enqueuing every launch (default off:
 //      measured no gain with the default group count, eig.cu)
+//  15: AED window of the QR phase (0 = automatic: 24 for n <= 1024, else 32; at most 48)
 void gemm_set_tuning(int key, int value) { if (key >= 0 && key < 16) g_tune[key] = value; }
 int gemm_get_tuning(int key) { return (key >= 0 && key < 16) ? g_tune[key] : 0; }
 
