@@ -193,8 +193,8 @@ int rcwa_eig_backward(const void* lam, const void* X, const void* glam, const vo
  * Minimal algebra: V = Q W Kz^-1, two LU right-solves; replaces
  * rcwa._solve_layer_smatrix, rcwa.py:1244-1281 (dense inv of the 4N x 4N coupling matrix).
  * gemm_slices (here and in the star products): 0 = every dense product on the fp64 tensor pipe (DMMA; the complex128
- * contract); 2..8 = the n x n x n products and the K = 512 block updates of the triangular solves run on the tcgen05
- * int8-digit GEMM with that many digits (see rcwa_zgemm_tc_batched; the Python host uses 7 for complex64 simulations:
+ * contract); 2..8 = the n x n x n products (and, with tuning key 12, the K = 512 block updates of the triangular solves) run
+ * on the tcgen05 int8-digit GEMM with that many digits when n >= 768 -- below that the DMMA kernel is faster and is used (see rcwa_zgemm_tc_batched; the Python host uses 7 for complex64 simulations:
  * the stage amplifies a product's error by up to ~1e6 into the far-evanescent S-block entries).  The
  * workspace size depends on it. */
 size_t rcwa_layer_smatrix_workspace_bytes(int N, int nb, int gemm_slices);

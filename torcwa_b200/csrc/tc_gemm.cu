@@ -665,8 +665,11 @@ size_t tc_ctx_bytes(int n, int nb, int slices) {
 cudaError_t gemm_auto(const TcCtx* tc, int opa, int opb, int M, int N, int K, double alpha, const cplx* A, int lda, long long sa,
                       const cplx* B, int ldb, long long sb, cplx beta, cplx* Cm, int ldc, long long sc, int batch,
                       ZGemmProblem* gscratch, cudaStream_t st) {
-    // the digit path pays a split of both operands (~O(MK + KN) bytes each way): only for products with enough work per element
-    const bool big = M >= 256 && N >= 128 && K >= 256;
+    // the digit path pays a split of both operands (~O(MK + KN) bytes each way) and an epilogue of three read-modify-write passes
+    // over C: only for products with enough work per element.  Measured at 7 digits, split included: 71 TF/s-equivalent at
+    // M = N = K = 1922 (DMMA 38), but 24 at 481 (DMMA ~30: the symmetry blocks of order 15), and K = 512 block updates were
+    // slower than DMMA too (profiles/r2_summary.md sections 3 and 6) -- hence the K threshold.
+    const bool big = M >= 256 && N >= 128 && K >= 768;
     if (tc && tc->slices >= 2 && big && tc_supported(tc->slices, M, N, K) && tc->ws_bytes >= tc_workspace_min_bytes(M, N, K, tc->slices))
         return tc_zgemm_strided(tc->slices, opa, opb, M, N, K, alpha, A, lda, sa, B, ldb, sb, beta, Cm, ldc, sc, batch, tc->ws, tc->ws_bytes, st);
     return zgemm_strided(opa, opb, M, N, K, C(alpha, 0.0), A, lda, sa, B, ldb, sb, beta, Cm, ldc, sc, batch, gscratch, st);
