@@ -1434,6 +1434,7 @@ cudaError_t eig(cplx* A, int n, int nb, cplx* wout, cplx* V, char* wsb, size_t w
     const size_t smem_small = qr_pass_smem_bytes(n, QR_MODE_SMALL);
     const bool split = (gemm_get_tuning(13) == 2) || (gemm_get_tuning(13) == 0 && nb > 2 * QR_SMS);
     int G = gemm_get_tuning(9) > 0 ? gemm_get_tuning(9) : ((nb > 2 * QR_SMS) ? (nb + QR_SMS - 1) / QR_SMS : 2);
+    if (gemm_get_tuning(9) <= 0 && G > 4) G = 4;          // more directly enqueued groups are host-bound (measured, see the graph note below)
     if (G > QR_MAXG) G = QR_MAXG;
     while (G > 1 && nb < 8 * G) --G;
     // Internal streams and events are created ONCE per host thread and device and reused by later calls (thread-local
