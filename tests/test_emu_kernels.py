@@ -72,6 +72,32 @@ def test_qr_and_eigenvectors_random(emu, n):
     assert np.abs(A @ V - V * w).max() < 1e-11 * n
 
 
+@pytest.mark.parametrize("n", [49, 97, 130, 200])
+@pytest.mark.parametrize("aed_w", [0, 32, 24, 16])
+def test_qr_two_launch_mode_and_aed_windows(emu, n, aed_w):
+    """The large-batch device path runs every iteration as two launches (bulge-chase windows, then the small dense solves on
+    48-row buffers) and picks the AED window by matrix size.  Per matrix the two-launch mode does exactly the same arithmetic
+    as the single launch: bit-identical T and Z; every AED window gives a valid Schur decomposition."""
+    rng = np.random.default_rng(4000 + n)
+    A = crand(rng, n, n)
+    H0, Z0 = sl.hessenberg(A, calc_q=True)
+    out = []
+    for split in (0, 1):
+        H, Z = np.ascontiguousarray(H0.copy()), np.ascontiguousarray(Z0.copy())
+        stats = np.zeros(8, np.int32)
+        info = emu.emu_qr_opts(P(H), P(Z), n, 10 ** 6, P(stats), split, aed_w)
+        assert info == 0
+        out.append((H, Z, stats.copy()))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert out[0][2][0] == out[1][2][0] and out[0][2][4] == out[1][2][4]          # same sweeps and AEDs
+    T, Z = np.triu(out[1][0]), out[1][1]
+    assert np.abs(np.tril(out[1][0], -1)).max() == 0.0
+    assert np.abs(Z @ T @ Z.conj().T - A).max() < 1e-12 * n
+    assert np.abs(Z.conj().T @ Z - np.eye(n)).max() < 1e-12 * n
+    w_ref = np.linalg.eigvals(A)
+    assert max(np.abs(w_ref - x).min() for x in np.diag(T)) < 1e-10 * np.abs(w_ref).max()
+
+
 def test_qr_on_rcwa_matrix_and_degenerate_cell(emu):
     for name in ("ex1_o3", "square_o4"):
         case = C.CASES[name]

@@ -1054,7 +1054,11 @@ static void emu_gemm(const ZGemmProblem& g, int opa) {
 }
 
 // H (upper Hessenberg, n x n) -> T in place, Z <- Z U.  Returns info; stats[0..2] = sweeps, passes, done.
-extern "C" int emu_qr(cplx* H, cplx* Z, int n, int max_passes, int* stats) {
+// split != 0: every iteration as the two launches of the large-batch device path (QR_MODE_WIN, then QR_MODE_SMALL);
+// aed_w: AED window (0 = the compile-time maximum)
+extern "C" int emu_qr_opts(cplx* H, cplx* Z, int n, int max_passes, int* stats, int split, int aed_w);
+extern "C" int emu_qr(cplx* H, cplx* Z, int n, int max_passes, int* stats) { return emu_qr_opts(H, Z, n, max_passes, stats, 0, 0); }
+extern "C" int emu_qr_opts(cplx* H, cplx* Z, int n, int max_passes, int* stats, int split, int aed_w) {
     std::vector<char> smem(qr_pass_smem_bytes(n));
     std::vector<cplx> U((size_t)QR_W * QR_W), Tgbuf((size_t)QR_W * QR_W), Vgbuf((size_t)QR_W * QR_W);
     // the QR phase keeps H current only inside active blocks; the caller's Z holds the Hessenberg
@@ -1073,8 +1077,12 @@ extern "C" int emu_qr(cplx* H, cplx* Z, int n, int max_passes, int* stats) {
     ZGemmProblem pr, pcm, pc, pz;
     int it = 0;
     for (; it < max_passes && !st.done; ++it) {
-        QrBudget bud; bud.schur = 160; bud.swaps = 100; bud.restore = 12; bud.cycles = 0; bud.aed_w = 0;     // count budgets exercise the slicing on the CPU
-        qr_pass_body(c, H, n, n, Z, n, &st, U.data(), Vgbuf.data(), Tgbuf.data(), &pr, &pcm, &pc, &pz, bud);
+        QrBudget bud; bud.schur = 160; bud.swaps = 100; bud.restore = 12; bud.cycles = 0; bud.aed_w = aed_w;     // count budgets exercise the slicing on the CPU
+        if (!split) qr_pass_body(c, H, n, n, Z, n, &st, U.data(), Vgbuf.data(), Tgbuf.data(), &pr, &pcm, &pc, &pz, bud);
+        else {
+            qr_pass_body(c, H, n, n, Z, n, &st, U.data(), Vgbuf.data(), Tgbuf.data(), &pr, &pcm, &pc, &pz, bud, QR_MODE_WIN);
+            qr_pass_body(c, H, n, n, Z, n, &st, U.data(), Vgbuf.data(), Tgbuf.data(), &pr, &pcm, &pc, &pz, bud, QR_MODE_SMALL);
+        }
         emu_gemm(pr, 2); emu_gemm(pcm, 0); emu_gemm(pc, 0); emu_gemm(pz, 0);
     }
     {   // T = Z^H A0 Z (as the device path does); strictly lower part set to exact zero
