@@ -694,13 +694,17 @@ class rcwa:
                 return [a, b, b, a]
             S = part(self._layers[0])
             for i in range(1, self.layer_N):
-                S, info_r = _lib.redheffer(S, part(self._layers[i]), slices=self._digits)
+                nxt = part(self._layers[i])
+                if isinstance(self._layers[i], _BlockLayer):
+                    S, info_r = _lib.redheffer(S, nxt, slices=self._digits)
+                else:       # a homogeneous layer: four diagonals in the original basis, like a half space
+                    S, info_r = self._four_diagonal_product(nxt, S, left=False)
                 self._status.append(('star product with layer %d (block %s)' % (i, chi), info_r))
             if hasattr(self, 'Sin'):
-                S, info_r = self._half_space_product(basis, chi, Sin_d, S, left=True)
+                S, info_r = self._four_diagonal_product([self._proj(basis, s, chi) for s in Sin_d], S, left=True)
                 self._status.append(('star product with the input half space (block %s)' % (chi,), info_r))
             if hasattr(self, 'Sout'):
-                S, info_r = self._half_space_product(basis, chi, Sout_d, S, left=False)
+                S, info_r = self._four_diagonal_product([self._proj(basis, s, chi) for s in Sout_d], S, left=False)
                 self._status.append(('star product with the output half space (block %s)' % (chi,), info_r))
             Sblocks[chi] = S
         del Sin_d, Sout_d
@@ -711,15 +715,18 @@ class rcwa:
         self.C = [[], []]
         self._modes_ready = False
 
-    def _half_space_product(self, basis, chi, half, S, left):
-        """half (x) S or S (x) half in block chi.  A half-space block is four diagonals, i.e. a diagonal plus one partner entry
-        per row in the adapted basis (symmetry.PairSparse): six (left) or four (right) of the eight dense products of the
-        star product become row / column combinations.  Falls back to the dense routine if the pattern is not found."""
-        blocks = [self._proj(basis, s, chi) for s in half]
-        sparse = [symmetry.PairSparse.from_dense(b) for b in blocks]
-        if not bool(torch.stack([x.ok for x in sparse]).all()):            # one host read for the four blocks
+    def _four_diagonal_product(self, blocks, S, left):
+        """blocks (x) S (left) or S (x) blocks, where `blocks` are the projections of four-diagonal matrices (a half space, a
+        homogeneous layer): a diagonal plus one partner entry per row in the adapted basis (symmetry.PairSparse), so six
+        (left) or four (right) of the eight dense products of the star product become row / column combinations.  Falls back
+        to the dense routine if the pattern is not found."""
+        uniq = {}
+        for b in blocks:                                     # a layer passes [S11, S21, S21, S11]: analyse each tensor once
+            if id(b) not in uniq:
+                uniq[id(b)] = symmetry.PairSparse.from_dense(b)
+        if not bool(torch.stack([x.ok for x in uniq.values()]).all()):            # one host read for all blocks
             return _lib.redheffer(blocks, S, slices=self._digits) if left else _lib.redheffer(S, blocks, slices=self._digits)
-        del blocks
+        sparse = [uniq[id(b)] for b in blocks]
         if left:
             return symmetry.redheffer_sparse_left(_lib, sparse, S)
         return symmetry.redheffer_sparse_right(_lib, S, sparse)
