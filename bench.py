@@ -362,7 +362,12 @@ def bench_b200(args):
         out = {
             "metric": "layers/sec (order %dx%d, c64)" % (args.order, args.order), "value": value, "unit": "layers/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64 eigensolver and solves; the S-matrix stage's dense products on tcgen05 int8 digits (7 x 8 bit, fp64-grade) behind the complex64 API; results rounded to c64",
+            "vs_baseline": None,
+            "dtype": ("f64 behind the complex64 API (results rounded to c64): eigensolver, solves and the dense products of the %s-size symmetry blocks on the fp64 "
+                      "pipes (DMMA); the tcgen05 int8-digit GEMM (7 x 8 bit, fp64-grade) takes the dense products of the S-matrix stage only for K >= 768, "
+                      "i.e. on the general path (general_path, roofline_tensor.tcgen05)" % "/".join(str(b) for b in sorted(set(sym_probe["block_sizes"]))))
+                     if sym_probe and "block_sizes" in sym_probe else
+                     "f64 eigensolver and solves; the S-matrix stage's dense products on tcgen05 int8 digits (7 x 8 bit, fp64-grade) behind the complex64 API; results rounded to c64",
             "data": "synthetic (Example1 cell, linear a-Si:H dispersion, 512 wavelengths 400-700 nm)",
             "config": {"workload": "BASELINE configs[1]: order %dx%d (n=%d), 1 patterned layer + SiO2 half space, 512-wavelength sweep, complex64 API"
                                    % (args.order, args.order, n), "points_per_step_per_gpu": P, "layers_per_point": 1,
