@@ -230,6 +230,31 @@ def test_pair_sparse_star_products_equal_the_dense_routine(cpu_double):
     assert not bool(symmetry.PairSparse.from_dense(S[0]).ok)                         # a dense matrix is not mistaken for one
 
 
+@pytest.mark.parametrize("bump,expect", [(0.0, ("x", "y")), (1e-7, None), (1e-3, None)])
+def test_nearly_symmetric_cells_are_not_reduced(cpu_double, bump, expect):
+    """The symmetry must hold to 1e-11 of the largest Fourier coefficient to be used: a cell that is symmetric only to 1e-7
+    would otherwise pick up an error of that order, far above the 1e-10 parity gate.  Either way the result equals the
+    general path."""
+    case = C.CASES["ex1_o3"]
+    cd = torch.complex128
+    d0, grid0 = C.build_layers(case, cd)[0]
+    grid = grid0.clone()
+    grid[40:60, 200:230] += bump                      # an off-centre patch: breaks both mirrors and C2
+
+    def run(sym):
+        sim = cpu_double.rcwa(freq=torch.tensor(1.0 / case["lam"], dtype=torch.float64), order=case["order"], L=case["L"], dtype=cd, device=CPU,
+                              symmetry_reduction=sym)
+        sim.add_input_layer(eps=case["eps_in"])
+        sim.set_incident_angle(0.0, 0.0)
+        sim.add_layer(thickness=d0, eps=grid)
+        sim.solve_global_smatrix()
+        return sim
+    a, b = run(None), run(False)
+    assert (a._sym.gens if a._sym not in (None, False) else None) == expect
+    for k in range(4):
+        assert relfro(a.S[k].numpy(), b.S[k].numpy()) <= 1e-11
+
+
 def test_unanalysed_layers_send_the_stack_to_the_general_path(cpu_double):
     """A symmetric patterned layer (solved in blocks) followed by (a) a layer with patterned permeability, (b) a layer on the
     differentiable pipeline: neither is analysed for symmetry, so the stack is cascaded in the original basis -- same
