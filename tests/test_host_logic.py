@@ -255,6 +255,46 @@ def test_nearly_symmetric_cells_are_not_reduced(cpu_double, bump, expect):
         assert relfro(a.S[k].numpy(), b.S[k].numpy()) <= 1e-11
 
 
+@pytest.mark.parametrize("batched", [False, True])
+def test_fields_and_resolve_after_a_symmetry_reduced_solve(cpu_double, batched):
+    """Solve, add layers, solve again, then ask for fields: the mode coefficients are carried in the original basis from the
+    unprojected block layers, the global S-matrix densifies on demand.  Everything equals the general path."""
+    import sys
+    import torcwa_b200.fields as F
+    F._lib = sys.modules["fake_lib"]
+    try:
+        case = C.CASES["ex1_o3"]
+        cd = torch.complex128
+        d0, grid0 = C.build_layers(case, cd)[0]
+        x = torch.linspace(0, 300, 7, dtype=torch.float64)
+        z = torch.linspace(-50, 500, 9, dtype=torch.float64)
+
+        def run(sym):
+            lam = torch.tensor([case["lam"], 600.0], dtype=torch.float64) if batched else torch.tensor(case["lam"], dtype=torch.float64)
+            sim = cpu_double.rcwa(freq=1.0 / lam, order=case["order"], L=case["L"], dtype=cd, device=CPU, symmetry_reduction=sym,
+                                  **({"store_intermediates": True} if batched else {}))
+            sim.add_input_layer(eps=case["eps_in"])
+            sim.set_incident_angle(0.0, 0.0)
+            sim.add_layer(thickness=d0, eps=grid0)
+            sim.solve_global_smatrix()
+            out = [sim.S_parameters(orders=[0, 0], polarization="xx")]
+            sim.add_layer(thickness=70.0, eps=2.3)
+            sim.add_layer(thickness=50.0, eps=grid0 * 0.7 + 0.3)
+            sim.solve_global_smatrix()
+            out.append(sim.S_parameters(orders=[0, 0], polarization="yy"))
+            sim.source_planewave(amplitude=[1.0, 0.0], direction="forward")
+            (Ex, Ey, Ez), (Hx, Hy, Hz) = sim.field_xz(x, z, 150.0)
+            (Ex2, _, _), _ = sim.field_xy(0, x, x, z_prop=20.0)
+            return sim, out + [Ex, Ez, Hy, Ex2]
+        a, fa = run(None)
+        b, fb = run(False)
+        assert a._sym not in (None, False) and b._sym is None
+        for u, v in zip(fa, fb):
+            assert float((u - v).abs().max()) <= 1e-11 * max(float(v.abs().max()), 1.0)
+    finally:
+        F._lib = sys.modules["torcwa_b200._lib"]
+
+
 def test_unanalysed_layers_send_the_stack_to_the_general_path(cpu_double):
     """A symmetric patterned layer (solved in blocks) followed by (a) a layer with patterned permeability, (b) a layer on the
     differentiable pipeline: neither is analysed for symmetry, so the stack is cascaded in the original basis -- same

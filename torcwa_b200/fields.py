@@ -57,7 +57,7 @@ class _PointView:
         self._batched = False
         self._modes_ready = False
         self._modes_src = [{k: (v if v is None else v[b:b + 1]) for k, v in rec.items()} for rec in sim._modes_src]
-        self._layers = [[x[b:b + 1] for x in lay] for lay in sim._layers]
+        self._layers = [[x[b:b + 1] for x in lay] for lay in sim._layer_pairs_dense()]     # symmetry-block layers in the original basis
         self._S = [x[b:b + 1] for x in sim._S]
         if hasattr(sim, '_Sin'):
             self._Sin = [x[b:b + 1] for x in sim._Sin]
@@ -75,6 +75,9 @@ class _PointView:
 
     def _b(self, v):
         return self._sim._b(v)[self._pt:self._pt + 1]
+
+    def _layer_pairs_dense(self):
+        return self._layers                     # this point's slices (already in the original basis)
 
     def _pub(self, t):
         return t.to(self._sim._dtype)[0]
@@ -209,12 +212,13 @@ def ensure_modes(sim):
     sim.H_eigvec = [sim._pub(m[1][None]) for m in sim._modes]
     sim.Cf = [sim._pub(m[3][None]) for m in sim._modes]
     sim.Cb = [sim._pub(m[4][None]) for m in sim._modes]
+    layers = sim._layer_pairs_dense()       # the mode coefficients are carried in the original basis (symmetry blocks unprojected)
     if sim.layer_N > 0:
-        s11, s21 = (x[0] for x in sim._layers[0])
+        s11, s21 = (x[0] for x in layers[0])
         S = [s11, s21, s21, s11]
         C = [[sim._modes[0][3]], [sim._modes[0][4]]]
         for l in range(1, sim.layer_N):
-            n11, n21 = (x[0] for x in sim._layers[l])
+            n11, n21 = (x[0] for x in layers[l])
             S, C = _star_with_modes(S, [n11, n21, n21, n11], C, [[sim._modes[l][3]], [sim._modes[l][4]]])
     else:
         eye = torch.eye(n, dtype=_C, device=dev)

@@ -731,10 +731,22 @@ class rcwa:
             return symmetry.redheffer_sparse_left(_lib, sparse, S)
         return symmetry.redheffer_sparse_right(_lib, S, sparse)
 
+    def _layer_pairs_dense(self):
+        """[S11, S21] of every layer in the original basis (layers held as symmetry blocks are unprojected, O(n^2) each; cached
+        until the layer list changes -- the field code asks once per design point)"""
+        key = tuple(id(l.blocks) if isinstance(l, _BlockLayer) else id(l) for l in self._layers)
+        cached = getattr(self, '_pairs_cache', None)
+        if cached is None or cached[0] != key:
+            pairs = [[l.basis.unproject({c: v[k] for c, v in l.blocks.items()}) for k in range(2)] if isinstance(l, _BlockLayer) else l
+                     for l in self._layers]
+            if not any(isinstance(l, _BlockLayer) for l in self._layers):
+                return pairs                          # nothing was computed: nothing to cache
+            self._pairs_cache = (key, pairs, list(self._layers))      # the layer objects are kept alive so that the ids stay theirs
+        return self._pairs_cache[1]
+
     def _dense_layers(self):
         """bring layers held as symmetry blocks back to the original basis (the stack is not cascaded in blocks after all)"""
-        self._layers = [[l.basis.unproject({c: v[k] for c, v in l.blocks.items()}) for k in range(2)] if isinstance(l, _BlockLayer) else l
-                        for l in self._layers]
+        self._layers = self._layer_pairs_dense()
 
     def _check_status(self):
         """Numerical status of everything enqueued so far: ONE device-to-host read of the per-matrix info words
