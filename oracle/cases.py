@@ -77,6 +77,9 @@ CASES = {
                                          dict(kind="homogeneous", d=100.0, eps=SU8),
                                          _rect(theta=math.pi / 3, eps_in=SI_EPS[650.0], eps_bg=SU8, d=150.0)], lam=650.0, eps_out=2.1, full=True),
     "ymirror_o3": _base(order=[3, 2], layers=[_rect()], inc=0.35, azi=0.0, nxy=[96, 80], full=True),
+    # the other single mirror: incidence in the y-z plane keeps the x mirror; spacer layer and output half space on top
+    "xmirror_o3": _base(order=[2, 3], layers=[_rect(), dict(kind="homogeneous", d=80.0, eps=complex(2.0, 0.2)), _rect(Wx=120.0, Wy=200.0, d=150.0)],
+                        inc=0.3, azi=math.pi / 2, nxy=[80, 96], eps_out=2.1, full=True),
     "offcentre_o3": _base(order=[3, 3], layers=[dict(kind="rect", d=250.0, Wx=140.0, Wy=90.0, Cx=101.0, Cy=187.5, theta=0.0,
                                                      eps_in=SI_EPS[532.0], eps_bg=1.0)], full=True),
     # C4v-symmetric cell: exactly degenerate eigenpairs

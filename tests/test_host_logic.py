@@ -10,10 +10,10 @@ from fake_lib import cpu_double  # noqa: F401  (fixture)
 from oracle import cases as C
 from oracle.rcwa_oracle import OracleSim
 
-SMALL = ["ex1_o3", "ex1_o5", "stack_o3", "stack_o4x2", "fresnel_o2", "square_o4", "c2_o3", "ymirror_o3", "offcentre_o3"]
+SMALL = ["ex1_o3", "ex1_o5", "stack_o3", "stack_o4x2", "fresnel_o2", "square_o4", "c2_o3", "ymirror_o3", "xmirror_o3", "offcentre_o3"]
 # which symmetry the reduction (torcwa_b200/symmetry.py) must find in each case (None: general path)
 SYMMETRY = {"ex1_o3": ("x", "y"), "ex1_o5": ("x", "y"), "square_o4": ("x", "y"), "offcentre_o3": ("x", "y"), "c2_o3": ("c2",),
-            "ymirror_o3": ("y",), "stack_o3": None, "stack_o4x2": None, "fresnel_o2": None}
+            "ymirror_o3": ("y",), "xmirror_o3": ("x",), "stack_o3": None, "stack_o4x2": None, "fresnel_o2": None}
 CPU = torch.device("cpu")
 
 

@@ -11,7 +11,7 @@ import torch
 from oracle import cases as C
 from oracle.rcwa_oracle import OracleSim, PI_REF
 
-SMALL = ["ex1_o3", "ex1_o5", "stack_o3", "stack_o4x2", "fresnel_o2", "square_o4"]
+SMALL = ["ex1_o3", "ex1_o5", "stack_o3", "stack_o4x2", "fresnel_o2", "square_o4", "c2_o3", "ymirror_o3", "xmirror_o3", "offcentre_o3"]
 
 
 def oracle_factory(freq, order, L, dtype):
