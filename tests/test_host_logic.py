@@ -295,6 +295,63 @@ def test_fields_and_resolve_after_a_symmetry_reduced_solve(cpu_double, batched):
         F._lib = sys.modules["torcwa_b200._lib"]
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_random_symmetric_cells_equal_the_general_path(cpu_double, seed):
+    """Randomised cells built to have a given symmetry about a random centre (two mirrors, one mirror, or C2 only, from pairs of
+    tilted bars), random rectangular truncation, lossy materials, incidence chosen to keep or to break the symmetry, spacer
+    layer and output half space at random: whatever the detection decides, the result equals the general path, and when the
+    illumination allows it the expected group is found."""
+    import math
+    from oracle.cases import rectangle_grid
+    g = torch.Generator().manual_seed(9000 + seed)
+    u = lambda a, b: float(a + (b - a) * torch.rand((), generator=g))
+    L = [300.0, 360.0]
+    nxy = [90, 108]
+    px, py = L[0] / nxy[0], L[1] / nxy[1]
+    kind = ("xy", "x", "y", "c2")[seed % 4]
+    # centres on the half-pixel lattice: the sampled grid is then symmetric to round-off, like a designed cell
+    x0, y0 = 0.5 * px * round(u(130.0, 170.0) / (0.5 * px)), 0.5 * py * round(u(150.0, 210.0) / (0.5 * py))     # everything stays inside the cell
+    order = [int(torch.randint(1, 4, (), generator=g)), int(torch.randint(1, 4, (), generator=g))]
+    bar = lambda cx, cy, wx, wy, th: rectangle_grid(L[0], L[1], nxy[0], nxy[1], wx, wy, cx, cy, th, 1000.0, torch.float64)
+    wx, wy, dx, dy, th = u(30.0, 60.0), u(30.0, 60.0), u(10.0, 25.0), u(15.0, 35.0), u(0.2, 1.2)
+    if kind == "xy":
+        mask = bar(x0, y0, wx, wy, 0.0)
+    elif kind == "x":          # mirror x -> 2 x0 - x only: two bars at x0 -+ dx with opposite tilt, and a small bar off to one side in y
+        mask = torch.clamp(bar(x0 - dx - wx / 2, y0, wx, wy, th) + bar(x0 + dx + wx / 2, y0, wx, wy, -th) + bar(x0, y0 + 1.5 * dy + wy, 30.0, 20.0, 0.0), max=1.0)
+    elif kind == "y":
+        mask = torch.clamp(bar(x0, y0 - dy - wy / 2, wx, wy, th) + bar(x0, y0 + dy + wy / 2, wx, wy, -th) + bar(x0 + 1.5 * dx + wx, y0, 20.0, 30.0, 0.0), max=1.0)
+    else:                      # inversion centre only: one tilted bar
+        mask = bar(x0, y0, wx, wy, th)
+    eps = complex(u(6.0, 14.0), u(0.0, 0.8))
+    grid = (mask * eps + (1.0 - mask) * 1.0).to(torch.complex128)
+    keep = seed % 3 != 2       # every third trial breaks the symmetry with a skew incidence
+    inc = 0.0 if (kind in ("xy", "c2") and keep) else u(0.1, 0.5)
+    azi = (math.pi / 2 if kind == "x" else 0.0) if keep else u(0.3, 1.2)
+    if kind == "xy" and keep and seed % 8 == 4:
+        inc, azi = u(0.1, 0.5), 0.0                                  # incidence in the xz plane: only the y mirror survives
+    expect = None if not keep else {"xy": ("y",) if inc else ("x", "y"), "x": ("x",), "y": ("y",), "c2": ("c2",)}[kind]
+    d = 173.0 + 10.0 * seed
+    sims = []
+    for sym in (None, False):
+        sim = cpu_double.rcwa(freq=torch.tensor(1.0 / 560.0, dtype=torch.float64), order=order, L=L, dtype=torch.complex128, device=CPU,
+                              symmetry_reduction=sym)
+        sim.add_input_layer(eps=2.1)
+        if seed % 2:
+            sim.add_output_layer(eps=complex(1.8, 0.0))
+        sim.set_incident_angle(inc, azi)
+        sim.add_layer(thickness=d, eps=grid)
+        if seed % 3 == 1:
+            sim.add_layer(thickness=60.0, eps=complex(2.4, 0.1))
+            sim.add_layer(thickness=d * 0.5, eps=grid * 0.6 + 0.4)
+        sim.solve_global_smatrix()
+        sims.append(sim)
+    a, b = sims
+    found = a._sym.gens if a._sym not in (None, False) else None
+    assert found == expect, (kind, inc, azi, found, expect)
+    for k in range(4):
+        assert relfro(a.S[k].numpy(), b.S[k].numpy()) <= 1e-10
+
+
 def test_unanalysed_layers_send_the_stack_to_the_general_path(cpu_double):
     """A symmetric patterned layer (solved in blocks) followed by (a) a layer with patterned permeability, (b) a layer on the
     differentiable pipeline: neither is analysed for symmetry, so the stack is cascaded in the original basis -- same
