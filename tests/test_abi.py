@@ -33,6 +33,10 @@ def test_argument_checks_do_not_touch_the_gpu():
     assert lib.rcwa_eig(None, 4, 1, None, None, None, 0, None, None, None) == -1
     assert lib.rcwa_lu_factor(None, 0, 4, 4, 1, None, None, None, None, None, None) == -1
     assert lib.rcwa_eig_workspace_bytes(1922, 1) > 2 * 1922 * 1922 * 16
+    assert lib.rcwa_sym_project(None, 1, 8, None, None, None, None, 2, 4, 4, None, None) == -1
+    one = ctypes.c_void_p(16)          # a non-null placeholder: the checks return before anything is dereferenced
+    assert lib.rcwa_sym_project(one, 1, 8, one, one, one, one, 5, 4, 4, one, None) == -8      # G > 4
+    assert lib.rcwa_sym_project(one, 0, 8, one, one, one, one, 2, 4, 4, one, None) == -2
 
 
 def test_product_refuses_cpu_devices():
